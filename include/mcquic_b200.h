@@ -1,0 +1,136 @@
+/*
+ * mcquic_b200 -- C ABI of the B200-native McQuic hot path (analysis/synthesis convolutions + multi-codebook VQ).
+ *
+ * Every pointer is a DEVICE pointer owned by the caller (PyTorch tensors in the host-side mirror,
+ * mcquic_b200/); the library allocates nothing the caller can see, keeps no mutable global state and
+ * launches on the stream it is given.  Return value: 0 = ok, >0 = cudaError_t, <0 = library error
+ * (see mcq_error_string).  The Python wrapper raises RuntimeError on non-zero, like the reference
+ * does for bad shapes (mcquic/modules/entropyCoder.py:79-93).
+ *
+ * There is no FFI on the reference side for this path (it is eager PyTorch over cuDNN/cuBLAS,
+ * SURVEY.md section 2b); each entry point names the reference Python interface it replaces.
+ *
+ * Activation format ("split-fp16 planes"): an fp32 activation a is carried between convolutions as two
+ * fp16 NHWC planes  hi = fp16(a),  lo = fp16((a - hi) * 2048)   =>   a ~= hi + lo / 2048  (22+ bits).
+ * Convolutions run on tcgen05 tensor cores (kind::f16, fp32 accumulate in TMEM) either with 3 passes
+ * (hi*hi + (hi*lo + lo*hi)/2048: fp32-grade, used by encode so that code indices match the fp32
+ * reference) or 1 pass (hi*hi: TF32-grade, used by decode).  Tensors that are only ever consumed by an
+ * epilogue (residual identities, GDN operands, VQ inputs, pixels) stay fp32.
+ */
+#ifndef MCQUIC_B200_H_
+#define MCQUIC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mcq_stream_t; /* cudaStream_t */
+
+/* epilogue modes */
+enum {
+  MCQ_EPI_LINEAR = 0, /* y = conv + bias (+ res1_scale*res1) (+ res2)        ResidualBlock tail, blocks.py:62-78   */
+  MCQ_EPI_GATE   = 1, /* y = res1 + aux * sigmoid(conv + bias)               AttentionBlock tail, blocks.py:281-288 */
+  MCQ_EPI_GDN    = 2, /* y = aux * rsqrt(conv + bias)   (conv over aux^2)    GenDivNorm, gdn.py:67-86              */
+  MCQ_EPI_IGDN   = 3  /* y = aux *  sqrt(conv + bias)                        InvGenDivNorm, gdn.py:89-91           */
+};
+/* activation applied to y before it is written as a split-fp16 plane pair */
+enum { MCQ_ACT_NONE = 0, MCQ_ACT_SILU = 1, MCQ_ACT_SQUARE = 2 };
+/* output addressing */
+enum {
+  MCQ_STORE_NHWC         = 0, /* [n, hout, wout, cout]                                                       */
+  MCQ_STORE_SHUFFLE_NHWC = 1, /* PixelShuffle(2) folded into the store: GEMM column (2i+j)*C+c -> [n,2y+i,2x+j,c] (convs.py:244-255) */
+  MCQ_STORE_SHUFFLE_NCHW = 2  /* last layer: GEMM column 4c+2i+j -> fp32 NCHW [n, c, 2y+i, 2x+j] (compressor.py:139) */
+};
+/* kernel implementation */
+enum { MCQ_IMPL_TCGEN05 = 0, MCQ_IMPL_SIMT = 1 };
+
+typedef struct mcq_conv_params {
+  /* A operand: split-fp16 NHWC planes [n, hin, win, cin]; a_lo may be NULL when passes == 1 */
+  const void* a_hi;
+  const void* a_lo;
+  int32_t n, hin, win, cin;
+  /* B operand: packed weights [cout_pad, ksize*ksize*cin] fp16, K-major with K = (tap, cin); value = w * 2^w_exp */
+  const void* w_hi;
+  const void* w_lo;
+  int32_t cout;     /* real number of GEMM columns            */
+  int32_t cout_pad; /* rows of the packed weight matrix (multiple of the N tile) */
+  int32_t ksize;    /* 1 or 3 (padding = ksize / 2, zeros: convs.py:98-100)      */
+  int32_t stride;   /* 1 or 2                                                    */
+  float w_scale;    /* 2^-w_exp, applied to the accumulator                      */
+  const float* bias; /* [cout] indexed by GEMM column */
+  int32_t mode;     /* MCQ_EPI_*  */
+  int32_t store;    /* MCQ_STORE_* */
+  const float* res1; /* fp32, addressed like the output */
+  float res1_scale;
+  const float* res2;
+  const float* aux;
+  float* out_f32;   /* optional fp32 output */
+  void* out0_hi;    /* optional split-fp16 output #0 = act0(y) */
+  void* out0_lo;    /* may be NULL: only the hi plane is written (1-pass consumers) */
+  int32_t out0_act;
+  void* out1_hi;    /* optional split-fp16 output #1 = act1(y) */
+  void* out1_lo;
+  int32_t out1_act;
+  int32_t passes;   /* 1 or 3 */
+  int32_t impl;     /* MCQ_IMPL_* */
+} mcq_conv_params;
+
+/* Replaces nn.Conv2d 3x3 / 1x1 (+ the elementwise ops around it) as used by mcquic/nn/blocks.py:62-288,
+ * mcquic/nn/convs.py:77-100,221-276 and mcquic/nn/gdn.py:67-91. */
+int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream);
+
+/* First layer: conv3x3 stride 2, 3 -> cout, on the fp32 NCHW image, with AlignedPadding's reflect pad folded
+ * into the gather (mcquic/data/transforms.py:86-99, mcquic/modules/compressor.py:124).
+ * x: [n, 3, h, w] fp32; pad_top/pad_left: reflect padding already split as the reference does; hp, wp: padded size.
+ * w: [cout, 27] fp32 (cin, r, s order = nn.Conv2d layout), bias [cout]. Output grid is hp/2 x wp/2, NHWC. */
+int mcq_stem_conv(const float* x, int32_t n, int32_t h, int32_t w, int32_t pad_top, int32_t pad_left, int32_t hp,
+                  int32_t wp, const float* wgt, const float* bias, int32_t cout, float* out_f32, void* out_hi,
+                  void* out_lo, int32_t out_act, mcq_stream_t stream);
+
+/* Replaces _multiCodebookQuantization._distance + .encode (mcquic/modules/quantizer.py:144-179):
+ * code[n,m,h,w] = argmin_k (|x|^2 + |c_k|^2) - 2 x.c_k, first index on ties.
+ * x: fp32 NHWC [n,h,w,m*d] (channel = m_idx*d + d_idx); codebook [m,k,d]; c2 [m,k] = sum_d codebook^2.
+ * codes: int64 [n,m,h,w].  logits (optional): fp32 [n,m,h,w,k] = -(distance)/sqrt(k) * logit_scale[m]
+ * (quantizer.py:181-183,204; logit_scale = max(temperature, 1e-6), may be NULL = 1).
+ * hist (optional): int32 [m,k], incremented (not cleared) by the occurrence count of every code
+ * (the counting half of mcquic/modules/entropyCoder.py:28-36 / validate/handlers.py:138-172). */
+int mcq_vq_assign(const float* x, const float* codebook, const float* c2, int64_t* codes, float* logits,
+                  const float* logit_scale, int32_t* hist, int32_t n, int32_t h, int32_t w, int32_t m, int32_t k,
+                  int32_t d, mcq_stream_t stream);
+
+/* Replaces _multiCodebookDeQuantization.decode (mcquic/modules/quantizer.py:249-259): gather codebook[m, code].
+ * codes int64 [n,m,h,w] -> fp32 NHWC [n,h,w,m*d] and/or split-fp16 plane pairs (raw and/or act). Returns
+ * MCQ_ERR_CODE_RANGE via *status (device int32, optional) if a code is outside [0,k). */
+int mcq_vq_dequant(const int64_t* codes, const float* codebook, int32_t n, int32_t h, int32_t w, int32_t m, int32_t k,
+                   int32_t d, float* out_f32, void* out0_hi, void* out0_lo, int32_t out0_act, void* out1_hi,
+                   void* out1_lo, int32_t out1_act, int32_t* status, mcq_stream_t stream);
+
+/* Code histogram, int32 [m,k] += count (validate/handlers.py:138-172; entropyCoder.py:28-36). */
+int mcq_code_histogram(const int64_t* codes, int32_t n, int32_t m, int32_t hw, int32_t k, int32_t* hist,
+                       mcq_stream_t stream);
+
+/* fp32 [count] -> split-fp16 planes, act applied first (boundary helper; also NCHW->NHWC when c,h,w given). */
+int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, mcq_stream_t stream);
+int mcq_nchw_to_nhwc(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, float* out_f32, void* out0_hi,
+                     void* out0_lo, int32_t out0_act, void* out1_hi, void* out1_lo, int32_t out1_act,
+                     mcq_stream_t stream);
+int mcq_nhwc_to_nchw(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, float* out, mcq_stream_t stream);
+
+/* Introspection */
+const char* mcq_error_string(int code);
+int mcq_version(void);            /* ABI version */
+int mcq_device_error_flag(void);  /* last device-side watchdog code (0 = none); resets on read */
+int mcq_kernel_launch_count(void); /* number of kernels this library has launched in this process */
+
+#define MCQ_ERR_BAD_ARG (-1)
+#define MCQ_ERR_UNSUPPORTED (-2)
+#define MCQ_ERR_DRIVER (-3)
+#define MCQ_ERR_CODE_RANGE (-4)
+#define MCQ_ERR_WATCHDOG (-5)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCQUIC_B200_H_ */

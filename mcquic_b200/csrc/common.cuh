@@ -1,0 +1,170 @@
+// Shared device-side definitions: kernel parameter block, split-fp16 helpers, the fused epilogue.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mcquic_b200.h"
+
+namespace mcq {
+
+constexpr float kLoScale = 2048.0f;          // lo plane = (a - hi) * 2^11
+constexpr float kLoInv = 1.0f / 2048.0f;
+
+// Device view of one convolution launch (mcq_conv_params + derived geometry).
+struct ConvArgs {
+  const __half* a_hi;
+  const __half* a_lo;
+  const __half* w_hi;
+  const __half* w_lo;
+  const float* bias;
+  const float* res1;
+  const float* res2;
+  const float* aux;
+  float* out_f32;
+  __half* o0_hi;
+  __half* o0_lo;
+  __half* o1_hi;
+  __half* o1_lo;
+  float w_scale;
+  float res1_scale;
+  int n, hin, win, cin;
+  int hout, wout;  // conv output grid (before any pixel shuffle)
+  int cout, cout_pad, ksize, stride, ktotal;
+  int mode, store, o0_act, o1_act, passes;
+  // tensor-core tiling: a tile is a (tw x th x tn) box of output pixels (x fastest), tw*th*tn == 128
+  int tw, th, tn;
+  int tiles_x, tiles_y, tiles_n;  // tiles along W, H, N
+  int bn;                         // N tile (GEMM columns per CTA tile)
+  int tiles_c;                    // cout_pad / bn
+  int stages;
+  // per-tap TMA coordinate offsets in the 5-D view of A (see conv_tc.cuh)
+  int tap_c[9], tap_dx[9], tap_py[9], tap_dy[9];
+};
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float y, int act) {
+  if (act == MCQ_ACT_SILU) return silu_f(y);
+  if (act == MCQ_ACT_SQUARE) return y * y;
+  return y;
+}
+
+__device__ __forceinline__ unsigned short f2h_sat(float a) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float h2f(unsigned short h) { return __half2float(__ushort_as_half(h)); }
+
+// a ~= hi + lo / 2048, both fp16
+__device__ __forceinline__ void split_f32(float a, unsigned short& hi, unsigned short& lo) {
+  hi = f2h_sat(a);
+  lo = f2h_sat((a - h2f(hi)) * kLoScale);
+}
+
+template <int NV>
+__device__ __forceinline__ void store_planes(__half* hi_p, __half* lo_p, size_t off, const float (&y)[NV], int act) {
+  static_assert(NV == 4 || NV == 8, "NV");
+  unsigned short h[NV], l[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) split_f32(apply_act(y[j], act), h[j], l[j]);
+  if constexpr (NV == 8) {
+    uint4 ph = make_uint4(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16), h[4] | (uint32_t(h[5]) << 16),
+                          h[6] | (uint32_t(h[7]) << 16));
+    *reinterpret_cast<uint4*>(hi_p + off) = ph;
+    if (lo_p) {
+      uint4 pl = make_uint4(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16),
+                            l[4] | (uint32_t(l[5]) << 16), l[6] | (uint32_t(l[7]) << 16));
+      *reinterpret_cast<uint4*>(lo_p + off) = pl;
+    }
+  } else {
+    uint2 ph = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+    *reinterpret_cast<uint2*>(hi_p + off) = ph;
+    if (lo_p) {
+      uint2 pl = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
+      *reinterpret_cast<uint2*>(lo_p + off) = pl;
+    }
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void load_f32v(const float* p, size_t off, float (&r)[NV]) {
+#pragma unroll
+  for (int j = 0; j < NV; j += 4) {
+    float4 t = *reinterpret_cast<const float4*>(p + off + j);
+    r[j] = t.x; r[j + 1] = t.y; r[j + 2] = t.z; r[j + 3] = t.w;
+  }
+}
+
+// Fused epilogue for NV consecutive GEMM columns [c0, c0+NV) of output pixel (n, oy, ox).
+// v[] = accumulator * w_scale (bias NOT yet added).  c0 % NV == 0.
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy, int ox, int c0, float (&v)[NV]) {
+  if (c0 >= p.cout) return;
+  if (p.store == MCQ_STORE_SHUFFLE_NCHW) {
+    // last layer (compressor.py:139): GEMM column 4c+2i+j -> out[n, c, 2oy+i, 2ox+j], fp32 NCHW
+    const int cq = p.cout >> 2, H2 = p.hout * 2, W2 = p.wout * 2;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = c0 + j;
+      if (col < p.cout) {
+        const int c = col >> 2, i = (col >> 1) & 1, jj = col & 1;
+        p.out_f32[(((size_t)n * cq + c) * H2 + (2 * oy + i)) * W2 + (2 * ox + jj)] = v[j] + p.bias[col];
+      }
+    }
+    return;
+  }
+  int C = p.cout, H = p.hout, W = p.wout, py = oy, px = ox, c = c0;
+  if (p.store == MCQ_STORE_SHUFFLE_NHWC) {
+    const int cq = p.cout >> 2;
+    const int sub = c0 / cq;
+    c = c0 - sub * cq;
+    py = 2 * oy + (sub >> 1);
+    px = 2 * ox + (sub & 1);
+    H *= 2; W *= 2; C = cq;
+  }
+  const size_t off = (((size_t)n * H + py) * W + px) * C + c;
+  float b[NV], y[NV];
+  load_f32v<NV>(p.bias, c0, b);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) y[j] = v[j] + b[j];
+  if (p.mode == MCQ_EPI_LINEAR) {
+    if (p.res1) {
+      float r[NV];
+      load_f32v<NV>(p.res1, off, r);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) y[j] = y[j] + p.res1_scale * r[j];
+    }
+    if (p.res2) {
+      float r[NV];
+      load_f32v<NV>(p.res2, off, r);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) y[j] = y[j] + r[j];
+    }
+  } else if (p.mode == MCQ_EPI_GATE) {
+    float r[NV], a[NV];
+    load_f32v<NV>(p.res1, off, r);
+    load_f32v<NV>(p.aux, off, a);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) y[j] = a[j] * sigmoid_f(y[j]) + r[j];
+  } else {
+    float a[NV];
+    load_f32v<NV>(p.aux, off, a);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float s = sqrtf(y[j]);
+      y[j] = (p.mode == MCQ_EPI_GDN) ? a[j] * (1.0f / s) : a[j] * s;
+    }
+  }
+  if (p.out_f32) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 4)
+      *reinterpret_cast<float4*>(p.out_f32 + off + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+  }
+  if (p.o0_hi) store_planes<NV>(p.o0_hi, p.o0_lo, off, y, p.o0_act);
+  if (p.o1_hi) store_planes<NV>(p.o1_hi, p.o1_lo, off, y, p.o1_act);
+}
+
+}  // namespace mcq

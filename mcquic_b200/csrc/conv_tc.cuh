@@ -1,0 +1,322 @@
+// tcgen05 implicit-GEMM convolution for sm_100a.
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel @ tap, cin] * W[cout, tap, cin]
+//
+// * A is never materialised: for every filter tap the 128-pixel x 64-channel operand tile is one TMA box of
+//   the NHWC activation (5-D view, zero fill outside the image = the conv's zero padding), landing in shared
+//   memory already in the K-major SWIZZLE_128B layout tcgen05.mma consumes.  Stride-2 convolutions use the
+//   view [n, h/2, 2, w/2, 2*c] so that every tap is again a unit-stride box.
+// * B (packed weights [cout_pad, taps*cin]) is a 2-D TMA box per (tap, 64-channel chunk).
+// * One elected thread issues tcgen05.mma (kind::f16, M=128, N=bn, K=16) into TMEM accumulators.
+//   PASSES==3: acc_hh += Ahi*Bhi, acc_lo += Ahi*Blo + Alo*Bhi (split-fp16, fp32-grade); PASSES==1: Ahi*Bhi.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
+//   (tcgen05.ld -> registers -> fused epilogue -> global).  The accumulator is double-buffered in TMEM
+//   when it fits, so the epilogue of tile i overlaps the MMAs of tile i+1.  Persistent CTAs, static schedule.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mcq {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                        // fp16 elements per stage along K (= 128 B swizzle span)
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;    // 16 KB
+constexpr uint32_t TC_TMEM_COLS = 512;
+constexpr unsigned long long TC_WATCHDOG_SPINS = 40ull * 1000 * 1000;
+
+__device__ int g_watchdog_flag = 0;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug (wrong tx byte count, bad tensor map) traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
+  for (unsigned long long i = 0;; ++i) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (i > TC_WATCHDOG_SPINS) {
+      atomicExch(&g_watchdog_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 operands, fp32 accumulate), one CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row atoms 1024 B apart.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  const uint32_t lo = (saddr >> 4) & 0x3FFF;                       // start address, LBO = 0 (unused, swizzled K-major)
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO = 1024 B, version = 1 (sm_100), SWIZZLE_128B
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// ---------------------------------------------------------------- kernel
+template <int PASSES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const ConvArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16 B aligned: round up to the 1024 B the 128B swizzle needs
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bn = p.bn;
+  const uint32_t b_bytes = (uint32_t)bn * TC_BK * 2;
+  const uint32_t stage_bytes = (TC_A_BYTES + b_bytes) * (PASSES == 3 ? 2u : 1u);
+  const int stages = p.stages;
+
+  // smem carve-up: [stage][A_hi | A_lo | B_hi | B_lo] ... barriers
+  const uint32_t bar_base = smem_base + stage_bytes * stages;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * stages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * stages + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + stage_bytes * stages + 8u * (2 * stages + 4));
+
+  const int acc_cols = (PASSES == 3 ? 2 : 1) * bn;   // TMEM columns per accumulator buffer
+  const int nbuf = (2 * acc_cols <= (int)TC_TMEM_COLS) ? 2 : 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (PASSES == 3) {
+      tma_prefetch_desc(&tmA_lo);
+      tma_prefetch_desc(&tmB_lo);
+    }
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_n * p.tiles_y * p.tiles_x;
+  const int total_tiles = tiles_m * p.tiles_c;
+  const int ntaps = p.ksize * p.ksize;
+  const int kchunks = p.cin / TC_BK;
+  const int kiters = ntaps * kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int ct = t / tiles_m;
+        int mt = t - ct * tiles_m;
+        const int bx = mt % p.tiles_x;
+        mt /= p.tiles_x;
+        const int by = mt % p.tiles_y;
+        const int bz = mt / p.tiles_y;
+        const int x0 = bx * p.tw, y0 = by * p.th, n0 = bz * p.tn, c0 = ct * bn;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(empty_bar(s), ph ^ 1u, 1);
+            const uint32_t sa = smem_base + stage_bytes * s;
+            mbar_expect_tx(full_bar(s), stage_bytes);
+            const int ca = p.tap_c[tap] + kc * TC_BK;
+            const int kb = tap * p.cin + kc * TC_BK;
+            tma_load_5d(&tmA_hi, sa, full_bar(s), ca, x0 + p.tap_dx[tap], p.tap_py[tap], y0 + p.tap_dy[tap], n0);
+            if (PASSES == 3) {
+              tma_load_5d(&tmA_lo, sa + TC_A_BYTES, full_bar(s), ca, x0 + p.tap_dx[tap], p.tap_py[tap],
+                          y0 + p.tap_dy[tap], n0);
+              tma_load_2d(&tmB_hi, sa + 2 * TC_A_BYTES, full_bar(s), kb, c0);
+              tma_load_2d(&tmB_lo, sa + 2 * TC_A_BYTES + b_bytes, full_bar(s), kb, c0);
+            } else {
+              tma_load_2d(&tmB_hi, sa + TC_A_BYTES, full_bar(s), kb, c0);
+            }
+            if (++s == stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int buf = (nbuf == 2) ? (it & 1) : 0;
+        const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+        mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_hh = tmem_base + (uint32_t)(buf * acc_cols);
+        const uint32_t d_lo = d_hh + (uint32_t)bn;
+        for (int ki = 0; ki < kiters; ++ki) {
+          mbar_wait(full_bar(s), ph, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage_bytes * s;
+          const uint64_t a_hi = make_sdesc(sa);
+          if (PASSES == 3) {
+            const uint64_t a_lo = make_sdesc(sa + TC_A_BYTES);
+            const uint64_t b_hi = make_sdesc(sa + 2 * TC_A_BYTES);
+            const uint64_t b_lo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint32_t acc = (ki > 0 || k > 0) ? 1u : 0u;
+              const uint64_t ko = (uint64_t)(k * 2);  // +32 B per K=16 step, in 16 B units
+              umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc, acc);
+              umma_f16(d_lo, a_hi + ko, b_lo + ko, idesc, acc);
+              umma_f16(d_lo, a_lo + ko, b_hi + ko, idesc, 1u);
+            }
+          } else {
+            const uint64_t b_hi = make_sdesc(sa + TC_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);
+              umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above have read it
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;      // GEMM row inside the tile = pixel (x fastest, then y, then n)
+    const int ix = row % p.tw;
+    const int iy = (row / p.tw) % p.th;
+    const int in = row / (p.tw * p.th);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int ct = t / tiles_m;
+      int mt = t - ct * tiles_m;
+      const int bx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int by = mt % p.tiles_y;
+      const int bz = mt / p.tiles_y;
+      const int ox = bx * p.tw + ix, oy = by * p.th + iy, n = bz * p.tn + in;
+      const bool valid = (ox < p.wout) && (oy < p.hout) && (n < p.n);
+      const int buf = (nbuf == 2) ? (it & 1) : 0;
+      const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+      mbar_wait(tfull_bar(buf), use & 1u, 4);
+      tc_fence_after();
+      const uint32_t t_hh = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
+      for (int cc = 0; cc < bn; cc += 32) {
+        uint32_t r[32];
+        float v[32];
+        tmem_ld32(t_hh + (uint32_t)cc, r);
+        if (PASSES == 3) {
+          uint32_t l[32];
+          tmem_ld32(t_hh + (uint32_t)(bn + cc), l);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(l[j]), kLoInv, __uint_as_float(r[j])) * p.w_scale;
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.w_scale;
+        }
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float vv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = v[g * 8 + j];
+            epilogue_store<8>(p, n, oy, ox, ct * bn + cc + g * 8, vv);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+}  // namespace mcq

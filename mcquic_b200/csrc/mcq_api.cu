@@ -1,0 +1,389 @@
+// C ABI of libmcquic_b200.so (see include/mcquic_b200.h).  Host-side launch logic only: argument
+// validation, tile geometry, TMA tensor maps, kernel launches on the caller's stream.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "conv_simt.cuh"
+#include "conv_tc.cuh"
+#include "misc.cuh"
+#include "vq.cuh"
+
+using namespace mcq;
+
+namespace {
+
+std::atomic<int> g_launches{0};
+
+#define MCQ_CHECK_ARG(cond)            \
+  do {                                 \
+    if (!(cond)) return MCQ_ERR_BAD_ARG; \
+  } while (0)
+
+inline int cuda_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+// ---- driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+struct TcPlan {
+  ConvArgs args;
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  size_t smem_bytes;
+  int grid;
+};
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// Encode the 5-D view of an NHWC fp16 plane that makes every filter tap a unit-stride TMA box.
+//   stride 1: dims {C,  W,   1, H,   N}
+//   stride 2: dims {2C, W/2, 2, H/2, N}   (x parity folded into the channel axis, y parity its own axis)
+int encode_act_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int stride, int tw, int th, int tn) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MCQ_ERR_DRIVER;
+  cuuint64_t dims[5], strides[4];
+  const cuuint64_t es = 2;
+  if (stride == 1) {
+    dims[0] = c; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = n;
+    strides[0] = (cuuint64_t)c * es;
+    strides[1] = (cuuint64_t)w * c * es;
+    strides[2] = (cuuint64_t)w * c * es;
+    strides[3] = (cuuint64_t)h * w * c * es;
+  } else {
+    dims[0] = 2 * c; dims[1] = w / 2; dims[2] = 2; dims[3] = h / 2; dims[4] = n;
+    strides[0] = (cuuint64_t)2 * c * es;
+    strides[1] = (cuuint64_t)w * c * es;
+    strides[2] = (cuuint64_t)2 * w * c * es;
+    strides[3] = (cuuint64_t)h * w * c * es;
+  }
+  cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)tw, 1u, (cuuint32_t)th, (cuuint32_t)tn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MCQ_ERR_DRIVER;
+}
+
+int encode_weight_map(CUtensorMap* map, const void* ptr, int cout_pad, int ktotal, int bn) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MCQ_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)ktotal, (cuuint64_t)cout_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)ktotal * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MCQ_ERR_DRIVER;
+}
+
+int fill_args(const mcq_conv_params* p, ConvArgs& a) {
+  MCQ_CHECK_ARG(p && p->a_hi && p->w_hi && p->bias);
+  MCQ_CHECK_ARG(p->n > 0 && p->hin > 0 && p->win > 0 && p->cin > 0 && p->cout > 0);
+  MCQ_CHECK_ARG(p->ksize == 1 || p->ksize == 3);
+  MCQ_CHECK_ARG(p->stride == 1 || p->stride == 2);
+  MCQ_CHECK_ARG(p->passes == 1 || p->passes == 3);
+  MCQ_CHECK_ARG(p->cin % 4 == 0);
+  MCQ_CHECK_ARG(p->cout_pad >= p->cout);
+  if (p->passes == 3) MCQ_CHECK_ARG(p->a_lo && p->w_lo);
+  if (p->stride == 2) MCQ_CHECK_ARG(p->hin % 2 == 0 && p->win % 2 == 0);
+  MCQ_CHECK_ARG(p->mode >= MCQ_EPI_LINEAR && p->mode <= MCQ_EPI_IGDN);
+  MCQ_CHECK_ARG(p->store >= MCQ_STORE_NHWC && p->store <= MCQ_STORE_SHUFFLE_NCHW);
+  if (p->mode == MCQ_EPI_GATE) MCQ_CHECK_ARG(p->res1 && p->aux);
+  if (p->mode == MCQ_EPI_GDN || p->mode == MCQ_EPI_IGDN) MCQ_CHECK_ARG(p->aux);
+  if (p->store == MCQ_STORE_SHUFFLE_NCHW) {
+    MCQ_CHECK_ARG(p->out_f32 && p->cout % 4 == 0 && p->mode == MCQ_EPI_LINEAR && !p->res1 && !p->res2);
+    MCQ_CHECK_ARG(!p->out0_hi && !p->out1_hi);
+  } else if (p->store == MCQ_STORE_SHUFFLE_NHWC) {
+    MCQ_CHECK_ARG(p->cout % 4 == 0 && (p->cout / 4) % 8 == 0);
+  } else {
+    MCQ_CHECK_ARG(p->cout % 8 == 0);
+  }
+  MCQ_CHECK_ARG(p->out_f32 || p->out0_hi || p->out1_hi);
+  std::memset(&a, 0, sizeof(a));
+  a.a_hi = (const __half*)p->a_hi; a.a_lo = (const __half*)p->a_lo;
+  a.w_hi = (const __half*)p->w_hi; a.w_lo = (const __half*)p->w_lo;
+  a.bias = p->bias; a.res1 = p->res1; a.res2 = p->res2; a.aux = p->aux;
+  a.out_f32 = p->out_f32;
+  a.o0_hi = (__half*)p->out0_hi; a.o0_lo = (__half*)p->out0_lo;
+  a.o1_hi = (__half*)p->out1_hi; a.o1_lo = (__half*)p->out1_lo;
+  a.w_scale = p->w_scale; a.res1_scale = p->res1_scale;
+  a.n = p->n; a.hin = p->hin; a.win = p->win; a.cin = p->cin;
+  a.hout = p->hin / p->stride; a.wout = p->win / p->stride;
+  a.cout = p->cout; a.cout_pad = p->cout_pad; a.ksize = p->ksize; a.stride = p->stride;
+  a.ktotal = p->ksize * p->ksize * p->cin;
+  a.mode = p->mode; a.store = p->store; a.o0_act = p->out0_act; a.o1_act = p->out1_act; a.passes = p->passes;
+  return 0;
+}
+
+int launch_simt(const ConvArgs& a, cudaStream_t st) {
+  const long long M = (long long)a.n * a.hout * a.wout;
+  dim3 grid((unsigned)((M + SIMT_TM - 1) / SIMT_TM), (unsigned)((a.cout + SIMT_TN - 1) / SIMT_TN));
+  conv_simt_kernel<<<grid, SIMT_THREADS, 0, st>>>(a);
+  g_launches++;
+  return cuda_status();
+}
+
+bool tc_supported(const ConvArgs& a) {
+  if (a.cin % TC_BK != 0) return false;
+  if (a.cout_pad % 16 != 0) return false;
+  return true;
+}
+
+int launch_tc(ConvArgs& a, cudaStream_t st) {
+  // ---- N tile: the whole (padded) cout when it fits one MMA, else 128-column tiles
+  int bn = (a.cout_pad <= 256 && a.cout_pad % 128 != 0) ? a.cout_pad : 128;
+  if (a.cout_pad < 128) bn = a.cout_pad;
+  if (a.cout_pad % bn != 0) return MCQ_ERR_UNSUPPORTED;
+  if (bn % 16 != 0 || bn > 256) return MCQ_ERR_UNSUPPORTED;
+  if (bn > 32 && bn % 32 != 0) return MCQ_ERR_UNSUPPORTED;
+  if ((a.passes == 3 ? 2 : 1) * bn > (int)TC_TMEM_COLS) return MCQ_ERR_UNSUPPORTED;
+  a.bn = bn;
+  a.tiles_c = a.cout_pad / bn;
+  // ---- M tile: (tw x th x tn) box of output pixels, 128 rows
+  a.tw = pow2_ceil(a.wout) < 16 ? pow2_ceil(a.wout) : 16;
+  const int th_max = TC_BM / a.tw;
+  a.th = pow2_ceil(a.hout) < th_max ? pow2_ceil(a.hout) : th_max;
+  a.tn = TC_BM / (a.tw * a.th);
+  a.tiles_x = (a.wout + a.tw - 1) / a.tw;
+  a.tiles_y = (a.hout + a.th - 1) / a.th;
+  a.tiles_n = (a.n + a.tn - 1) / a.tn;
+  // ---- taps
+  const int pad = a.ksize / 2;
+  for (int t = 0; t < a.ksize * a.ksize; ++t) {
+    const int r = t / a.ksize - pad, s = t % a.ksize - pad;  // offsets in [-1, 1]
+    if (a.stride == 1) {
+      a.tap_c[t] = 0; a.tap_dx[t] = s; a.tap_py[t] = 0; a.tap_dy[t] = r;
+    } else {
+      // input row 2*oy + r: parity (r & 1), coarse row oy + floor(r / 2)
+      a.tap_py[t] = r & 1;
+      a.tap_dy[t] = (r < 0) ? -1 : 0;
+      a.tap_c[t] = (s & 1) * a.cin;
+      a.tap_dx[t] = (s < 0) ? -1 : 0;
+    }
+  }
+  // ---- pipeline depth
+  const size_t stage_bytes = (size_t)(TC_A_BYTES + bn * TC_BK * 2) * (a.passes == 3 ? 2 : 1);
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return MCQ_ERR_UNSUPPORTED;
+  a.stages = stages;
+  const size_t smem = stage_bytes * stages + 8 * (2 * stages + 4) + 16 + 1024;
+
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  int rc = encode_act_map(&tmA_hi, a.a_hi, a.n, a.hin, a.win, a.cin, a.stride, a.tw, a.th, a.tn);
+  if (rc) return rc;
+  rc = encode_weight_map(&tmB_hi, a.w_hi, a.cout_pad, a.ktotal, bn);
+  if (rc) return rc;
+  if (a.passes == 3) {
+    rc = encode_act_map(&tmA_lo, a.a_lo, a.n, a.hin, a.win, a.cin, a.stride, a.tw, a.th, a.tn);
+    if (rc) return rc;
+    rc = encode_weight_map(&tmB_lo, a.w_lo, a.cout_pad, a.ktotal, bn);
+    if (rc) return rc;
+  } else {
+    tmA_lo = tmA_hi;
+    tmB_lo = tmB_hi;
+  }
+  const int total_tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.tiles_c;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  cudaError_t e;
+  if (a.passes == 3) {
+    static bool attr3 = false;
+    if (!attr3) {
+      e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      attr3 = true;
+    }
+    conv_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
+  } else {
+    static bool attr1 = false;
+    if (!attr1) {
+      e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      attr1 = true;
+    }
+    conv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
+  }
+  g_launches++;
+  return cuda_status();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
+  ConvArgs a;
+  int rc = fill_args(p, a);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->impl == MCQ_IMPL_SIMT) return launch_simt(a, st);
+  if (p->impl != MCQ_IMPL_TCGEN05) return MCQ_ERR_BAD_ARG;
+  if (!tc_supported(a)) return MCQ_ERR_UNSUPPORTED;
+  return launch_tc(a, st);
+}
+
+int mcq_stem_conv(const float* x, int32_t n, int32_t h, int32_t w, int32_t pad_top, int32_t pad_left, int32_t hp,
+                  int32_t wp, const float* wgt, const float* bias, int32_t cout, float* out_f32, void* out_hi,
+                  void* out_lo, int32_t out_act, mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && wgt && bias && (out_f32 || out_hi));
+  MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && hp >= h && wp >= w && hp % 2 == 0 && wp % 2 == 0);
+  MCQ_CHECK_ARG(pad_top >= 0 && pad_left >= 0 && pad_top <= hp - h && pad_left <= wp - w);
+  MCQ_CHECK_ARG(pad_top < h && (hp - h - pad_top) < h && pad_left < w && (wp - w - pad_left) < w);  // reflect pad limit
+  MCQ_CHECK_ARG(cout % 4 == 0 && cout / 4 <= 256 && 27 * cout * 4 <= 48 * 1024);
+  StemArgs a;
+  a.x = x; a.w = wgt; a.bias = bias; a.out_f32 = out_f32; a.o_hi = (__half*)out_hi; a.o_lo = (__half*)out_lo;
+  a.o_act = out_act; a.n = n; a.h = h; a.w_ = w; a.pad_top = pad_top; a.pad_left = pad_left; a.hp = hp; a.wp = wp;
+  a.cout = cout; a.hout = hp / 2; a.wout = wp / 2;
+  const int cg = cout / 4;
+  const int ppb = 256 / cg > 0 ? 256 / cg : 1;
+  const int threads = ppb * cg;
+  const long long total = (long long)n * a.hout * a.wout;
+  const unsigned grid = (unsigned)((total + ppb - 1) / ppb);
+  stem_conv_kernel<<<grid, threads, 27 * cout * sizeof(float), (cudaStream_t)stream>>>(a);
+  g_launches++;
+  return cuda_status();
+}
+
+int mcq_vq_assign(const float* x, const float* codebook, const float* c2, int64_t* codes, float* logits,
+                  const float* logit_scale, int32_t* hist, int32_t n, int32_t h, int32_t w, int32_t m, int32_t k,
+                  int32_t d, mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && codebook && c2 && codes);
+  MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && m > 0 && k > 0 && d > 0 && d % 4 == 0 && d <= 256);
+  VqArgs a;
+  a.x = x; a.codebook = codebook; a.c2 = c2; a.codes = (long long*)codes; a.logits = logits;
+  a.logit_scale = logit_scale; a.hist = hist;
+  a.P = n * h * w; a.hw = h * w; a.m = m; a.k = k; a.d = d;
+  a.inv_sqrt_k = 1.0f / sqrtf((float)k);
+  const size_t smem = ((size_t)d * (VQ_TP + VQ_TK) + VQ_TP) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(vq_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
+  }
+  dim3 grid((unsigned)((a.P + VQ_TP - 1) / VQ_TP), (unsigned)m);
+  vq_assign_kernel<<<grid, VQ_THREADS, smem, (cudaStream_t)stream>>>(a);
+  g_launches++;
+  return cuda_status();
+}
+
+int mcq_vq_dequant(const int64_t* codes, const float* codebook, int32_t n, int32_t h, int32_t w, int32_t m, int32_t k,
+                   int32_t d, float* out_f32, void* out0_hi, void* out0_lo, int32_t out0_act, void* out1_hi,
+                   void* out1_lo, int32_t out1_act, int32_t* status, mcq_stream_t stream) {
+  MCQ_CHECK_ARG(codes && codebook && (out_f32 || out0_hi || out1_hi));
+  MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && m > 0 && k > 0 && d > 0 && d % 4 == 0);
+  DequantArgs a;
+  a.codes = (const long long*)codes; a.codebook = codebook; a.out_f32 = out_f32;
+  a.o0_hi = (__half*)out0_hi; a.o0_lo = (__half*)out0_lo; a.o1_hi = (__half*)out1_hi; a.o1_lo = (__half*)out1_lo;
+  a.o0_act = out0_act; a.o1_act = out1_act; a.status = status;
+  a.P = n * h * w; a.hw = h * w; a.m = m; a.k = k; a.d = d;
+  const long long total = (long long)a.P * (m * d / 4);
+  vq_dequant_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  g_launches++;
+  return cuda_status();
+}
+
+int mcq_code_histogram(const int64_t* codes, int32_t n, int32_t m, int32_t hw, int32_t k, int32_t* hist,
+                       mcq_stream_t stream) {
+  MCQ_CHECK_ARG(codes && hist && n > 0 && m > 0 && hw > 0 && k > 0);
+  const long long total = (long long)n * m * hw;
+  code_histogram_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const long long*)codes, n,
+                                                                                          m, hw, k, hist);
+  g_launches++;
+  return cuda_status();
+}
+
+int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && out_hi && count > 0 && count % 4 == 0);
+  const long long c4 = count / 4;
+  split_planes_kernel<<<(unsigned)((c4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, c4, act, (__half*)out_hi,
+                                                                                      (__half*)out_lo);
+  g_launches++;
+  return cuda_status();
+}
+
+int mcq_nchw_to_nhwc(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, float* out_f32, void* out0_hi,
+                     void* out0_lo, int32_t out0_act, void* out1_hi, void* out1_lo, int32_t out1_act,
+                     mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && (out_f32 || out0_hi || out1_hi) && n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535);
+  LayoutArgs a;
+  a.x = x; a.out_f32 = out_f32; a.o0_hi = (__half*)out0_hi; a.o0_lo = (__half*)out0_lo; a.o1_hi = (__half*)out1_hi;
+  a.o1_lo = (__half*)out1_lo; a.o0_act = out0_act; a.o1_act = out1_act; a.n = n; a.c = c; a.hw = h * w;
+  dim3 grid((unsigned)((a.hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(a);
+  g_launches++;
+  return cuda_status();
+}
+
+int mcq_nhwc_to_nchw(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, float* out, mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && out && n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535);
+  dim3 grid((unsigned)((h * w + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, c, h * w, out);
+  g_launches++;
+  return cuda_status();
+}
+
+const char* mcq_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case MCQ_ERR_BAD_ARG: return "mcquic_b200: bad argument (shape/pointer/alignment contract violated)";
+    case MCQ_ERR_UNSUPPORTED: return "mcquic_b200: configuration not supported by the tcgen05 kernel";
+    case MCQ_ERR_DRIVER: return "mcquic_b200: CUDA driver call failed (cuTensorMapEncodeTiled)";
+    case MCQ_ERR_CODE_RANGE: return "mcquic_b200: code index outside [0, k)";
+    case MCQ_ERR_WATCHDOG: return "mcquic_b200: device-side pipeline watchdog fired";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "mcquic_b200: unknown error";
+  }
+}
+
+int mcq_version(void) { return 1; }
+
+int mcq_device_error_flag(void) {
+  int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_watchdog_flag, sizeof(int)) != cudaSuccess) return MCQ_ERR_WATCHDOG;
+  if (v) {
+    int z = 0;
+    cudaMemcpyToSymbol(g_watchdog_flag, &z, sizeof(int));
+  }
+  return v;
+}
+
+int mcq_kernel_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

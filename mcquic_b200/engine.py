@@ -1,0 +1,367 @@
+"""Host-side executor: walks the reference-shaped module tree and issues one fused CUDA launch per convolution.
+
+PyTorch is used for device memory, streams and (one-time) weight repacking only; every FLOP of the hot path
+runs in libmcquic_b200.so (`_lib.py`).  Fusion map (reference op -> where it went):
+
+  nn.SiLU before a conv              -> producer epilogue writes silu(y) as a split-fp16 plane pair
+  `out += identity` (blocks.py:77)   -> residual operand of the consuming conv's epilogue
+  GDN / IGDN (gdn.py:67-91)          -> 1x1 tensor-core conv over x^2 planes, epilogue x * rsqrt/sqrt(.)
+  PixelShuffle (convs.py:252-255)    -> store addressing of the producing conv (weights row-permuted at load)
+  a * sigmoid(b) + x (blocks.py:281) -> epilogue of the AttentionBlock's trailing 1x1 conv
+  z - dequant(code) (quantizer.py:318), q + side (quantizer.py:354) -> residual operands
+  AlignedPadding (transforms.py:86)  -> index arithmetic of the stem kernel
+"""
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Set, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .nn.blocks import AttentionBlock, ResidualBlock, ResidualBlockShuffle, ResidualBlockWithStride
+from .nn.gdn import GenDivNorm
+
+Planes = Tuple[torch.Tensor, Optional[torch.Tensor]]  # (hi, lo) fp16 NHWC; lo is None on the 1-pass path
+
+LO_SCALE = 2048.0
+
+
+@dataclass
+class Act:
+    """One activation, NHWC, in whichever representations its consumers need."""
+    n: int
+    h: int
+    w: int
+    c: int
+    f32: Optional[torch.Tensor] = None
+    raw: Optional[Planes] = None
+    silu: Optional[Planes] = None
+    sq: Optional[Planes] = None
+
+
+@dataclass
+class PackedConv:
+    w_hi: torch.Tensor
+    w_lo: torch.Tensor
+    bias: torch.Tensor
+    cin: int
+    cout: int
+    cout_pad: int
+    ksize: int
+    stride: int
+    w_scale: float
+    store: int
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def split_weight(w2d: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, float]:
+    """fp32 [rows, K] -> (hi, lo) fp16 with  w * 2^e ~= hi + lo / 2048  and the accumulator scale 2^-e."""
+    amax = float(w2d.abs().max())
+    e = 0 if amax == 0.0 or not math.isfinite(amax) else int(max(-14, min(14, math.floor(math.log2(256.0 / amax)))))
+    ws = w2d.double() * (2.0 ** e)
+    hi = ws.to(torch.float16)
+    lo = ((ws - hi.double()) * LO_SCALE).to(torch.float16)
+    return hi.contiguous(), lo.contiguous(), float(2.0 ** (-e))
+
+
+def pack_conv(weight: torch.Tensor, bias: torch.Tensor, stride: int, store: int, device) -> PackedConv:
+    """nn.Conv2d weight [cout, cin, k, k] -> K-major GEMM matrix [cout_pad, (r, s, cin)] (split fp16)."""
+    cout, cin, k, _ = weight.shape
+    w = weight.detach().to(device=device, dtype=torch.float32).permute(0, 2, 3, 1).reshape(cout, k * k * cin)
+    b = bias.detach().to(device=device, dtype=torch.float32)
+    if store == _lib.STORE_SHUFFLE_NHWC:
+        # PixelShuffle(2): conv channel 4c + 2i + j -> GEMM column (2i + j) * C + c, so an N tile is one sub-pixel
+        cq = cout // 4
+        perm = torch.arange(cout, device=device).reshape(cq, 4).t().reshape(-1)
+        w, b = w[perm], b[perm]
+    cout_pad = cout if cout % 128 == 0 or (cout <= 256 and cout % 32 == 0) else ((cout + 15) // 16) * 16
+    if cout_pad != cout:
+        w = torch.cat([w, torch.zeros(cout_pad - cout, w.shape[1], device=device)], 0)
+    hi, lo, scale = split_weight(w)
+    return PackedConv(hi, lo, b.contiguous(), cin, cout, cout_pad, k, stride, scale, store)
+
+
+class Engine:
+    """passes: 3 = split-fp16 fp32-grade (encode), 1 = single fp16 pass, TF32-grade (decode).
+    impl: 'tcgen05' (tensor cores) or 'simt' (fp32 CUDA-core cross-check kernel)."""
+
+    def __init__(self, impl: str = "tcgen05", lib=None):
+        # `lib` is a test seam (tests/emulator.py injects a CPU model of the C ABI to check this host logic
+        # without a GPU); the product always binds the CUDA library and raises if it cannot be loaded.
+        self.emulated = lib is not None
+        self.lib = lib if lib is not None else _lib.load()
+        self.impl = {"tcgen05": _lib.IMPL_TCGEN05, "simt": _lib.IMPL_SIMT}[impl]
+        self.passes = 3
+        self._packed: Dict[Tuple[int, int], Tuple[Tuple, PackedConv]] = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        if self.emulated:
+            return ctypes.c_void_p(0)
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _planes(self, n, h, w, c, device) -> Planes:
+        hi = torch.empty((n, h, w, c), dtype=torch.float16, device=device)
+        lo = torch.empty((n, h, w, c), dtype=torch.float16, device=device) if self.passes == 3 else None
+        return hi, lo
+
+    def _packed_for(self, mod: nn.Module, store: int = _lib.STORE_NHWC) -> PackedConv:
+        key = (id(mod), store)
+        if isinstance(mod, GenDivNorm):
+            ver = (mod.beta._version, mod.gamma._version, mod.beta.data_ptr(), mod.gamma.data_ptr())
+        else:
+            ver = (mod.weight._version, mod.bias._version, mod.weight.data_ptr(), mod.bias.data_ptr())
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        if isinstance(mod, GenDivNorm):
+            beta, gamma = mod.effective()
+            pc = pack_conv(gamma[:, :, None, None], beta, 1, _lib.STORE_NHWC, gamma.device)
+        else:
+            pc = pack_conv(mod.weight, mod.bias, mod.stride[0], store, mod.weight.device)
+        self._packed[key] = (ver, pc)
+        return pc
+
+    def prepare(self, root: nn.Module):
+        """Repack every convolution under `root` now (otherwise done lazily on first use)."""
+        for mod in root.modules():
+            if isinstance(mod, ResidualBlockShuffle):
+                self._packed_for(mod._branch[1][0], _lib.STORE_SHUFFLE_NHWC)
+                self._packed_for(mod._skip[0], _lib.STORE_SHUFFLE_NHWC)
+            elif isinstance(mod, GenDivNorm):
+                self._packed_for(mod)
+
+    # ------------------------------------------------------------------ one fused conv launch
+    def conv(self, pc: PackedConv, a: Planes, x: Act, want: Set[str], *, mode: int = _lib.EPI_LINEAR,
+             res1: Optional[torch.Tensor] = None, res1_scale: float = 1.0, res2: Optional[torch.Tensor] = None,
+             aux: Optional[torch.Tensor] = None) -> Act:
+        assert pc.cin == x.c, (pc.cin, x.c)
+        dev = a[0].device
+        ho, wo = x.h // pc.stride, x.w // pc.stride
+        co = pc.cout
+        if pc.store != _lib.STORE_NHWC:
+            ho, wo, co = ho * 2, wo * 2, pc.cout // 4
+        out = Act(x.n, ho, wo, co)
+        p = _lib.ConvParams()
+        p.a_hi, p.a_lo = _ptr(a[0]), _ptr(a[1])
+        p.n, p.hin, p.win, p.cin = x.n, x.h, x.w, x.c
+        p.w_hi, p.w_lo = _ptr(pc.w_hi), _ptr(pc.w_lo)
+        p.cout, p.cout_pad, p.ksize, p.stride = pc.cout, pc.cout_pad, pc.ksize, pc.stride
+        p.w_scale = pc.w_scale
+        p.bias = _ptr(pc.bias)
+        p.mode, p.store = mode, pc.store
+        p.res1, p.res1_scale, p.res2, p.aux = _ptr(res1), res1_scale, _ptr(res2), _ptr(aux)
+        keep = [a, res1, res2, aux]
+        if pc.store == _lib.STORE_SHUFFLE_NCHW:
+            out.f32 = torch.empty((x.n, co, ho, wo), dtype=torch.float32, device=dev)  # NCHW pixels
+            p.out_f32 = _ptr(out.f32)
+        else:
+            if "f32" in want:
+                out.f32 = torch.empty((x.n, ho, wo, co), dtype=torch.float32, device=dev)
+                p.out_f32 = _ptr(out.f32)
+            slots = []
+            for name, act in (("raw", _lib.ACT_NONE), ("silu", _lib.ACT_SILU), ("sq", _lib.ACT_SQUARE)):
+                if name in want:
+                    pl = self._planes(x.n, ho, wo, co, dev)
+                    setattr(out, name, pl)
+                    slots.append((pl, act))
+            assert len(slots) <= 2, want
+            if len(slots) > 0:
+                p.out0_hi, p.out0_lo, p.out0_act = _ptr(slots[0][0][0]), _ptr(slots[0][0][1]), slots[0][1]
+            if len(slots) > 1:
+                p.out1_hi, p.out1_lo, p.out1_act = _ptr(slots[1][0][0]), _ptr(slots[1][0][1]), slots[1][1]
+        p.passes = self.passes if a[1] is not None else 1
+        p.impl = self.impl if (pc.cin % 64 == 0) else _lib.IMPL_SIMT
+        _lib.check(self.lib.mcq_conv2d(ctypes.byref(p), self._stream()), "mcq_conv2d")
+        del keep
+        return out
+
+    # ------------------------------------------------------------------ blocks
+    @staticmethod
+    def needs_of(mod: nn.Module) -> Set[str]:
+        """Representations of its input a module reads."""
+        if isinstance(mod, (ResidualBlock, AttentionBlock)):
+            return {"f32", "silu"}
+        if isinstance(mod, (ResidualBlockWithStride, ResidualBlockShuffle)):
+            return {"raw", "silu"}
+        if isinstance(mod, (nn.Conv2d, nn.Sequential)):
+            return {"raw"}
+        raise NotImplementedError(f"mcquic_b200: no accelerated path for {type(mod).__name__}")
+
+    def residual_block(self, mod: ResidualBlock, x: Act, want: Set[str], res2: Optional[torch.Tensor] = None) -> Act:
+        t = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"silu"})
+        return self.conv(self._packed_for(mod._branch[3]), t.silu, t, want, res1=x.f32, res2=res2)
+
+    def residual_block_stride(self, mod: ResidualBlockWithStride, x: Act, want: Set[str]) -> Act:
+        u = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"f32", "sq"})
+        t = self.conv(self._packed_for(mod._branch[2]), u.sq, u, {"raw"}, mode=_lib.EPI_GDN, aux=u.f32)
+        s = self.conv(self._packed_for(mod._skip), x.raw, x, {"f32"})
+        return self.conv(self._packed_for(mod._branch[3]), t.raw, t, want, res1=s.f32)
+
+    def residual_block_shuffle(self, mod: ResidualBlockShuffle, x: Act, want: Set[str]) -> Act:
+        sh = _lib.STORE_SHUFFLE_NHWC
+        u = self.conv(self._packed_for(mod._branch[1][0], sh), x.silu, x, {"f32", "sq"})
+        t = self.conv(self._packed_for(mod._branch[2]), u.sq, u, {"raw"}, mode=_lib.EPI_IGDN, aux=u.f32)
+        s = self.conv(self._packed_for(mod._skip[0], sh), x.raw, x, {"f32"})
+        return self.conv(self._packed_for(mod._branch[3]), t.raw, t, want, res1=s.f32)
+
+    def attention_block(self, mod: AttentionBlock, x: Act, want: Set[str]) -> Act:
+        a = x
+        for i in range(3):
+            a = self.residual_block(mod._mainBranch[i], a, {"f32", "silu"} if i < 2 else {"f32"})
+        b = x
+        for i in range(3):
+            b = self.residual_block(mod._sideBranch[i], b, {"f32", "silu"} if i < 2 else {"raw"})
+        return self.conv(self._packed_for(mod._sideBranch[3]), b.raw, b, want, mode=_lib.EPI_GATE, res1=x.f32,
+                         aux=a.f32)
+
+    def run(self, mod: nn.Module, x: Act, want: Set[str], tail: Optional[Tuple[torch.Tensor, float]] = None) -> Act:
+        """tail = (tensor, scale): an extra fp32 NHWC term added by the module's last epilogue."""
+        if isinstance(mod, ResidualBlock):
+            assert tail is None or tail[1] == 1.0
+            return self.residual_block(mod, x, want, None if tail is None else tail[0])
+        if isinstance(mod, nn.Conv2d):
+            if tail is None:
+                return self.conv(self._packed_for(mod), x.raw, x, want)
+            return self.conv(self._packed_for(mod), x.raw, x, want, res1=tail[0], res1_scale=tail[1])
+        assert tail is None
+        if isinstance(mod, ResidualBlockWithStride):
+            return self.residual_block_stride(mod, x, want)
+        if isinstance(mod, ResidualBlockShuffle):
+            return self.residual_block_shuffle(mod, x, want)
+        if isinstance(mod, AttentionBlock):
+            return self.attention_block(mod, x, want)
+        if isinstance(mod, nn.Sequential) and len(mod) == 2 and isinstance(mod[1], nn.PixelShuffle):
+            # pixelShuffle3x3 used stand-alone = last decoder layer -> fp32 NCHW pixels
+            return self.conv(self._packed_for(mod[0], _lib.STORE_SHUFFLE_NCHW), x.raw, x, want)
+        raise NotImplementedError(f"mcquic_b200: no accelerated path for {type(mod).__name__}")
+
+    def run_seq(self, mods: Sequence[nn.Module], x: Act, want: Set[str],
+                tail: Optional[Tuple[torch.Tensor, float]] = None) -> Act:
+        mods = list(mods)
+        for i, mod in enumerate(mods):
+            last = i + 1 == len(mods)
+            x = self.run(mod, x, want if last else self.needs_of(mods[i + 1]), tail if last else None)
+        return x
+
+    # ------------------------------------------------------------------ boundary ops
+    def stem(self, conv: nn.Conv2d, x: torch.Tensor, pad: Tuple[int, int, int, int], want: Set[str]) -> Act:
+        """conv3x3 s2 on the fp32 NCHW image; pad = (top, left, padded_h, padded_w) (AlignedPadding folded in)."""
+        n, c, h, w = x.shape
+        if c != 3 or conv.in_channels != 3 or conv.stride[0] != 2:
+            raise RuntimeError("mcquic_b200: the stem expects [n, 3, h, w] input and conv3x3(3, C, stride=2)")
+        top, left, hp, wp = pad
+        cout = conv.out_channels
+        out = Act(n, hp // 2, wp // 2, cout)
+        dev = x.device
+        if "f32" in want:
+            out.f32 = torch.empty((n, out.h, out.w, cout), dtype=torch.float32, device=dev)
+        pl, act = (None, None), _lib.ACT_NONE
+        if "silu" in want:
+            out.silu = pl = self._planes(n, out.h, out.w, cout, dev)
+            act = _lib.ACT_SILU
+        elif "raw" in want:
+            out.raw = pl = self._planes(n, out.h, out.w, cout, dev)
+        wgt = conv.weight.detach().reshape(cout, 27).contiguous().float()
+        bias = conv.bias.detach().contiguous().float()
+        xc = x.contiguous().float()
+        _lib.check(self.lib.mcq_stem_conv(_ptr(xc), n, h, w, top, left, hp, wp, _ptr(wgt), _ptr(bias), cout,
+                                          _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act, self._stream()),
+                   "mcq_stem_conv")
+        return out
+
+    def from_nchw(self, x: torch.Tensor, want: Set[str]) -> Act:
+        n, c, h, w = x.shape
+        out = Act(n, h, w, c)
+        xc = x.contiguous().float()
+        dev = x.device
+        if "f32" in want:
+            out.f32 = torch.empty((n, h, w, c), dtype=torch.float32, device=dev)
+        slots = []
+        for name, act in (("raw", _lib.ACT_NONE), ("silu", _lib.ACT_SILU), ("sq", _lib.ACT_SQUARE)):
+            if name in want:
+                pl = self._planes(n, h, w, c, dev)
+                setattr(out, name, pl)
+                slots.append((pl, act))
+        slots += [((None, None), 0)] * (2 - len(slots))
+        _lib.check(self.lib.mcq_nchw_to_nhwc(_ptr(xc), n, c, h, w, _ptr(out.f32), _ptr(slots[0][0][0]),
+                                             _ptr(slots[0][0][1]), slots[0][1], _ptr(slots[1][0][0]),
+                                             _ptr(slots[1][0][1]), slots[1][1], self._stream()), "mcq_nchw_to_nhwc")
+        return out
+
+    def to_nchw(self, x: Act) -> torch.Tensor:
+        out = torch.empty((x.n, x.c, x.h, x.w), dtype=torch.float32, device=x.f32.device)
+        _lib.check(self.lib.mcq_nhwc_to_nchw(_ptr(x.f32), x.n, x.c, x.h, x.w, _ptr(out), self._stream()),
+                   "mcq_nhwc_to_nchw")
+        return out
+
+    def run_module_nchw(self, mod: nn.Module, x: torch.Tensor) -> torch.Tensor:
+        """Stand-alone execution of one block on an NCHW tensor (API parity with calling the reference module)."""
+        if not x.is_cuda and not self.emulated:
+            raise RuntimeError("mcquic_b200 runs on CUDA tensors only (no CPU fallback)")
+        with torch.no_grad():
+            act = self.from_nchw(x, self.needs_of(mod))
+            return self.to_nchw(self.run(mod, act, {"f32"}))
+
+    # ------------------------------------------------------------------ VQ
+    def vq_assign(self, x_nhwc: torch.Tensor, codebook: torch.Tensor, c2: torch.Tensor, n: int, h: int, w: int,
+                  logits: bool = False, logit_scale: Optional[torch.Tensor] = None,
+                  hist: Optional[torch.Tensor] = None):
+        m, k, d = codebook.shape
+        codes = torch.empty((n, m, h, w), dtype=torch.int64, device=x_nhwc.device)
+        lg = torch.empty((n, m, h, w, k), dtype=torch.float32, device=x_nhwc.device) if logits else None
+        _lib.check(self.lib.mcq_vq_assign(_ptr(x_nhwc), _ptr(codebook), _ptr(c2), _ptr(codes), _ptr(lg),
+                                          _ptr(logit_scale), _ptr(hist), n, h, w, m, k, d, self._stream()),
+                   "mcq_vq_assign")
+        return (codes, lg) if logits else codes
+
+    def vq_dequant(self, codes: torch.Tensor, codebook: torch.Tensor, want: Set[str],
+                   status: Optional[torch.Tensor] = None) -> Act:
+        n, m, h, w = codes.shape
+        _, k, d = codebook.shape
+        out = Act(n, h, w, m * d)
+        dev = codes.device
+        if "f32" in want:
+            out.f32 = torch.empty((n, h, w, m * d), dtype=torch.float32, device=dev)
+        slots = []
+        for name, act in (("raw", _lib.ACT_NONE), ("silu", _lib.ACT_SILU)):
+            if name in want:
+                pl = self._planes(n, h, w, m * d, dev)
+                setattr(out, name, pl)
+                slots.append((pl, act))
+        slots += [((None, None), 0)] * (2 - len(slots))
+        _lib.check(self.lib.mcq_vq_dequant(_ptr(codes), _ptr(codebook), n, h, w, m, k, d, _ptr(out.f32),
+                                           _ptr(slots[0][0][0]), _ptr(slots[0][0][1]), slots[0][1],
+                                           _ptr(slots[1][0][0]), _ptr(slots[1][0][1]), slots[1][1], _ptr(status),
+                                           self._stream()), "mcq_vq_dequant")
+        return out
+
+    def code_histogram(self, codes: List[torch.Tensor], ks: Sequence[int], out: Optional[torch.Tensor] = None):
+        """One flat int32 buffer [sum_l m*k_l] (level-major) -- the only thing that ever crosses NVLink."""
+        m = codes[0].shape[1]
+        total = sum(m * k for k in ks)
+        if out is None:
+            out = torch.zeros(total, dtype=torch.int32, device=codes[0].device)
+        off = 0
+        for code, k in zip(codes, ks):
+            n, mm, h, w = code.shape
+            view = out[off:off + mm * k]
+            _lib.check(self.lib.mcq_code_histogram(_ptr(code.contiguous()), n, mm, h * w, k, _ptr(view),
+                                                   self._stream()), "mcq_code_histogram")
+            off += mm * k
+        return out
+
+
+_DEFAULT: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _DEFAULT
+    if _DEFAULT is None:
+        _DEFAULT = Engine()
+    return _DEFAULT

@@ -1,0 +1,197 @@
+"""CPU model of the C ABI in include/mcquic_b200.h  --  TEST INFRASTRUCTURE ONLY.
+
+Implements every entry point on host memory with numpy/torch so that the *host-side* logic of
+mcquic_b200 (module walk, fusion map, weight repacking / PixelShuffle row permutation, stride-2 tap
+tables, split-fp16 plane format) can be checked against the oracle on a box without a GPU.  It is written
+from the header's contract, not from the CUDA sources, so it doubles as a second reading of the spec.
+Never imported by the product.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from mcquic_b200 import _lib
+
+LO = 2048.0
+
+
+def _arr(ptr, shape, dtype):
+    if not ptr:
+        return None
+    count = int(np.prod(shape))
+    ctype = {np.float32: ctypes.c_float, np.float16: ctypes.c_uint16, np.int64: ctypes.c_int64,
+             np.int32: ctypes.c_int32}[dtype]
+    buf = (ctype * count).from_address(ptr)
+    a = np.ctypeslib.as_array(buf)
+    if dtype is np.float16:
+        a = a.view(np.float16)
+    return a.reshape(shape)
+
+
+def _act(y, act):
+    if act == _lib.ACT_SILU:
+        return F.silu(y)
+    if act == _lib.ACT_SQUARE:
+        return y * y
+    return y
+
+
+def _store_planes(hi_ptr, lo_ptr, shape, y, act):
+    if not hi_ptr:
+        return
+    t = _act(y, act).float()
+    hi = t.clamp(-65504, 65504).half()
+    _arr(hi_ptr, shape, np.float16)[...] = hi.numpy()
+    if lo_ptr:
+        lo = ((t - hi.float()) * LO).clamp(-65504, 65504).half()
+        _arr(lo_ptr, shape, np.float16)[...] = lo.numpy()
+
+
+class EmulatedLib:
+    """duck-types the ctypes CDLL object `mcquic_b200._lib.load()` returns"""
+
+    def __init__(self):
+        self.launches = 0
+
+    # ------------------------------------------------------------------
+    def mcq_conv2d(self, pref, stream):
+        p = pref._obj
+        n, hin, win, cin = p.n, p.hin, p.win, p.cin
+        k, s = p.ksize, p.stride
+        K = k * k * cin
+        a = torch.from_numpy(_arr(p.a_hi, (n, hin, win, cin), np.float16).astype(np.float32))
+        w = torch.from_numpy(_arr(p.w_hi, (p.cout_pad, K), np.float16).astype(np.float32))
+        if p.passes == 3:
+            a = a.double() + torch.from_numpy(_arr(p.a_lo, (n, hin, win, cin), np.float16).astype(np.float64)) / LO
+            w = w.double() + torch.from_numpy(_arr(p.w_lo, (p.cout_pad, K), np.float16).astype(np.float64)) / LO
+        else:
+            a, w = a.double(), w.double()
+        w4 = w[:p.cout].reshape(p.cout, k, k, cin).permute(0, 3, 1, 2)
+        acc = F.conv2d(a.permute(0, 3, 1, 2), w4, None, stride=s, padding=k // 2)  # [n, cout, ho, wo]
+        bias = torch.from_numpy(_arr(p.bias, (p.cout,), np.float32).copy())
+        v = (acc * p.w_scale).float() + bias[None, :, None, None]
+        ho, wo = hin // s, win // s
+        if p.store == _lib.STORE_SHUFFLE_NCHW:
+            _arr(p.out_f32, (n, p.cout // 4, 2 * ho, 2 * wo), np.float32)[...] = F.pixel_shuffle(v, 2).numpy()
+            self.launches += 1
+            return 0
+        y = v.permute(0, 2, 3, 1)  # NHWC, GEMM-column order
+        if p.store == _lib.STORE_SHUFFLE_NHWC:
+            cq = p.cout // 4
+            # column (2i+j)*cq + c -> pixel (2y+i, 2x+j), channel c
+            y = y.reshape(n, ho, wo, 2, 2, cq).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * ho, 2 * wo, cq)
+        shape = tuple(y.shape)
+        g = lambda ptr: None if not ptr else torch.from_numpy(_arr(ptr, shape, np.float32).copy())
+        res1, res2, aux = g(p.res1), g(p.res2), g(p.aux)
+        if p.mode == _lib.EPI_LINEAR:
+            if res1 is not None:
+                y = y + p.res1_scale * res1
+            if res2 is not None:
+                y = y + res2
+        elif p.mode == _lib.EPI_GATE:
+            y = aux * torch.sigmoid(y) + res1
+        elif p.mode == _lib.EPI_GDN:
+            y = aux * (1.0 / torch.sqrt(y))
+        else:
+            y = aux * torch.sqrt(y)
+        y = y.contiguous()
+        if p.out_f32:
+            _arr(p.out_f32, shape, np.float32)[...] = y.numpy()
+        _store_planes(p.out0_hi, p.out0_lo, shape, y, p.out0_act)
+        _store_planes(p.out1_hi, p.out1_lo, shape, y, p.out1_act)
+        self.launches += 1
+        return 0
+
+    def mcq_stem_conv(self, x, n, h, w, top, left, hp, wp, wgt, bias, cout, out_f32, out_hi, out_lo, act, stream):
+        xi = torch.from_numpy(_arr(x.value, (n, 3, h, w), np.float32).copy())
+        if hp != h or wp != w:
+            xi = F.pad(xi, (left, wp - w - left, top, hp - h - top), "reflect")
+        wt = torch.from_numpy(_arr(wgt.value, (cout, 3, 3, 3), np.float32).copy())
+        b = torch.from_numpy(_arr(bias.value, (cout,), np.float32).copy())
+        y = F.conv2d(xi, wt, b, stride=2, padding=1).permute(0, 2, 3, 1).contiguous()
+        shape = tuple(y.shape)
+        if out_f32 is not None and out_f32.value:
+            _arr(out_f32.value, shape, np.float32)[...] = y.numpy()
+        _store_planes(out_hi.value if out_hi is not None else 0, out_lo.value if out_lo is not None else 0, shape, y, act)
+        self.launches += 1
+        return 0
+
+    def mcq_vq_assign(self, x, codebook, c2, codes, logits, logit_scale, hist, n, h, w, m, k, d, stream):
+        xi = torch.from_numpy(_arr(x.value, (n * h * w, m, d), np.float32).copy())
+        cb = torch.from_numpy(_arr(codebook.value, (m, k, d), np.float32).copy())
+        cc = torch.from_numpy(_arr(c2.value, (m, k), np.float32).copy())
+        x2 = (xi ** 2).sum(-1)                                    # [P, m]
+        inter = torch.einsum("pmd,mkd->pmk", xi, cb)
+        dist = (x2[..., None] + cc[None]) - 2 * inter             # [P, m, k]
+        code = dist.argmin(-1).reshape(n, h * w, m).permute(0, 2, 1).reshape(n, m, h, w)
+        _arr(codes.value, (n, m, h, w), np.int64)[...] = code.numpy()
+        if logits is not None and logits.value:
+            sc = torch.ones(m) if logit_scale is None or not logit_scale.value else torch.from_numpy(
+                _arr(logit_scale.value, (m,), np.float32).copy())
+            lg = (-dist / (k ** 0.5)) * sc[None, :, None]
+            _arr(logits.value, (n, m, h, w, k), np.float32)[...] = lg.reshape(n, h, w, m, k).permute(0, 3, 1, 2, 4).numpy()
+        if hist is not None and hist.value:
+            hv = _arr(hist.value, (m, k), np.int32)
+            for j in range(m):
+                hv[j] += np.bincount(code[:, j].flatten().numpy(), minlength=k).astype(np.int32)
+        self.launches += 1
+        return 0
+
+    def mcq_vq_dequant(self, codes, codebook, n, h, w, m, k, d, out_f32, o0h, o0l, a0, o1h, o1l, a1, status, stream):
+        code = torch.from_numpy(_arr(codes.value, (n, m, h, w), np.int64).copy())
+        cb = torch.from_numpy(_arr(codebook.value, (m, k, d), np.float32).copy())
+        if ((code < 0) | (code >= k)).any():
+            if status is not None and status.value:
+                _arr(status.value, (1,), np.int32)[0] = -4
+            code = code.clamp(0, k - 1) * ((code >= 0) & (code < k))
+        ix = torch.arange(m)[None, None, None, :].expand(n, h, w, m)
+        y = cb[ix, code.permute(0, 2, 3, 1)].reshape(n, h, w, m * d).contiguous()
+        shape = tuple(y.shape)
+        v = lambda q: q.value if q is not None and q.value else 0
+        if v(out_f32):
+            _arr(v(out_f32), shape, np.float32)[...] = y.numpy()
+        _store_planes(v(o0h), v(o0l), shape, y, a0)
+        _store_planes(v(o1h), v(o1l), shape, y, a1)
+        self.launches += 1
+        return 0
+
+    def mcq_code_histogram(self, codes, n, m, hw, k, hist, stream):
+        code = _arr(codes.value, (n, m, hw), np.int64)
+        hv = _arr(hist.value, (m, k), np.int32)
+        for j in range(m):
+            c = code[:, j].reshape(-1)
+            c = c[(c >= 0) & (c < k)]
+            hv[j] += np.bincount(c, minlength=k).astype(np.int32)
+        self.launches += 1
+        return 0
+
+    def mcq_split_planes(self, x, count, act, out_hi, out_lo, stream):
+        y = torch.from_numpy(_arr(x.value, (count,), np.float32).copy())
+        _store_planes(out_hi.value, out_lo.value if out_lo is not None and out_lo.value else 0, (count,), y, act)
+        self.launches += 1
+        return 0
+
+    def mcq_nchw_to_nhwc(self, x, n, c, h, w, out_f32, o0h, o0l, a0, o1h, o1l, a1, stream):
+        y = torch.from_numpy(_arr(x.value, (n, c, h, w), np.float32).copy()).permute(0, 2, 3, 1).contiguous()
+        shape = tuple(y.shape)
+        v = lambda q: q.value if q is not None and q.value else 0
+        if v(out_f32):
+            _arr(v(out_f32), shape, np.float32)[...] = y.numpy()
+        _store_planes(v(o0h), v(o0l), shape, y, a0)
+        _store_planes(v(o1h), v(o1l), shape, y, a1)
+        self.launches += 1
+        return 0
+
+    def mcq_nhwc_to_nchw(self, x, n, c, h, w, out, stream):
+        y = torch.from_numpy(_arr(x.value, (n, h, w, c), np.float32).copy()).permute(0, 3, 1, 2).contiguous()
+        _arr(out.value, (n, c, h, w), np.float32)[...] = y.numpy()
+        self.launches += 1
+        return 0
+
+    def mcq_error_string(self, code):
+        return f"emulated error {code}".encode()
+
+    def mcq_kernel_launch_count(self):
+        return self.launches
