@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: encode+decode MPix/s at qp=1, batch 64x3x256x256 per GPU (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch: `model.encode(x)` (analysis transform + 3-level VQ, code
+histogram fused into the VQ launch) then `model.decode(codes)` (gather + synthesis transform), plus -- at N>1 --
+the single NCCL all-gather of the int32 code histogram (the path's only exchange step).  Each rank processes its
+own batch of 64 images (weak scaling; images are independent).  Prints ONE JSON line on rank 0.
+
+value      device time of K steps (CUDA events per step on the launching stream, L2 flushed between steps,
+           max over ranks), inputs resident in HBM.
+e2e        same steps through the public API from pinned HOST memory: H2D of the images, encode, D2H of the
+           codes, decode, D2H of the pixels -- all inside the timed region.
+roofline   every tcgen05 convolution launch of one step bracketed by CUDA events (eager pass after the timed
+           region): achieved = sum(algorithmic FLOPs) / sum(durations) against the measured dense bf16/fp16 peak.
+cpu_baseline / --impl reference: the oracle restatement of the reference's PyTorch CPU path (oracle/mcquic_oracle.py;
+           /root/reference itself cannot travel to the GPU box) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHANNEL, M, K = 128, 1, [8192, 2048, 512]   # qp=1
+BATCH, H, W = 64, 256, 256
+ALG_GFLOP_PER_IMAGE = 89.44                  # encode 37.33 + decode 52.11 at 256x256
+METRIC = "encode+decode MPix/s at qp=1, batch 64x3x256x256"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fp:
+            return json.load(fp), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        busy = [v for v in sm if v >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _cpu_oracle_throughput(sample_images: int, repeats: int):
+    """encode+decode MPix/s of the CPU oracle on `sample_images` synthetic 256x256 images, best of `repeats`."""
+    import torch
+    from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
+    from oracle import mcquic_oracle as oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic_state_dict(CHANNEL, M, K, seed=0)
+    x = uniform((sample_images, 3, H, W), "bench.image", 0)
+    oracle.decode(sd, oracle.encode(sd, x[:1]))  # warm-up
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        codes = oracle.encode(sd, x)
+        oracle.decode(sd, codes)
+        best = min(best, time.perf_counter() - t0)
+    return sample_images * H * W / best / 1e6, best, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU PyTorch path (oracle restatement) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 4
+    times = []
+    import torch
+    from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
+    from oracle import mcquic_oracle as oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synthetic_state_dict(CHANNEL, M, K, seed=0)
+    x = uniform((sample, 3, H, W), "bench.image", 0)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        oracle.decode(sd, oracle.encode(sd, x))
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = sample * H * W * len(times) / total / 1e6
+    desc = f"{sample} of the 64 images of a step (CPU time scales linearly in batch, SURVEY.md section 8d)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "qp=1 Compressor(128,1,[8192,2048,512]) encode+decode, 256x256 RGB, CPU PyTorch fp32",
+                   "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mcquic_b200 import Compressor, _lib
+    from mcquic_b200.dist import gather_histograms
+    from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = Compressor(CHANNEL, M, K).eval()
+    model.load_state_dict(synthetic_state_dict(CHANNEL, M, K, seed=0))
+    model = model.to(dev)
+    x_host = uniform((BATCH, 3, H, W), f"bench.image.{rank}", 0).pin_memory()
+    x_dev = x_host.to(dev)
+    hist_total = sum(M * k for k in K)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_device():
+        hist = torch.zeros(hist_total, dtype=torch.int32, device=dev)
+        codes = model.encode(x_dev, hist=hist)
+        ghist = gather_histograms(hist) if world > 1 else hist
+        xhat = model.decode(codes)
+        return codes, xhat, ghist
+
+    xhat_host = torch.empty((BATCH, 3, H, W), dtype=torch.float32).pin_memory()
+    codes_host = [torch.empty((BATCH, M, H >> (4 + l), W >> (4 + l)), dtype=torch.int64).pin_memory() for l in range(len(K))]
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        hist = torch.zeros(hist_total, dtype=torch.int32, device=dev)
+        codes = model.encode(xd, hist=hist)
+        if world > 1:
+            gather_histograms(hist)
+        for dst, src in zip(codes_host, codes):
+            dst.copy_(src, non_blocking=True)
+        xhat = model.decode(codes)
+        xhat_host.copy_(xhat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(xhat_host[0, 0, 0, 0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """sum of per-step device durations (ms); L2 flushed (untimed) before every step"""
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        step_e2e()
+    barrier()
+    launches_before = _lib.launch_count() + model.graph_launches
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ms = timed(step_device, args.steps)
+        barrier()
+        launches = _lib.launch_count() + model.graph_launches - launches_before
+        ms_e2e = timed(step_e2e, args.steps)
+        barrier()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    pix = world * BATCH * H * W * args.steps
+    value = pix / (ms * 1e-3) / 1e6
+    e2e_value = pix / (ms_e2e * 1e-3) / 1e6
+
+    out = None
+    if rank == 0:
+        # ---- roofline leg: one eager step with every conv launch bracketed by events (single stream)
+        peaks, peak_src = _peaks()
+        model.use_graphs = False
+        model.engine.multistream = False
+        prof = []
+        model.engine.profile = prof
+        codes = model.encode(x_dev)
+        model.decode(codes)
+        torch.cuda.synchronize()
+        model.engine.profile = None
+        model.use_graphs = True
+        model.engine.multistream = True
+        tc = [p for p in prof if p["impl"] == _lib.IMPL_TCGEN05]
+        t_tc = sum(p["ev"][0].elapsed_time(p["ev"][1]) for p in tc) * 1e-3
+        f_tc = sum(p["flops"] for p in tc)
+        f_exec = sum(p["flops"] * p["passes"] for p in tc)
+        achieved = f_tc / t_tc / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "conv_tc_kernel<1|3> (all %d launches of one step)" % len(tc),
+                    "executed_tflops": f_exec / t_tc / 1e12, "executed_frac": f_exec / t_tc / 1e12 / peak,
+                    "conv_ms_per_step": t_tc * 1e3, "conv_share_of_step": t_tc * 1e3 / (ms / args.steps),
+                    "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained (fp16 dense = bf16 dense)",
+                    "note": "achieved counts algorithmic (fp32-semantics) FLOPs; the 3-pass split-fp16 encode executes 3x of them"}
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as fp:
+                roofline["traffic"] = json.load(fp).get("dram_bytes_per_step")
+        cpu = None
+        if world == 1:
+            cpu_val, cpu_s, cores = _cpu_oracle_throughput(sample_images=2, repeats=3)
+            cpu = {"value": cpu_val, "unit": "MPix/s", "cores": cores, "kind": "port",
+                   "sample": f"2 images encode+decode, best of 3 ({cpu_s:.2f} s each), oracle/mcquic_oracle.py"}
+        out = {
+            "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 split x3 (fp32-grade) encode / f16 x1 decode, f32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": "qp=1 Compressor(128,1,[8192,2048,512]) encode+decode, batch 64x3x256x256 per GPU",
+                       "images_per_gpu": BATCH, "l2": "256 MB flush before every timed step", "cuda_graphs": True,
+                       "collective": "all_gather int32[10752] code histogram per step" if world > 1 else "none (1 GPU)"},
+            "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": xhat_host.numel() * 4 + sum(c.numel() * 8 for c in codes_host),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "alg_tflops": pix * ALG_GFLOP_PER_IMAGE / (H * W) * 1e9 / (ms * 1e-3) / 1e12,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,11 +42,22 @@ struct ConvArgs {
   int tap_c[9], tap_dx[9], tap_py[9], tap_dy[9];
 };
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// FAST = SFU approximations (ex2.approx / rcp.approx / rsqrt.approx, a few ulp): used by the 1-pass (TF32-grade)
+// path where operand rounding (2^-11) dominates anyway; the 3-pass path keeps IEEE division / sqrt and expf.
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_f(float x) {
+  if constexpr (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
+  return 1.0f / (1.0f + expf(-x));
+}
+template <bool FAST>
+__device__ __forceinline__ float silu_f(float x) {
+  if constexpr (FAST) return __fdividef(x, 1.0f + __expf(-x));
+  return x / (1.0f + expf(-x));
+}
 
+template <bool FAST>
 __device__ __forceinline__ float apply_act(float y, int act) {
-  if (act == MCQ_ACT_SILU) return silu_f(y);
+  if (act == MCQ_ACT_SILU) return silu_f<FAST>(y);
   if (act == MCQ_ACT_SQUARE) return y * y;
   return y;
 }
@@ -64,12 +75,12 @@ __device__ __forceinline__ void split_f32(float a, unsigned short& hi, unsigned 
   lo = f2h_sat((a - h2f(hi)) * kLoScale);
 }
 
-template <int NV>
+template <int NV, bool FAST = false>
 __device__ __forceinline__ void store_planes(__half* hi_p, __half* lo_p, size_t off, const float (&y)[NV], int act) {
   static_assert(NV == 4 || NV == 8, "NV");
   unsigned short h[NV], l[NV];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) split_f32(apply_act(y[j], act), h[j], l[j]);
+  for (int j = 0; j < NV; ++j) split_f32(apply_act<FAST>(y[j], act), h[j], l[j]);
   if constexpr (NV == 8) {
     uint4 ph = make_uint4(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16), h[4] | (uint32_t(h[5]) << 16),
                           h[6] | (uint32_t(h[7]) << 16));
@@ -100,7 +111,7 @@ __device__ __forceinline__ void load_f32v(const float* p, size_t off, float (&r)
 
 // Fused epilogue for NV consecutive GEMM columns [c0, c0+NV) of output pixel (n, oy, ox).
 // v[] = accumulator * w_scale (bias NOT yet added).  c0 % NV == 0.
-template <int NV>
+template <int NV, bool FAST = false>
 __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy, int ox, int c0, float (&v)[NV]) {
   if (c0 >= p.cout) return;
   if (p.store == MCQ_STORE_SHUFFLE_NCHW) {
@@ -148,14 +159,19 @@ __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy,
     load_f32v<NV>(p.res1, off, r);
     load_f32v<NV>(p.aux, off, a);
 #pragma unroll
-    for (int j = 0; j < NV; ++j) y[j] = a[j] * sigmoid_f(y[j]) + r[j];
+    for (int j = 0; j < NV; ++j) y[j] = a[j] * sigmoid_f<FAST>(y[j]) + r[j];
   } else {
     float a[NV];
     load_f32v<NV>(p.aux, off, a);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const float s = sqrtf(y[j]);
-      y[j] = (p.mode == MCQ_EPI_GDN) ? a[j] * (1.0f / s) : a[j] * s;
+      if constexpr (FAST) {
+        const float rs = rsqrtf(y[j]);
+        y[j] = (p.mode == MCQ_EPI_GDN) ? a[j] * rs : a[j] * (y[j] * rs);
+      } else {
+        const float s = sqrtf(y[j]);
+        y[j] = (p.mode == MCQ_EPI_GDN) ? a[j] * (1.0f / s) : a[j] * s;
+      }
     }
   }
   if (p.out_f32) {
@@ -163,8 +179,8 @@ __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy,
     for (int j = 0; j < NV; j += 4)
       *reinterpret_cast<float4*>(p.out_f32 + off + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
   }
-  if (p.o0_hi) store_planes<NV>(p.o0_hi, p.o0_lo, off, y, p.o0_act);
-  if (p.o1_hi) store_planes<NV>(p.o1_hi, p.o1_lo, off, y, p.o1_act);
+  if (p.o0_hi) store_planes<NV, FAST>(p.o0_hi, p.o0_lo, off, y, p.o0_act);
+  if (p.o1_hi) store_planes<NV, FAST>(p.o1_hi, p.o1_lo, off, y, p.o1_act);
 }
 
 }  // namespace mcq

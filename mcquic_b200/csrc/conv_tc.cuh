@@ -9,8 +9,9 @@
 // * B (packed weights [cout_pad, taps*cin]) is a 2-D TMA box per (tap, 64-channel chunk).
 // * One elected thread issues tcgen05.mma (kind::f16, M=128, N=bn, K=16) into TMEM accumulators.
 //   PASSES==3: acc_hh += Ahi*Bhi, acc_lo += Ahi*Blo + Alo*Bhi (split-fp16, fp32-grade); PASSES==1: Ahi*Bhi.
-// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
-//   (tcgen05.ld -> registers -> fused epilogue -> global).  The accumulator is double-buffered in TMEM
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..17 = epilogue
+//   (tcgen05.ld -> registers -> fused epilogue -> global; warp w owns TMEM lanes 32*(w%4).. and every 4th
+//   32-column chunk, so 16 warps share one 128x128 tile).  The accumulator is double-buffered in TMEM
 //   when it fits, so the epilogue of tile i overlaps the MMAs of tile i+1.  Persistent CTAs, static schedule.
 #pragma once
 #include <cuda.h>
@@ -19,7 +20,8 @@
 
 namespace mcq {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 16;                 // 4 TMEM lane quarters x 4 column groups
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                        // fp16 elements per stage along K (= 128 B swizzle span)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;    // 16 KB
@@ -156,7 +158,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(b), TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -259,7 +261,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
-    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware rule: warp % 4)
+    const int cg = (warp - 2) >> 2;     // column group: this warp handles 32-column chunks cg, cg+4, ...
     const int row = q * 32 + lane;      // GEMM row inside the tile = pixel (x fastest, then y, then n)
     const int ix = row % p.tw;
     const int iy = (row / p.tw) % p.th;
@@ -279,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(tfull_bar(buf), use & 1u, 4);
       tc_fence_after();
       const uint32_t t_hh = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      for (int cc = 0; cc < bn; cc += 32) {
+      for (int cc = cg * 32; cc < bn; cc += 128) {
         uint32_t r[32];
         float v[32];
         tmem_ld32(t_hh + (uint32_t)cc, r);
@@ -297,10 +300,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (valid) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
+            if (cc + g * 8 >= bn) break;  // N tiles narrower than a 32-column chunk (bn = 16)
             float vv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) vv[j] = v[g * 8 + j];
-            epilogue_store<8>(p, n, oy, ox, ct * bn + cc + g * 8, vv);
+            epilogue_store<8, PASSES == 1>(p, n, oy, ox, ct * bn + cc + g * 8, vv);
           }
         }
       }

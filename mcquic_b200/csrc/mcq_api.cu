@@ -174,8 +174,6 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   if (bn % 16 != 0 || bn > 256) return MCQ_ERR_UNSUPPORTED;
   if (bn > 32 && bn % 32 != 0) return MCQ_ERR_UNSUPPORTED;
   if ((a.passes == 3 ? 2 : 1) * bn > (int)TC_TMEM_COLS) return MCQ_ERR_UNSUPPORTED;
-  a.bn = bn;
-  a.tiles_c = a.cout_pad / bn;
   // ---- M tile: (tw x th x tn) box of output pixels, 128 rows
   a.tw = pow2_ceil(a.wout) < 16 ? pow2_ceil(a.wout) : 16;
   const int th_max = TC_BM / a.tw;
@@ -184,6 +182,12 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   a.tiles_x = (a.wout + a.tw - 1) / a.tw;
   a.tiles_y = (a.hout + a.th - 1) / a.th;
   a.tiles_n = (a.n + a.tn - 1) / a.tn;
+  // small feature maps: narrow the N tile so that the few pixel tiles still spread over the SMs
+  // (these layers are latency-bound; re-reading A per N tile is free compared with idle SMs)
+  const int tiles_m = a.tiles_x * a.tiles_y * a.tiles_n;
+  while (tiles_m * (a.cout_pad / bn) < (num_sms() * 2) / 3 && bn >= 32 && (bn / 2) % 16 == 0) bn /= 2;
+  a.bn = bn;
+  a.tiles_c = a.cout_pad / bn;
   // ---- taps
   const int pad = a.ksize / 2;
   for (int t = 0; t < a.ksize * a.ksize; ++t) {

@@ -103,13 +103,13 @@ __global__ void nchw_to_nhwc_kernel(const LayoutArgs a) {
       if (a.out_f32) a.out_f32[off] = y;
       if (a.o0_hi) {
         unsigned short h, l;
-        split_f32(apply_act(y, a.o0_act), h, l);
+        split_f32(apply_act<false>(y, a.o0_act), h, l);
         a.o0_hi[off] = __ushort_as_half(h);
         if (a.o0_lo) a.o0_lo[off] = __ushort_as_half(l);
       }
       if (a.o1_hi) {
         unsigned short h, l;
-        split_f32(apply_act(y, a.o1_act), h, l);
+        split_f32(apply_act<false>(y, a.o1_act), h, l);
         a.o1_hi[off] = __ushort_as_half(h);
         if (a.o1_lo) a.o1_lo[off] = __ushort_as_half(l);
       }

@@ -98,12 +98,37 @@ class Engine:
         self.impl = {"tcgen05": _lib.IMPL_TCGEN05, "simt": _lib.IMPL_SIMT}[impl]
         self.passes = 3
         self._packed: Dict[Tuple[int, int], Tuple[Tuple, PackedConv]] = {}
+        # independent sub-graphs (the two AttentionBlock branches, quantizationHead || latentHead,
+        # dequantizationHead || sideHead) run on side streams: on <=16x16 feature maps one conv cannot fill 148 SMs
+        self.multistream = not self.emulated
+        self._side_streams: List["torch.cuda.Stream"] = []
+        self._depth = 0
+        # when a list, every conv launch is bracketed by CUDA events and logged (bench.py's roofline leg)
+        self.profile: Optional[list] = None
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
         if self.emulated:
             return ctypes.c_void_p(0)
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def parallel(self, fa, fb):
+        """Run the independent closures fa and fb concurrently (fb on a side stream); returns (fa(), fb())."""
+        if not self.multistream:
+            return fa(), fb()
+        while len(self._side_streams) <= self._depth:
+            self._side_streams.append(torch.cuda.Stream())
+        main, side = torch.cuda.current_stream(), self._side_streams[self._depth]
+        self._depth += 1
+        try:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                rb = fb()
+            ra = fa()
+            main.wait_stream(side)
+        finally:
+            self._depth -= 1
+        return ra, rb
 
     def _planes(self, n, h, w, c, device) -> Planes:
         hi = torch.empty((n, h, w, c), dtype=torch.float16, device=device)
@@ -177,7 +202,15 @@ class Engine:
                 p.out1_hi, p.out1_lo, p.out1_act = _ptr(slots[1][0][0]), _ptr(slots[1][0][1]), slots[1][1]
         p.passes = self.passes if a[1] is not None else 1
         p.impl = self.impl if (pc.cin % 64 == 0) else _lib.IMPL_SIMT
+        if self.profile is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         _lib.check(self.lib.mcq_conv2d(ctypes.byref(p), self._stream()), "mcq_conv2d")
+        if self.profile is not None:
+            ev1.record()
+            self.profile.append({"flops": 2.0 * x.n * (x.h // pc.stride) * (x.w // pc.stride) * pc.cout * pc.cin * pc.ksize ** 2,
+                                 "passes": p.passes, "impl": p.impl, "ev": (ev0, ev1),
+                                 "shape": (x.n, x.h, x.w, pc.cin, pc.cout, pc.ksize, pc.stride)})
         del keep
         return out
 
@@ -211,12 +244,19 @@ class Engine:
         return self.conv(self._packed_for(mod._branch[3]), t.raw, t, want, res1=s.f32)
 
     def attention_block(self, mod: AttentionBlock, x: Act, want: Set[str]) -> Act:
-        a = x
-        for i in range(3):
-            a = self.residual_block(mod._mainBranch[i], a, {"f32", "silu"} if i < 2 else {"f32"})
-        b = x
-        for i in range(3):
-            b = self.residual_block(mod._sideBranch[i], b, {"f32", "silu"} if i < 2 else {"raw"})
+        def main_branch():
+            a = x
+            for i in range(3):
+                a = self.residual_block(mod._mainBranch[i], a, {"f32", "silu"} if i < 2 else {"f32"})
+            return a
+
+        def side_branch():
+            b = x
+            for i in range(3):
+                b = self.residual_block(mod._sideBranch[i], b, {"f32", "silu"} if i < 2 else {"raw"})
+            return b
+
+        a, b = self.parallel(main_branch, side_branch)
         return self.conv(self._packed_for(mod._sideBranch[3]), b.raw, b, want, mode=_lib.EPI_GATE, res1=x.f32,
                          aux=a.f32)
 

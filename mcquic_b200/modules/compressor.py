@@ -34,6 +34,10 @@ class BaseCompressor(nn.Module):
         self._engine: Optional[Engine] = None
         self.encode_passes = 3  # split-fp16 x3: fp32-grade, code indices match the fp32 reference
         self.decode_passes = 1  # single fp16 pass: TF32-grade, pixels within 1e-3
+        # encode/decode are ~170 dependent launches each: replay them as one CUDA graph per input shape
+        self.use_graphs = True
+        self._graphs = {}
+        self.graph_launches = 0  # kernels launched through graph replays (the library counts eager launches)
 
     @property
     def QuantizationParameter(self) -> str:
@@ -67,10 +71,22 @@ class BaseCompressor(nn.Module):
         if not x.is_cuda and not self.engine.emulated:
             raise RuntimeError("mcquic_b200 runs on CUDA tensors only (there is no CPU fallback)")
 
-    @torch.no_grad()
-    def encode(self, x: torch.Tensor, hist: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
-        """compressor.py:79-88.  `hist`: optional flat int32 [sum_l m*k_l] code histogram, accumulated in place."""
-        self._check_image(x)
+    def invalidate(self):
+        """Drop captured graphs and repacked weights (call after changing parameters in place)."""
+        self._graphs.clear()
+        if self._engine is not None:
+            self._engine._packed.clear()
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    # ------------------------------------------------------------------ eager bodies
+    def _encode_eager(self, x: torch.Tensor, hist: Optional[torch.Tensor]) -> List[torch.Tensor]:
         eng = self.engine
         eng.passes = self.encode_passes
         n, _, h, w = x.shape
@@ -78,16 +94,87 @@ class BaseCompressor(nn.Module):
         y = eng.run_seq(list(self._encoder)[1:], y0, self._quantizer.first_needs(eng))
         return self._quantizer.encode_act(eng, y, hist)
 
+    def _decode_eager(self, codes: List[torch.Tensor], status: torch.Tensor) -> torch.Tensor:
+        eng = self.engine
+        eng.passes = self.decode_passes
+        yHat = self._quantizer.decode_act(eng, codes, eng.needs_of(self._decoder[0]), status)
+        return eng.run_seq(list(self._decoder), yHat, set()).f32
+
+    def _graph(self, key, make_static, body):
+        """Capture `body(*static)` once per key; returns (graph, static inputs, static outputs, #launches)."""
+        entry = self._graphs.get(key)
+        if entry is None:
+            from .. import _lib
+            static = make_static()
+            cur = torch.cuda.current_stream()
+            warm = torch.cuda.Stream()
+            warm.wait_stream(cur)
+            with torch.cuda.stream(warm):       # eager warm-up: repacks weights, sets kernel attributes
+                body(*static)
+            cur.wait_stream(warm)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                out = body(*static)
+            entry = (graph, static, out, _lib.launch_count() - before)
+            self._graphs[key] = entry
+        return entry
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, hist: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        """compressor.py:79-88.  `hist`: optional flat int32 [sum_l m*k_l] code histogram, accumulated in place."""
+        self._check_image(x)
+        if not (self.use_graphs and x.is_cuda):
+            return self._encode_eager(x, hist)
+        x = x.contiguous().float()
+        total = sum(self._quantizer._m * k for k in self._quantizer._k)
+
+        def make_static():
+            return [torch.empty_like(x), torch.zeros(total, dtype=torch.int32, device=x.device)]
+
+        def body(sx, sh):
+            sh.zero_()
+            return self._encode_eager(sx, sh)
+
+        graph, (sx, sh), codes, launches = self._graph(("enc", tuple(x.shape), self.encode_passes, x.device), make_static, body)
+        sx.copy_(x)
+        graph.replay()
+        self.graph_launches += launches
+        if hist is not None:
+            hist += sh
+        return [c.clone() for c in codes]
+
     @torch.no_grad()
     def decode(self, codes: List[torch.Tensor]) -> torch.Tensor:
         """compressor.py:114-117 (no crop; `decompress` crops upstream)."""
         if len(codes) == 0:
             raise RuntimeError("Length of codes is 0.")
-        eng = self.engine
-        eng.passes = self.decode_passes
-        status = torch.zeros(1, dtype=torch.int32, device=codes[0].device)
-        yHat = self._quantizer.decode_act(eng, codes, eng.needs_of(self._decoder[0]), status)
-        out = eng.run_seq(list(self._decoder), yHat, set()).f32
+        dev = codes[0].device
+        if not (self.use_graphs and codes[0].is_cuda):
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            out = self._decode_eager(codes, status)
+        else:
+            codes = [c.contiguous() for c in codes]
+            for c in codes:
+                if c.dtype != torch.int64 or c.dim() != 4:
+                    raise RuntimeError(f"codes must be int64 [n, m, h, w], got {c.dtype} {tuple(c.shape)}")
+
+            def make_static():
+                return [[torch.empty_like(c) for c in codes], torch.zeros(1, dtype=torch.int32, device=dev)]
+
+            def body(sc, st):
+                st.zero_()
+                return self._decode_eager(sc, st)
+
+            key = ("dec", tuple(tuple(c.shape) for c in codes), self.decode_passes, dev)
+            graph, (sc, status), sout, launches = self._graph(key, make_static, body)
+            for dst, src in zip(sc, codes):
+                dst.copy_(src)
+            graph.replay()
+            self.graph_launches += launches
+            out = sout.clone()
         if int(status.item()) != 0:
             raise RuntimeError("code index out of range for its codebook")
         return out

@@ -158,12 +158,19 @@ class _quantizerEncoder(nn.Module):
     def encode_act(self, eng: Engine, x: Act, next_needs, hist: Optional[torch.Tensor]):
         """quantizer.py:310-318 on engine activations: returns (residual Act or None, codes)."""
         z = eng.run_seq(self._latentStageEncoder, x, {"f32", "silu"})
-        head = eng.run_seq(self._quantizationHead, z, {"f32"})
-        code = self._quantizer.encode_nhwc(head.f32, head.n, head.h, head.w, hist, eng)
         if self._latentHead is None:
-            return None, code
-        deq = self._dequantizer.decode_act(code, {"f32"}, eng)
-        return eng.run_seq(self._latentHead, z, next_needs, tail=(deq.f32, -1.0)), code
+            head = eng.run_seq(self._quantizationHead, z, {"f32"})
+            return None, self._quantizer.encode_nhwc(head.f32, head.n, head.h, head.w, hist, eng)
+        latent = list(self._latentHead)
+
+        def quantize():
+            head = eng.run_seq(self._quantizationHead, z, {"f32"})
+            code = self._quantizer.encode_nhwc(head.f32, head.n, head.h, head.w, hist, eng)
+            return code, self._dequantizer.decode_act(code, {"f32"}, eng)
+
+        # all of latentHead but its last conv is independent of the code (quantizer.py:313-316)
+        (code, deq), zl = eng.parallel(quantize, lambda: eng.run_seq(latent[:-1], z, eng.needs_of(latent[-1])))
+        return eng.run(latent[-1], zl, next_needs, tail=(deq.f32, -1.0)), code
 
 
 class _quantizerDecoder(nn.Module):
@@ -180,8 +187,10 @@ class _quantizerDecoder(nn.Module):
         q0 = self._dequantizer.decode_act(code, eng.needs_of(self._dequantizationHead[0]), eng, status)
         head_needs = eng.needs_of(self._restoreHead[0])
         if self._sideHead is not None:
-            side = eng.run_seq(self._sideHead, former, {"f32"})
-            q = eng.run_seq(self._dequantizationHead, q0, head_needs, tail=(side.f32, 1.0))
+            head = list(self._dequantizationHead)
+            qh, side = eng.parallel(lambda: eng.run_seq(head[:-1], q0, eng.needs_of(head[-1])),
+                                    lambda: eng.run_seq(self._sideHead, former, {"f32"}))
+            q = eng.run(head[-1], qh, head_needs, tail=(side.f32, 1.0))
         else:
             q = eng.run_seq(self._dequantizationHead, q0, head_needs)
         return eng.run_seq(self._restoreHead, q, next_needs)

@@ -1,0 +1,89 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference through
+oracle/ref_import.py) on deterministic inputs.  Run here (the reference tree does not exist on the GPU box):
+
+    python oracle/gen_golden.py
+
+Inputs and weights are *not* stored: they come from the counter-hash generator in
+mcquic_b200/utils/synthetic.py and are regenerated bit-identically by the tests.  Stored: the reference's
+outputs (all code indices, pixels -- full for the small case, a strided sample + statistics for qp=1), the
+top-2 distance margins of every code (so a flipped near-tie can be told from a bug) and sha256 digests.
+TEST INFRASTRUCTURE ONLY.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform  # noqa: E402
+from oracle import mcquic_oracle as O  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# name -> (channel, m, k, n, h, w, pixel sample stride)
+CASES = {
+    "compressor_small": (64, 2, [256, 128, 64], 2, 200, 136, 2),        # padded to 256x256 by AlignedPadding
+    "compressor_qp1_256": (128, 1, [8192, 2048, 512], 1, 256, 256, 4),   # BASELINE.json configs[0]
+    "compressor_c192_m6": (192, 6, [2048, 2048, 2048], 1, 128, 128, 4),  # "qp=3" shape of configs[2], one tile
+}
+
+
+def synthetic_image(n, h, w, seed):
+    return uniform((n, 3, h, w), "image", seed)
+
+
+def sha(t: torch.Tensor) -> str:
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref_import.load()
+    from mcquic.modules.compressor import Compressor
+    from mcquic.modules.quantizer import _multiCodebookDeQuantization, _multiCodebookQuantization
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_num_threads(8)
+    for name, (c, m, k, n, h, w, stride) in CASES.items():
+        sd = synthetic_state_dict(c, m, k, seed=0)
+        model = Compressor(c, m, list(k)).eval()
+        model.load_state_dict(sd)
+        x = synthetic_image(n, h, w, seed=1)
+        with torch.inference_mode():
+            codes = model.encode(x)
+            xhat = model.decode(codes)
+        _, margins = O.encode(sd, x, with_margin=True)
+        rec = {"config": np.array([c, m, n, h, w, stride] + list(k), dtype=np.int64),
+               "xhat_sample": xhat[..., ::stride, ::stride].numpy().astype(np.float32),
+               "xhat_stats": np.array([float(xhat.min()), float(xhat.max()), float(xhat.mean()), float(xhat.std())]),
+               "xhat_sha256": np.array(sha(xhat)), "codes_sha256": np.array(sha(torch.cat([q.flatten() for q in codes])))}
+        for lv, (q, mg) in enumerate(zip(codes, margins)):
+            rec[f"codes_{lv}"] = q.numpy().astype(np.int32)
+            rec[f"margin_{lv}"] = mg.numpy().astype(np.float32)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, [tuple(q.shape) for q in codes], tuple(xhat.shape), "min margin", min(float(mg.min()) for mg in margins))
+
+    # ---- quantizer alone (BASELINE.json configs[2]: M=6, K=2048, d=32), reference module on seeded latents
+    m, k, d, n, h, w = 6, 2048, 32, 4, 32, 32
+    cb = uniform((m, k, d), "vq.codebook", 3) * ((2.0 / (5 * d)) ** 0.5 * 3 ** 0.5)
+    x = uniform((n, m * d, h, w), "vq.latent", 3) * 0.26   # std 0.15 like observed latents
+    q = _multiCodebookQuantization(torch.nn.Parameter(cb.clone()), 0.0)
+    dq = _multiCodebookDeQuantization(q._codebook)
+    with torch.inference_mode():
+        code = q.encode(x)
+        deq = dq.decode(code)
+        logit = q._logit(x) * q._bound(q._temperature)
+    np.savez_compressed(os.path.join(OUT, "vq_m6_k2048_d32.npz"),
+                        config=np.array([m, k, d, n, h, w], dtype=np.int64), codes=code.numpy().astype(np.int32),
+                        margin=O.vq_margin(x, cb).numpy().astype(np.float32),
+                        deq_sha256=np.array(sha(deq)), logit_sample=logit[:, :, ::8, ::8, ::64].numpy())
+    print("vq", tuple(code.shape), "min margin", float(O.vq_margin(x, cb).min()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,111 @@
+"""Parity of the convolution kernels (tcgen05 and SIMT) through the C ABI against an fp64 torch evaluation of the
+same operands.  Tolerances (relative to the largest expected magnitude):
+  fp32 outputs, 3-pass split-fp16 or SIMT : 1e-5   (fp32-grade: measured ~2e-6 on B200)
+  fp32 outputs, 1-pass                    : 1e-5   (vs the same hi-only operands; operand rounding is not kernel error)
+  split-fp16 plane outputs                : 2^-19 with the lo plane (3-pass), 2^-10 hi only (1-pass)
+"""
+import pytest
+import torch
+
+from convcase import compare, run_case
+from mcquic_b200 import _lib
+from mcquic_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+
+
+def _tol(name, passes):
+    if name == "f32":
+        return TOL_F32
+    return 2.0 ** -19 + TOL_F32 if passes == 3 else 2.0 ** -10
+
+
+def _check(impl, want=("f32",), **kw):
+    eng = Engine(impl)
+    out, exp, _ = run_case(eng, want=want, **kw)
+    err = compare(out, exp, want, kw.get("passes", 3))
+    assert eng.lib.mcq_device_error_flag() == 0
+    for name, e in err.items():
+        assert e <= _tol(name, kw.get("passes", 3)), (name, e, kw)
+
+
+SHAPES = [
+    dict(n=1, h=16, w=16, cin=128, cout=128),                 # one tile
+    dict(n=4, h=64, w=64, cin=128, cout=128),                 # multi-tile, persistent loop, TMEM double buffering
+    dict(n=4, h=8, w=8, cin=128, cout=128),                   # two images per tile
+    dict(n=5, h=4, w=4, cin=128, cout=128),                   # eight images per tile, ragged batch
+    dict(n=3, h=2, w=2, cin=128, cout=128),                   # 2x2 maps (128-pixel inputs, level 2)
+    dict(n=2, h=24, w=40, cin=128, cout=128),                 # ragged H and W
+    dict(n=3, h=6, w=12, cin=128, cout=128),                  # non power-of-two maps (384x768 inputs)
+    dict(n=2, h=16, w=16, cin=192, cout=192),                 # C=192 (qp>=3 models): N tile 192
+    dict(n=2, h=16, w=16, cin=64, cout=64),
+    dict(n=2, h=32, w=32, cin=128, cout=128, stride=2),       # 5-D parity view
+    dict(n=3, h=8, w=8, cin=128, cout=128, stride=2),
+    dict(n=1, h=48, w=80, cin=128, cout=128, stride=2),
+    dict(n=2, h=16, w=16, cin=128, cout=128, ksize=1),
+]
+
+
+@pytest.mark.parametrize("passes", [3, 1])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "-".join(f"{k}{v}" for k, v in s.items()))
+def test_tcgen05_conv_shapes(shape, passes):
+    _check("tcgen05", passes=passes, **shape)
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_epilogue_modes(impl):
+    base = dict(n=2, h=16, w=16, cin=128, cout=128)
+    _check(impl, want=("f32", "silu"), ksize=1, mode=_lib.EPI_GATE, **base)          # AttentionBlock tail
+    _check(impl, want=("raw",), ksize=1, mode=_lib.EPI_GDN, **base)                   # GDN
+    _check(impl, want=("raw",), ksize=1, mode=_lib.EPI_IGDN, **base)                  # inverse GDN
+    _check(impl, want=("f32", "raw"), use_res1=True, res1_scale=-1.0, use_res2=True, **base)  # z - deq, q + side
+    _check(impl, want=("silu", "sq"), passes=1, **base)
+    _check(impl, want=("f32", "sq"), n=2, h=16, w=16, cin=128, cout=512, store=_lib.STORE_SHUFFLE_NHWC)
+    _check(impl, n=2, h=32, w=32, cin=128, cout=12, store=_lib.STORE_SHUFFLE_NCHW)   # last layer, NCHW pixels
+    _check(impl, n=2, h=32, w=32, cin=128, cout=12, store=_lib.STORE_SHUFFLE_NCHW, passes=1)
+
+
+def test_simt_serves_channel_counts_the_tensor_core_tiling_does_not():
+    _check("simt", n=1, h=9, w=7, cin=32, cout=40)
+    _check("simt", n=2, h=16, w=24, cin=64, cout=64, stride=2)
+    eng = Engine("tcgen05")
+    with pytest.raises(RuntimeError, match="not supported|bad argument"):
+        p = _lib.ConvParams()
+        x = torch.zeros(1, 8, 8, 32, dtype=torch.float16, device="cuda")
+        w = torch.zeros(32, 9 * 32, dtype=torch.float16, device="cuda")
+        b = torch.zeros(32, device="cuda")
+        o = torch.zeros(1, 8, 8, 32, device="cuda")
+        p.a_hi = p.a_lo = x.data_ptr(); p.w_hi = p.w_lo = w.data_ptr(); p.bias = b.data_ptr(); p.out_f32 = o.data_ptr()
+        p.n, p.hin, p.win, p.cin, p.cout, p.cout_pad, p.ksize, p.stride, p.passes = 1, 8, 8, 32, 32, 32, 3, 1, 3
+        p.w_scale = 1.0
+        p.impl = _lib.IMPL_TCGEN05
+        import ctypes
+        _lib.check(eng.lib.mcq_conv2d(ctypes.byref(p), None), "mcq_conv2d")
+
+
+def test_tcgen05_equals_simt_on_a_full_size_layer():
+    """same operands, two independent kernels (tensor cores vs fp32 FFMA): agree to fp32 rounding at N=64, 64x64"""
+    kw = dict(n=64, h=64, w=64, cin=128, cout=128, passes=3, want=("f32",))
+    a, _, _ = run_case(Engine("tcgen05"), **kw)
+    b, _, _ = run_case(Engine("simt"), **kw)
+    scale = float(b.f32.abs().max())
+    assert float((a.f32 - b.f32).abs().max()) / scale <= TOL_F32
+
+
+def test_linearity_at_full_size():
+    """size-independent property: conv(x1 + x2) - bias == (conv(x1) - bias) + (conv(x2) - bias) up to rounding"""
+    from convcase import make_planes
+    from mcquic_b200.engine import Act, pack_conv
+    g = torch.Generator().manual_seed(5)
+    n, h, w, c = 64, 32, 32, 128
+    x1 = torch.randn(n, h, w, c, generator=g).cuda()
+    x2 = torch.randn(n, h, w, c, generator=g).cuda()
+    wt = ((torch.rand(c, c, 3, 3, generator=g) * 2 - 1) / (9 * c) ** 0.5).cuda()
+    pc = pack_conv(wt, torch.zeros(c).cuda(), 1, 0, "cuda")
+    eng = Engine("tcgen05")
+    eng.passes = 3
+    f = lambda x: eng.conv(pc, make_planes(x, 3), Act(n, h, w, c), {"f32"}).f32
+    lhs, rhs = f(x1 + x2), f(x1) + f(x2)
+    assert float((lhs - rhs).abs().max()) <= 2e-5 * float(rhs.abs().max())

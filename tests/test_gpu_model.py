@@ -1,0 +1,120 @@
+"""End-to-end parity of Compressor.encode/decode on the GPU against the committed golden vectors (reference
+outputs) and the oracle: code indices bit-exact, pixels within 1e-3 absolute (north_star), plus size-independent
+properties at the benchmark size."""
+import pytest
+import torch
+
+from common import code_report, golden_codes, golden_inputs, load_golden
+from mcquic_b200 import Compressor, _lib
+from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
+from oracle import mcquic_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PIXEL_TOL = 1e-3   # BASELINE.json north_star: reconstructed pixels within 1e-3 abs fp32
+
+
+def _model(cfg, sd, impl="tcgen05"):
+    model = Compressor(cfg["channel"], cfg["m"], cfg["k"]).eval()
+    model.load_state_dict(sd)
+    model = model.cuda()
+    model.set_impl(impl)
+    return model
+
+
+@pytest.mark.parametrize("name", ["compressor_small", "compressor_qp1_256", "compressor_c192_m6"])
+@pytest.mark.parametrize("graphs", [False, True])
+def test_against_reference_golden(name, graphs):
+    g, cfg = load_golden(name)
+    sd, x = golden_inputs(cfg)
+    model = _model(cfg, sd)
+    model.use_graphs = graphs
+    before = _lib.launch_count() + model.graph_launches
+    codes = model.encode(x.cuda())
+    if graphs:
+        codes = model.encode(x.cuda())                     # second call = pure graph replay
+    ref = golden_codes(g, len(cfg["k"]))
+    margins = [g[f"margin_{lv}"] for lv in range(len(ref))]
+    flips, total, at = code_report(codes, ref, margins)
+    assert flips == 0, f"{flips}/{total} code indices differ from the reference; margins there: {at}"
+    assert all(c.dtype == torch.int64 and c.is_cuda and c.is_contiguous() for c in codes)
+    xhat = model.decode([c.cuda() for c in ref])
+    s = cfg["stride"]
+    err = float((xhat.cpu()[..., ::s, ::s] - torch.from_numpy(g["xhat_sample"])).abs().max())
+    assert err <= PIXEL_TOL, err
+    assert _lib.launch_count() + model.graph_launches - before >= 340     # the CUDA path really ran
+    assert model.engine.lib.mcq_device_error_flag() == 0
+
+
+def test_simt_and_tcgen05_agree_with_oracle_including_psnr():
+    g, cfg = load_golden("compressor_qp1_256")
+    sd, x = golden_inputs(cfg)
+    ref = O.encode(sd, x)
+    xref = O.decode(sd, ref)
+    for impl in ("simt", "tcgen05"):
+        model = _model(cfg, sd, impl)
+        codes = model.encode(x.cuda())
+        assert code_report(codes, ref)[0] == 0
+        for passes, tol in ((3, 5e-6), (1, PIXEL_TOL)):
+            model.decode_passes = passes
+            xhat = model.decode(codes).cpu()
+            assert float((xhat - xref).abs().max()) <= tol
+            # BASELINE configs[0]: PSNR of uint8 images (DeTransform + PSNR of the reference) >= 60 dB
+            assert float(O.psnr_uint8(O.to_uint8(xhat), O.to_uint8(xref)).min()) >= 60.0
+
+
+def test_unaligned_image_is_reflect_padded_like_the_reference():
+    cfg = dict(channel=64, m=2, k=[256, 128, 64])
+    sd = synthetic_state_dict(64, 2, [256, 128, 64], seed=0)
+    x = uniform((1, 3, 150, 333), "pad.image", 4)
+    model = _model(cfg, sd)
+    codes = model.encode(x.cuda())
+    ref, marg = O.encode(sd, x, with_margin=True)
+    assert [tuple(c.shape) for c in codes] == [tuple(r.shape) for r in ref] == [(1, 2, 16, 24), (1, 2, 8, 12), (1, 2, 4, 6)]
+    flips, _, at = code_report(codes, ref, marg)
+    assert flips == 0 or max(at) < 2e-6
+    assert float((model.decode(codes).cpu() - O.decode(sd, [c.cpu() for c in codes])).abs().max()) <= PIXEL_TOL
+
+
+def test_errors():
+    cfg = dict(channel=64, m=2, k=[256, 128, 64])
+    model = _model(cfg, synthetic_state_dict(64, 2, [256, 128, 64], seed=0))
+    with pytest.raises(RuntimeError):
+        model.encode(torch.zeros(1, 1, 128, 128, device="cuda"))
+    with pytest.raises(RuntimeError):
+        model.encode(torch.zeros(1, 3, 128, 128))                            # CPU tensor: no fallback
+    codes = model.encode(torch.zeros(1, 3, 128, 128, device="cuda"))
+    with pytest.raises(RuntimeError):
+        model.decode(codes[:2])
+    bad = [c.clone() for c in codes]
+    bad[1][0, 0, 0, 0] = 128
+    with pytest.raises(RuntimeError):
+        model.decode(bad)
+    with pytest.raises(RuntimeError):
+        model.decode([])
+
+
+def test_benchmark_size_properties():
+    """qp=1, batch 64 x 3 x 256 x 256 (BASELINE configs[1]): (a) batching invariance -- images are independent,
+    so the first 2 images alone give the same codes as inside the batch of 64 (this is also what makes the
+    multi-GPU sharding exact); (b) determinism across graph replays; (c) histogram == bincount of the codes;
+    (d) decode(encode(x)) is a fixed function: decoding twice is bit-identical; (e) oracle parity on 2 of the 64."""
+    cfg = dict(channel=128, m=1, k=[8192, 2048, 512])
+    sd = synthetic_state_dict(128, 1, cfg["k"], seed=0)
+    model = _model(cfg, sd)
+    x = uniform((64, 3, 256, 256), "bench.image.0", 0)
+    hist = torch.zeros(sum(cfg["k"]), dtype=torch.int32, device="cuda")
+    codes = model.encode(x.cuda(), hist=hist)
+    codes2 = model.encode(x.cuda())
+    assert all(torch.equal(a, b) for a, b in zip(codes, codes2))
+    small = model.encode(x[:2].cuda())
+    assert all(torch.equal(a[:2], b) for a, b in zip(codes, small))
+    exp = torch.cat([h.flatten() for h in O.code_histogram([c.cpu() for c in codes], cfg["k"])]).int()
+    assert torch.equal(hist.cpu(), exp) and int(hist.sum()) == 64 * (256 + 64 + 16)
+    xhat = model.decode(codes)
+    assert torch.equal(xhat, model.decode(codes)) and tuple(xhat.shape) == (64, 3, 256, 256)
+    ref, marg = O.encode(sd, x[:2], with_margin=True)
+    flips, total, at = code_report([c[:2] for c in codes], ref, marg)
+    assert flips == 0 or (flips <= 2 and max(at) < 2e-6), (flips, at)
+    if flips == 0:
+        assert float((xhat[:2].cpu() - O.decode(sd, ref)).abs().max()) <= PIXEL_TOL

@@ -1,0 +1,103 @@
+"""VQ kernels through the C ABI vs the oracle (bit-exact indices; ties -> first index; logits to 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from common import GOLDEN
+from mcquic_b200.engine import Engine
+from mcquic_b200.utils.synthetic import uniform
+from oracle import mcquic_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(x_nchw, cb, logits=False):
+    eng = Engine()
+    n, c, h, w = x_nchw.shape
+    xg = eng.from_nchw(x_nchw.cuda(), {"f32"}).f32
+    cbg = cb.cuda().contiguous()
+    c2 = (cbg ** 2).sum(-1).contiguous()
+    m, k, _ = cb.shape
+    hist = torch.zeros(m * k, dtype=torch.int32, device="cuda")
+    out = eng.vq_assign(xg, cbg, c2, n, h, w, logits=logits, hist=hist)
+    return out, hist, eng
+
+
+@pytest.mark.parametrize("n,h,w,m,k,d", [
+    (2, 16, 16, 1, 8192, 128),   # qp=1 level 0
+    (2, 8, 8, 1, 2048, 128), (3, 4, 4, 1, 512, 128),
+    (2, 32, 32, 6, 2048, 32),    # BASELINE configs[2] shape
+    (1, 5, 7, 3, 100, 8),        # k not a multiple of the tile, ragged point count
+    (1, 1, 1, 2, 1, 4),          # single codeword
+    (2, 3, 3, 12, 64, 16),
+])
+def test_assign_matches_oracle(n, h, w, m, k, d):
+    x = uniform((n, m * d, h, w), "vq.x", 11) * 0.26
+    cb = uniform((m, k, d), "vq.cb", 11) * 0.19
+    (codes, logit), hist, eng = _run(x, cb, logits=True)
+    ref = O.vq_assign(x, cb)
+    mism = codes.cpu() != ref
+    if int(mism.sum()):
+        assert float(O.vq_margin(x, cb)[mism].max()) < 2e-6, "index flips only allowed at fp32 near-ties"
+    assert codes.dtype == torch.int64 and codes.shape == (n, m, h, w)
+    lref = O.vq_logits(x, cb, torch.ones(m, 1, 1, 1))
+    assert float((logit.cpu() - lref).abs().max()) <= 1e-5 * max(1.0, float(lref.abs().max()))
+    # histogram fused into the assign launch
+    exp = torch.cat([h_.flatten() for h_ in O.code_histogram([codes.cpu()], [k])]).int()
+    assert torch.equal(hist.cpu(), exp)
+    # dequant: exact gather
+    deq = eng.to_nchw(eng.vq_dequant(codes, cb.cuda().contiguous(), {"f32"}))
+    assert torch.equal(deq.cpu(), O.vq_dequantize(codes.cpu(), cb))
+
+
+def test_exact_ties_pick_the_first_index():
+    m, k, d = 2, 300, 8
+    cb = uniform((m, k, d), "tie.cb", 2)
+    cb[:, 200] = cb[:, 17]          # duplicate codewords: distances tie exactly
+    cb[:, 250] = cb[:, 17]
+    x = cb[:, 17].reshape(1, m * d, 1, 1).repeat(3, 1, 2, 2).clone()
+    (codes), _, _ = _run(x, cb)
+    assert (codes == 17).all()
+    assert torch.equal(codes.cpu(), O.vq_assign(x, cb))
+
+
+def test_golden_vq_vector():
+    g = np.load(f"{GOLDEN}/vq_m6_k2048_d32.npz")
+    m, k, d, n, h, w = g["config"].tolist()
+    cb = uniform((m, k, d), "vq.codebook", 3) * ((2.0 / (5 * d)) ** 0.5 * 3 ** 0.5)
+    x = uniform((n, m * d, h, w), "vq.latent", 3) * 0.26
+    codes, _, _ = _run(x, cb)
+    ref = torch.from_numpy(g["codes"].astype(np.int64))
+    mism = codes.cpu() != ref
+    assert int(mism.sum()) == 0 or float(torch.from_numpy(g["margin"])[mism].max()) < 2e-6
+
+
+def test_sub_api_modules():
+    from mcquic_b200.modules.quantizer import _multiCodebookDeQuantization, _multiCodebookQuantization
+    cb = torch.nn.Parameter((uniform((3, 50, 8), "sub.cb", 1) * 0.2).cuda())
+    q, dq = _multiCodebookQuantization(cb).cuda(), _multiCodebookDeQuantization(cb)
+    x = (uniform((2, 24, 5, 7), "sub.x", 1) * 0.2).cuda()
+    code = q.encode(x)
+    assert torch.equal(code.cpu(), O.vq_assign(x.cpu(), cb.data.cpu()))
+    assert torch.equal(dq.decode(code).cpu(), O.vq_dequantize(code.cpu(), cb.data.cpu()))
+    with pytest.raises(RuntimeError):
+        dq.decode(torch.full_like(code, 50))
+    with pytest.raises(RuntimeError):
+        q.encode(x[:, :20])
+
+
+def test_full_size_properties():
+    """BASELINE configs[2] size (N=32, 32x32 grid, M=6, K=2048): every assigned codeword is at least as close as
+    a random other codeword (argmin property) and the histogram sums to the number of points."""
+    n, h, w, m, k, d = 32, 32, 32, 6, 2048, 32
+    x = uniform((n, m * d, h, w), "vq.big", 5) * 0.26
+    cb = uniform((m, k, d), "vq.bigcb", 5) * 0.19
+    codes, hist, eng = _run(x, cb)
+    assert int(hist.sum()) == n * h * w * m
+    xp = x.cuda().reshape(n, m, d, h * w).permute(0, 3, 1, 2)             # [n, hw, m, d]
+    cbg = cb.cuda()
+    pick = codes.reshape(n, m, h * w).permute(0, 2, 1)                     # [n, hw, m]
+    mi = torch.arange(m, device="cuda")[None, None, :]
+    best = ((xp - cbg[mi, pick]) ** 2).sum(-1)
+    other = ((xp - cbg[mi, torch.randint(0, k, pick.shape, device="cuda")]) ** 2).sum(-1)
+    assert bool((best <= other * (1 + 1e-5) + 1e-7).all())

@@ -1,0 +1,170 @@
+"""CPU checks of the host side: the C-ABI library loads and exports every symbol the header declares, the
+Python mirror has the reference's state_dict layout, and the module walk / fusion map / weight repacking is
+correct -- verified by running the product's Python against a CPU model of the C ABI (tests/emulator.py) and
+comparing with the oracle.  No CUDA compute happens here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from common import code_report, golden_codes, golden_inputs, load_golden
+from emulator import EmulatedLib
+from mcquic_b200 import Compressor, _lib
+from mcquic_b200.engine import Engine, pack_conv, split_weight
+from mcquic_b200.modules.compressor import aligned_pad_amounts
+from oracle import mcquic_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mcquic_b200.h")).read()
+    declared = set(re.findall(r"\b(mcq_[a-z0-9_]+)\s*\(", header)) - {"mcq_conv_params"}
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    lib = ctypes.CDLL(_lib.load().__dict__.get("_name", _lib.library_path()))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().mcq_version() == 1
+    assert b"bad argument" in _lib.load().mcq_error_string(-1)
+
+
+def test_conv_params_struct_matches_header_field_order():
+    header = open(os.path.join(ROOT, "include", "mcquic_b200.h")).read()
+    body = header[header.index("typedef struct mcq_conv_params {"):header.index("} mcq_conv_params;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        first, *rest = decl.split(",")
+        names.append(first.split()[-1].lstrip("*"))
+        names += [r.strip().lstrip("*") for r in rest]
+    assert names == [f[0] for f in _lib.ConvParams._fields_]
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    lib = _lib.load()
+    p = _lib.ConvParams()
+    assert lib.mcq_conv2d(ctypes.byref(p), None) == -1                     # null operands
+    assert lib.mcq_vq_assign(None, None, None, None, None, None, None, 1, 1, 1, 1, 1, 4, None) == -1
+    assert lib.mcq_code_histogram(None, 1, 1, 1, 1, None, None) == -1
+    with pytest.raises(RuntimeError):
+        _lib.check(-1, "x")
+
+
+def test_state_dict_layout_is_the_references():
+    sd = Compressor(32, 2, [16, 8]).state_dict()
+    keys = set(sd)
+    for must in ["_encoder.0.weight", "_encoder.2._branch.2.gamma", "_encoder.2._branch.2.beta_reparam.lowerBound.bound",
+                 "_encoder.2._skip.weight", "_encoder.3._sideBranch.3.weight", "_decoder.1._branch.1.0.weight",
+                 "_decoder.1._skip.0.bias", "_decoder.6.0.weight", "_quantizer._encoders.0._quantizer._codebook",
+                 "_quantizer._encoders.0._dequantizer._codebook", "_quantizer._decoders.0._dequantizer._codebook",
+                 "_quantizer._encoders.0._quantizer._temperature", "_quantizer._encoders.0._quantizer._bound.bound",
+                 "_quantizer._entropyCoder._freqEMA.1", "_quantizer._encoders.0._latentHead.2.weight"]:
+        assert must in keys, must
+    assert "_quantizer._encoders.1._latentHead.2.weight" not in keys      # last level has no latentHead / sideHead
+    assert "_quantizer._decoders.1._sideHead.1.weight" not in keys
+    assert sd["_decoder.6.0.weight"].shape == (12, 32, 3, 3)
+    assert sd["_quantizer._encoders.1._quantizer._codebook"].shape == (2, 8, 16)
+
+
+def test_state_dict_matches_reference_exactly():
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    ref = ref_import.build_reference_compressor(32, 2, [16, 8]).state_dict()
+    mine = Compressor(32, 2, [16, 8]).state_dict()
+    assert list(ref) == list(mine)
+    assert all(ref[k].shape == mine[k].shape and ref[k].dtype == mine[k].dtype for k in ref)
+
+
+def test_aligned_padding_amounts():
+    assert aligned_pad_amounts(256, 256) == (0, 0, 256, 256)
+    assert aligned_pad_amounts(200, 136) == (28, 60, 256, 256)
+    assert aligned_pad_amounts(1152, 2048) == (0, 0, 1152, 2048)
+    assert aligned_pad_amounts(129, 383) == (63, 0, 256, 384)
+    for h, w in [(200, 136), (257, 300), (768, 512)]:
+        top, left, hp, wp = aligned_pad_amounts(h, w)
+        assert tuple(O.aligned_padding(torch.zeros(1, 3, h, w)).shape[-2:]) == (hp, wp)
+
+
+def test_split_weight_is_accurate_and_pixel_shuffle_permutation():
+    w = torch.randn(16, 40) * 0.03
+    hi, lo, scale = split_weight(w)
+    rec = (hi.double() + lo.double() / 2048.0) * scale
+    assert float((rec - w.double()).abs().max()) <= float(w.abs().max()) * 2.0 ** -21
+    wt = torch.randn(16, 8, 3, 3)
+    pc = pack_conv(wt, torch.arange(16.0), 1, _lib.STORE_SHUFFLE_NHWC, "cpu")
+    # GEMM column (2i+j)*cq + c must hold conv channel 4c + 2i + j
+    assert pc.bias.tolist() == [float(4 * c + s) for s in range(4) for c in range(4)]
+    pc2 = pack_conv(torch.randn(12, 64, 3, 3), torch.zeros(12), 1, _lib.STORE_SHUFFLE_NCHW, "cpu")
+    assert pc2.cout == 12 and pc2.cout_pad == 16 and pc2.w_hi.shape == (16, 576)
+
+
+@pytest.mark.parametrize("name,passes_err", [("compressor_small", 2e-6)])
+def test_host_logic_against_oracle_through_emulated_abi(name, passes_err):
+    g, cfg = load_golden(name)
+    sd, x = golden_inputs(cfg)
+    model = Compressor(cfg["channel"], cfg["m"], cfg["k"]).eval()
+    model.load_state_dict(sd)
+    model._engine = Engine(lib=EmulatedLib())
+    ref = golden_codes(g, len(cfg["k"]))
+    hist = torch.zeros(sum(cfg["m"] * k for k in cfg["k"]), dtype=torch.int32)
+    codes = model.encode(x, hist=hist)
+    flips, total, _ = code_report(codes, ref)
+    assert flips == 0, f"{flips}/{total}"
+    assert all(c.dtype == torch.int64 and c.is_contiguous() for c in codes)
+    assert model.engine.lib.launches == 170 - 0  # one fused launch per conv/GDN + stem + VQ/dequant (no elementwise launches)
+    # histogram fused into the VQ launch == oracle bincount
+    exp = torch.cat([h.flatten() for h in O.code_histogram(ref, cfg["k"])]).int()
+    assert torch.equal(hist, exp)
+    xref = O.decode(sd, ref)
+    model.decode_passes = 3
+    assert float((model.decode(ref) - xref).abs().max()) <= passes_err
+    model.decode_passes = 1
+    assert float((model.decode(ref) - xref).abs().max()) <= 1e-3          # north_star pixel tolerance
+    with pytest.raises(RuntimeError):
+        model.decode([ref[0], ref[1]])                                     # wrong number of levels
+    bad = [r.clone() for r in ref]
+    bad[0][0, 0, 0, 0] = cfg["k"][0]
+    with pytest.raises(RuntimeError):
+        model.decode(bad)                                                  # code outside [0, k)
+    with pytest.raises(RuntimeError):
+        model.encode(torch.zeros(1, 1, 128, 128))                          # not an RGB batch
+
+
+def test_quantizer_sub_api_through_emulated_abi():
+    from mcquic_b200 import engine as E
+    from mcquic_b200.modules.quantizer import _multiCodebookDeQuantization, _multiCodebookQuantization
+    old = E._DEFAULT
+    E._DEFAULT = Engine(lib=EmulatedLib())
+    try:
+        cb = torch.nn.Parameter(torch.randn(3, 50, 8) * 0.2)
+        q, dq = _multiCodebookQuantization(cb), _multiCodebookDeQuantization(cb)
+        x = torch.randn(2, 24, 5, 7) * 0.2
+        code = q.encode(x)
+        assert torch.equal(code, O.vq_assign(x, cb.data))
+        assert torch.equal(dq.decode(code), O.vq_dequantize(code, cb.data))
+        c2, logit = q.logits(x)
+        assert torch.equal(c2, code)
+        assert float((logit - O.vq_logits(x, cb.data, q._temperature.data)).abs().max()) < 1e-5
+        sample, code2, onehot, logit2 = q(x)
+        assert sample.shape == onehot.shape == logit2.shape == (2, 3, 5, 7, 50)
+        assert torch.equal(onehot.argmax(-1), code2) and float(sample.sum()) == 2 * 3 * 5 * 7
+        assert torch.allclose(dq(onehot), dq.decode(code2), atol=1e-6)
+    finally:
+        E._DEFAULT = old
+
+
+def test_product_refuses_cpu_tensors_and_missing_library(monkeypatch):
+    model = Compressor(32, 1, [16, 8]).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.encode(torch.zeros(1, 3, 128, 128))
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "library_path", lambda: "/nonexistent/libmcquic_b200.so")
+    monkeypatch.setattr(_lib._build, "build", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("no nvcc")))
+    with pytest.raises(RuntimeError, match="missing|not found"):
+        Engine()
