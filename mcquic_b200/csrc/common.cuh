@@ -38,6 +38,7 @@ struct ConvArgs {
   int bn;                         // N tile (GEMM columns per CTA tile)
   int tiles_c;                    // cout_pad / bn
   int stages;
+  int debug_skip_store;           // MCQ_EPI_SKIP=1: drain TMEM but store nothing (profiling aid)
   // per-tap TMA coordinate offsets in the 5-D view of A (see conv_tc.cuh)
   int tap_c[9], tap_dx[9], tap_py[9], tap_dy[9];
 };

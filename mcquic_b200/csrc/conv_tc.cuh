@@ -26,7 +26,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                        // fp16 elements per stage along K (= 128 B swizzle span)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;    // 16 KB
 constexpr uint32_t TC_TMEM_COLS = 512;
-constexpr unsigned long long TC_WATCHDOG_SPINS = 40ull * 1000 * 1000;
+constexpr unsigned long long TC_WATCHDOG_NS = 4ull * 1000 * 1000 * 1000;   // 4 s: far beyond any legitimate wait
+constexpr int TC_EPI_STAGE_BYTES = 2048;          // per epilogue warp: 32 rows x 16 fp32 columns
 
 __device__ int g_watchdog_flag = 0;
 
@@ -54,10 +55,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug (wrong tx byte count, bad tensor map) traps instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
-  for (unsigned long long i = 0;; ++i) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  for (unsigned i = 1;; ++i) {
     if (mbar_try_wait(bar, parity)) return;
-    if (i > TC_WATCHDOG_SPINS) {
+    if ((i & 1023u) == 0 && global_ns() - t0 > TC_WATCHDOG_NS) {
       atomicExch(&g_watchdog_flag, code);
       __threadfence_system();
       __trap();
@@ -108,6 +116,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row atoms 1024 B apart.
@@ -115,6 +131,71 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   const uint32_t lo = (saddr >> 4) & 0x3FFF;                       // start address, LBO = 0 (unused, swizzled K-major)
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO = 1024 B, version = 1 (sm_100), SWIZZLE_128B
   return ((uint64_t)hi << 32) | lo;
+}
+
+// ---------------------------------------------------------------- epilogue
+// Drain this warp's share (TMEM lanes 32q.., 32-column chunks cg, cg+4, ...) of one accumulator tile.
+// tcgen05.ld hands every thread one GEMM row (= pixel); storing from that layout would touch 32 cache lines per
+// warp instruction.  So each 32x16 block goes through a per-warp, XOR-swizzled (conflict-free) smem transpose and
+// the fused epilogue runs with 2 lanes per pixel x 8 consecutive channels each: residual / aux loads and all stores
+// are 64 B-contiguous per pixel (16 lines per instruction -> full sectors).
+// pix(row, n, oy, ox) -> valid maps a tile row to its output pixel.
+template <int PASSES, class PixFn>
+__device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, int bn, int ct, int cg, int q, int lane,
+                                           uint32_t stage, PixFn pix) {
+  int n_[2], oy_[2], ox_[2];
+  bool ok_[2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) ok_[it] = pix(q * 32 + it * 16 + (lane >> 1), n_[it], oy_[it], ox_[it]);
+  const int col8 = (lane & 1) * 8;
+  for (int cc = cg * 32; cc < bn; cc += 128) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int col0 = cc + half * 16;
+      if (col0 >= bn) break;
+      uint32_t r[16];
+      float v[16];
+      tmem_ld16(t_acc + (uint32_t)col0, r);
+      if (PASSES == 3) {
+        uint32_t l[16];
+        tmem_ld16(t_acc + (uint32_t)(bn + col0), l);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(l[j]), kLoInv, __uint_as_float(r[j])) * p.w_scale;
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * p.w_scale;
+      }
+      // row-per-lane -> smem (64 B per row; 16 B chunk c stored at c ^ ((row >> 1) & 3))
+      const uint32_t wbase = stage + (uint32_t)lane * 64u;
+      const uint32_t wsw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wbase + ((((uint32_t)c) ^ wsw) << 4)),
+                     "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                     : "memory");
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int rl = it * 16 + (lane >> 1);
+        const uint32_t rbase = stage + (uint32_t)rl * 64u;
+        const uint32_t rsw = (uint32_t)((rl >> 1) & 3);
+        float vv[8];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t chunk = (uint32_t)((col8 >> 2) + c);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(vv[4 * c]), "=f"(vv[4 * c + 1]), "=f"(vv[4 * c + 2]), "=f"(vv[4 * c + 3])
+                       : "r"(rbase + ((chunk ^ rsw) << 4))
+                       : "memory");
+        }
+        if (ok_[it] && !p.debug_skip_store)
+          epilogue_store<8, PASSES == 1>(p, n_[it], oy_[it], ox_[it], ct * bn + col0 + col8, vv);
+      }
+      __syncwarp();
+    }
+  }
 }
 
 // ---------------------------------------------------------------- kernel
@@ -141,6 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * stages + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * stages + 2 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + stage_bytes * stages + 8u * (2 * stages + 4));
+  const uint32_t epi_base = (bar_base + 8u * (2 * stages + 4) + 16u + 127u) & ~127u;   // 16 x 2 KB transpose buffers
 
   const int acc_cols = (PASSES == 3 ? 2 : 1) * bn;   // TMEM columns per accumulator buffer
   const int nbuf = (2 * acc_cols <= (int)TC_TMEM_COLS) ? 2 : 1;
@@ -263,10 +345,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
     const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware rule: warp % 4)
     const int cg = (warp - 2) >> 2;     // column group: this warp handles 32-column chunks cg, cg+4, ...
-    const int row = q * 32 + lane;      // GEMM row inside the tile = pixel (x fastest, then y, then n)
-    const int ix = row % p.tw;
-    const int iy = (row / p.tw) % p.th;
-    const int in = row / (p.tw * p.th);
+    const uint32_t stage = epi_base + (uint32_t)(warp - 2) * TC_EPI_STAGE_BYTES;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int ct = t / tiles_m;
@@ -275,39 +354,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mt /= p.tiles_x;
       const int by = mt % p.tiles_y;
       const int bz = mt / p.tiles_y;
-      const int ox = bx * p.tw + ix, oy = by * p.th + iy, n = bz * p.tn + in;
-      const bool valid = (ox < p.wout) && (oy < p.hout) && (n < p.n);
+      // GEMM row inside the tile = pixel (x fastest, then y, then n)
+      auto pix = [&](int row, int& n, int& oy, int& ox) {
+        ox = bx * p.tw + row % p.tw;
+        oy = by * p.th + (row / p.tw) % p.th;
+        n = bz * p.tn + row / (p.tw * p.th);
+        return (ox < p.wout) && (oy < p.hout) && (n < p.n);
+      };
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
       mbar_wait(tfull_bar(buf), use & 1u, 4);
       tc_fence_after();
-      const uint32_t t_hh = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      for (int cc = cg * 32; cc < bn; cc += 128) {
-        uint32_t r[32];
-        float v[32];
-        tmem_ld32(t_hh + (uint32_t)cc, r);
-        if (PASSES == 3) {
-          uint32_t l[32];
-          tmem_ld32(t_hh + (uint32_t)(bn + cc), l);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(l[j]), kLoInv, __uint_as_float(r[j])) * p.w_scale;
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.w_scale;
-        }
-        if (valid) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (cc + g * 8 >= bn) break;  // N tiles narrower than a 32-column chunk (bn = 16)
-            float vv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) vv[j] = v[g * 8 + j];
-            epilogue_store<8, PASSES == 1>(p, n, oy, ox, ct * bn + cc + g * 8, vv);
-          }
-        }
-      }
+      const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
+      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -317,6 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
                  : "memory");

@@ -5,10 +5,12 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
 #include "conv_simt.cuh"
+#include "conv_halo.cuh"
 #include "conv_tc.cuh"
 #include "misc.cuh"
 #include "vq.cuh"
@@ -47,6 +49,11 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
 int pow2_ceil(int v) {
   int r = 1;
   while (r < v) r <<= 1;
@@ -75,6 +82,7 @@ int num_sms() {
 //   stride 1: dims {C,  W,   1, H,   N}
 //   stride 2: dims {2C, W/2, 2, H/2, N}   (x parity folded into the channel axis, y parity its own axis)
 int encode_act_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int stride, int tw, int th, int tn) {
+  // box = {64 channels, tw, 1, th, tn}
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MCQ_ERR_DRIVER;
   cuuint64_t dims[5], strides[4];
@@ -204,11 +212,13 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   }
   // ---- pipeline depth
   const size_t stage_bytes = (size_t)(TC_A_BYTES + bn * TC_BK * 2) * (a.passes == 3 ? 2 : 1);
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128;
+  int stages = (int)((226 * 1024 - 1024 - 512 - epi_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return MCQ_ERR_UNSUPPORTED;
   a.stages = stages;
-  const size_t smem = stage_bytes * stages + 8 * (2 * stages + 4) + 16 + 1024;
+  const size_t smem = stage_bytes * stages + 8 * (2 * stages + 4) + 16 + 1024 + epi_bytes;
+  a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
 
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   int rc = encode_act_map(&tmA_hi, a.a_hi, a.n, a.hin, a.win, a.cin, a.stride, a.tw, a.th, a.tn);
@@ -248,6 +258,115 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   return cuda_status();
 }
 
+
+// ---- halo kernel (3x3, stride 1): tap reuse in smem + weight multicast across a cluster
+bool halo_supported(const ConvArgs& a) {
+  return a.ksize == 3 && a.stride == 1 && a.cin % TC_BK == 0 && a.wout >= HALO_TW && a.hout >= HALO_TH &&
+         a.cout_pad % 16 == 0;
+}
+
+template <int PASSES, int CL>
+int launch_halo_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t smem, int grid, cudaStream_t st) {
+  static bool attr = false;
+  auto kern = conv_halo_kernel<PASSES, CL>;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], a, hp);
+  g_launches++;
+  return e == cudaSuccess ? cuda_status() : (int)e;
+}
+
+int launch_halo(ConvArgs& a, cudaStream_t st) {
+  int bn = (a.cout_pad <= 256 && a.cout_pad % 128 != 0) ? a.cout_pad : 128;
+  if (a.cout_pad < 128) bn = a.cout_pad;
+  if (a.cout_pad % bn != 0 || bn % 32 != 0) return MCQ_ERR_UNSUPPORTED;
+  const int np = a.passes == 3 ? 2 : 1;
+  if (np * bn > (int)TC_TMEM_COLS) return MCQ_ERR_UNSUPPORTED;
+  a.bn = bn;
+  a.tiles_c = a.cout_pad / bn;
+  a.tw = HALO_TW; a.th = HALO_TH; a.tn = 1;
+  a.tiles_x = (a.wout + HALO_TW - 1) / HALO_TW;
+  a.tiles_y = (a.hout + HALO_TH - 1) / HALO_TH;
+  a.tiles_n = a.n;
+  HaloArgs hp{};
+  hp.pitch = env_int("MCQ_HALO_PITCH", 10);
+  hp.box_w = hp.pitch;
+  hp.base_mode = env_int("MCQ_HALO_BASE", 0);
+  hp.a_bytes = ((hp.pitch * HALO_ROWS * 128) + 1023) / 1024 * 1024;
+  hp.tiles_m = a.tiles_x * a.tiles_y * a.tiles_n;
+  int cl = env_int("MCQ_HALO_CL", 2);
+  if (cl != 1 && cl != 2 && cl != 4) return MCQ_ERR_BAD_ARG;
+  while (cl > 1 && ((bn / cl) % 8 != 0 || hp.tiles_m < cl)) cl /= 2;
+  hp.groups_m = (hp.tiles_m + cl - 1) / cl;
+  // smem budget: A buffers (double/triple) + as many weight stages as fit
+  const size_t a_buf = (size_t)hp.a_bytes * np;
+  const size_t b_stage = (size_t)bn * TC_BK * 2 * np;
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128;
+  const size_t budget = 226 * 1024 - 1024 - 512 - epi_bytes;
+  a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
+  hp.na = (a.passes == 3) ? 2 : 3;
+  int nbs = (int)((budget - a_buf * hp.na) / b_stage);
+  if (nbs > 8) nbs = 8;
+  if (nbs < 2) { hp.na = 2; nbs = (int)((budget - a_buf * hp.na) / b_stage); }
+  if (nbs < 2) return MCQ_ERR_UNSUPPORTED;
+  hp.nbs = nbs;
+  const size_t smem = a_buf * hp.na + b_stage * nbs + 8 * (2 * hp.na + 2 * nbs + 4) + 16 + 1024 + epi_bytes;
+
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MCQ_ERR_DRIVER;
+  CUtensorMap maps[4];
+  auto enc_a = [&](CUtensorMap* m, const void* ptr) {
+    cuuint64_t dims[5] = {(cuuint64_t)a.cin, (cuuint64_t)a.win, 1, (cuuint64_t)a.hin, (cuuint64_t)a.n};
+    cuuint64_t strides[4] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.win * a.cin * 2, (cuuint64_t)a.win * a.cin * 2,
+                             (cuuint64_t)a.hin * a.win * a.cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)hp.box_w, 1u, (cuuint32_t)HALO_ROWS, 1u};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : MCQ_ERR_DRIVER;
+  };
+  int rc = enc_a(&maps[0], a.a_hi);
+  if (rc) return rc;
+  rc = encode_weight_map(&maps[2], a.w_hi, a.cout_pad, a.ktotal, bn / cl);
+  if (rc) return rc;
+  if (a.passes == 3) {
+    rc = enc_a(&maps[1], a.a_lo);
+    if (rc) return rc;
+    rc = encode_weight_map(&maps[3], a.w_lo, a.cout_pad, a.ktotal, bn / cl);
+    if (rc) return rc;
+  } else {
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+  }
+  const int work = hp.groups_m * a.tiles_c;
+  int clusters = num_sms() / cl;
+  if (work < clusters) clusters = work;
+  const int grid = clusters * cl;
+  if (a.passes == 3) {
+    if (cl == 1) return launch_halo_t<3, 1>(a, hp, maps, smem, grid, st);
+    if (cl == 2) return launch_halo_t<3, 2>(a, hp, maps, smem, grid, st);
+    return launch_halo_t<3, 4>(a, hp, maps, smem, grid, st);
+  }
+  if (cl == 1) return launch_halo_t<1, 1>(a, hp, maps, smem, grid, st);
+  if (cl == 2) return launch_halo_t<1, 2>(a, hp, maps, smem, grid, st);
+  return launch_halo_t<1, 4>(a, hp, maps, smem, grid, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -260,6 +379,7 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
   if (p->impl == MCQ_IMPL_SIMT) return launch_simt(a, st);
   if (p->impl != MCQ_IMPL_TCGEN05) return MCQ_ERR_BAD_ARG;
   if (!tc_supported(a)) return MCQ_ERR_UNSUPPORTED;
+  if (halo_supported(a) && env_int("MCQ_HALO", 0)) return launch_halo(a, st);
   return launch_tc(a, st);
 }
 

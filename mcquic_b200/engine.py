@@ -101,7 +101,7 @@ class Engine:
         # independent sub-graphs (the two AttentionBlock branches, quantizationHead || latentHead,
         # dequantizationHead || sideHead) run on side streams: on <=16x16 feature maps one conv cannot fill 148 SMs
         self.multistream = not self.emulated
-        self._side_streams: List["torch.cuda.Stream"] = []
+        self._side_streams: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
         self._depth = 0
         # when a list, every conv launch is bracketed by CUDA events and logged (bench.py's roofline leg)
         self.profile: Optional[list] = None
@@ -116,9 +116,13 @@ class Engine:
         """Run the independent closures fa and fb concurrently (fb on a side stream); returns (fa(), fb())."""
         if not self.multistream:
             return fa(), fb()
-        while len(self._side_streams) <= self._depth:
-            self._side_streams.append(torch.cuda.Stream())
-        main, side = torch.cuda.current_stream(), self._side_streams[self._depth]
+        # one side stream per (nesting depth, parent stream): a side stream shared by two parents would let the
+        # caching allocator hand a block to the second parent's branch while the first parent still reads it
+        main = torch.cuda.current_stream()
+        key = (self._depth, main.cuda_stream)
+        side = self._side_streams.get(key)
+        if side is None:
+            side = self._side_streams[key] = torch.cuda.Stream()
         self._depth += 1
         try:
             side.wait_stream(main)

@@ -244,8 +244,69 @@ def g_timing():
         print(f"  model N={N}: encode {te:.2f} ms decode {td:.2f} ms -> {N*256*256/(te+td)/1e3:.1f} MPix/s (eager launches, no graph)", flush=True)
 
 
+def g_halo():
+    """halo kernel variants; configuration comes from MCQ_HALO_* environment variables"""
+    import torch
+    from convcase import make_planes
+    from mcquic_b200 import _lib
+    from mcquic_b200.engine import Act, Engine, pack_conv
+    print("  env", {k: v for k, v in os.environ.items() if k.startswith("MCQ_")}, flush=True)
+    eng = Engine("tcgen05")
+    for passes in (1, 3):
+        _case(eng, f"halo 16x16 n1 p{passes}", n=1, h=16, w=16, cin=128, cout=128, passes=passes)
+        _case(eng, f"halo 64x64 n4 p{passes}", n=4, h=64, w=64, cin=128, cout=128, passes=passes)
+        _case(eng, f"halo 24x40 n3 p{passes} ragged", n=3, h=24, w=40, cin=128, cout=128, passes=passes)
+        _case(eng, f"halo 32x32 n2 c192 p{passes}", n=2, h=32, w=32, cin=192, cout=192, passes=passes)
+        _case(eng, f"halo shuffle c128->512 p{passes}", n=2, h=16, w=16, cin=128, cout=512, passes=passes,
+              store=_lib.STORE_SHUFFLE_NHWC, want=("f32", "sq"))
+    g = torch.Generator().manual_seed(0)
+    for passes in (3, 1):
+        for (n, h, w, cin, cout) in [(64, 128, 128, 128, 128), (64, 64, 64, 128, 128), (64, 64, 64, 128, 512), (64, 32, 32, 128, 128), (64, 16, 16, 128, 128)]:
+            x = torch.randn(n, h, w, cin, generator=g).cuda()
+            wt = ((torch.rand(cout, cin, 3, 3, generator=g) * 2 - 1) / (9 * cin) ** 0.5).cuda()
+            store = _lib.STORE_SHUFFLE_NHWC if cout == 512 else 0
+            pc = pack_conv(wt, torch.zeros(cout).cuda(), 1, store, "cuda")
+            eng.passes = passes
+            a = make_planes(x, passes)
+            act = Act(n, h, w, cin)
+            want = {"f32", "silu"} if store == 0 else {"f32"}
+            gr = torch.cuda.CUDAGraph()
+            for _ in range(2):
+                eng.conv(pc, a, act, want)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gr):
+                for _ in range(10):
+                    o = eng.conv(pc, a, act, want)
+            gr.replay()
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            gr.replay()
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / 10
+            fl = 2.0 * n * h * w * cout * cin * 9
+            print(f"  conv n{n} {h}x{w} c{cin}->{cout} passes={passes}: {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s(alg)", flush=True)
+    print("  flag", eng.lib.mcq_device_error_flag())
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "halo_sweep":
+        combos = [("0", "10", "0", "1", "0"), ("1", "10", "0", "1", "0"), ("1", "10", "0", "2", "0"), ("1", "10", "0", "2", "1"), ("0", "10", "0", "1", "1")]
+        for (on, pitch, base, cl, skip) in combos:
+            env = dict(os.environ, MCQ_HALO=on, MCQ_HALO_PITCH=pitch, MCQ_HALO_BASE=base, MCQ_HALO_CL=cl, MCQ_EPI_SKIP=skip)
+            print(f"==== halo={on} pitch={pitch} base={base} cl={cl} epi_skip={skip}", flush=True)
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "halo"], timeout=300, capture_output=True, text=True, env=env)
+                print(r.stdout[-5000:], end="")
+                if r.returncode != 0:
+                    print(f"!! exit {r.returncode}\n{r.stderr[-1500:]}")
+            except subprocess.TimeoutExpired as e:
+                print("!! TIMEOUT", (e.stdout or b"")[-2000:])
+        return
     if len(sys.argv) > 1:
+        import faulthandler
+        faulthandler.dump_traceback_later(150, exit=True)
         for name in sys.argv[1:]:
             print(f"== {name}", flush=True)
             globals()["g_" + name]()
