@@ -253,6 +253,10 @@ def run_ours(args):
         model.engine.profile = None
         model.use_graphs = True
         model.engine.multistream = True
+        if args.dump_profile:
+            with open(args.dump_profile, "w") as fp:
+                json.dump([{"shape": p["shape"], "passes": p["passes"], "flops": p["flops"],
+                            "us": 1e3 * p["ev"][0].elapsed_time(p["ev"][1])} for p in prof], fp)
         tc = [p for p in prof if p["impl"] == _lib.IMPL_TCGEN05]
         t_tc = sum(p["ev"][0].elapsed_time(p["ev"][1]) for p in tc) * 1e-3
         f_tc = sum(p["flops"] for p in tc)
@@ -304,6 +308,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dump-profile", default=None, help="write the per-conv-launch timing list of the roofline leg here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

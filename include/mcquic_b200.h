@@ -100,6 +100,16 @@ int mcq_vq_assign(const float* x, const float* codebook, const float* c2, int64_
                   const float* logit_scale, int32_t* hist, int32_t n, int32_t h, int32_t w, int32_t m, int32_t k,
                   int32_t d, mcq_stream_t stream);
 
+/* Tensor-core variant of mcq_vq_assign for d % 64 == 0 and k % 32 == 0 (qp=1: d=128): the x.c_k products run on
+ * tcgen05 (3-pass split-fp16, fp32-grade) and the distance + first-index argmin happens in the GEMM epilogue; the
+ * [n,m,h,w,k] distance tensor is never written.  cb_hi/cb_lo: codebook [m,k,d] as split-fp16 planes of c * 2^e,
+ * cb_scale = 2^-e.  workspace: >= mcq_vq_workspace_bytes(...) bytes, 256 B aligned, contents undefined afterwards.
+ * Same outputs / reference lines as mcq_vq_assign (no logits). Returns MCQ_ERR_UNSUPPORTED for other shapes. */
+int mcq_vq_assign_tc(const float* x, const void* cb_hi, const void* cb_lo, float cb_scale, const float* c2,
+                     int64_t* codes, int32_t* hist, int32_t n, int32_t h, int32_t w, int32_t m, int32_t k, int32_t d,
+                     void* workspace, int64_t workspace_bytes, mcq_stream_t stream);
+int64_t mcq_vq_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t m, int32_t k, int32_t d);
+
 /* Replaces _multiCodebookDeQuantization.decode (mcquic/modules/quantizer.py:249-259): gather codebook[m, code].
  * codes int64 [n,m,h,w] -> fp32 NHWC [n,h,w,m*d] and/or split-fp16 plane pairs (raw and/or act). Returns
  * MCQ_ERR_CODE_RANGE via *status (device int32, optional) if a code is outside [0,k). */

@@ -10,6 +10,13 @@ namespace mcq {
 
 constexpr float kLoScale = 2048.0f;          // lo plane = (a - hi) * 2^11
 constexpr float kLoInv = 1.0f / 2048.0f;
+constexpr int EPI_ARGMIN = 4;   // internal epilogue mode of the tensor-core VQ (vq_assign_tc): bias = |c|^2, aux = |x|^2
+
+// monotone map float -> uint32 (total order incl. negatives), so that (key << 32 | index) orders by (distance, index)
+__device__ __forceinline__ uint32_t ordered_f32(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
 // Device view of one convolution launch (mcq_conv_params + derived geometry).
 struct ConvArgs {
@@ -38,23 +45,31 @@ struct ConvArgs {
   int bn;                         // N tile (GEMM columns per CTA tile)
   int tiles_c;                    // cout_pad / bn
   int stages;
+  int cin_total, ch_off;          // A is the channel slice [ch_off, ch_off + cin) of a [.., cin_total] tensor
+  unsigned long long* argmin_keys;  // EPI_ARGMIN: per-point packed (ordered distance << 32 | index) minima
+  int argmin_stride;              // points are argmin_stride keys / aux entries apart (= number of codebooks)
   int debug_skip_store;           // MCQ_EPI_SKIP=1: drain TMEM but store nothing (profiling aid)
   // per-tap TMA coordinate offsets in the 5-D view of A (see conv_tc.cuh)
   int tap_c[9], tap_dx[9], tap_py[9], tap_dy[9];
 };
 
-// FAST = SFU approximations (ex2.approx / rcp.approx / rsqrt.approx, a few ulp): used by the 1-pass (TF32-grade)
-// path where operand rounding (2^-11) dominates anyway; the 3-pass path keeps IEEE division / sqrt and expf.
+// Activation math.  Both variants use the SFU (ex2.approx, rcp.approx); the exact variant adds one Newton step to the
+// reciprocal so that sigmoid/SiLU carry <= ~2 ulp error (the exponential's 2^-22), i.e. fp32-grade like the rest of
+// the 3-pass path, at a quarter of the instructions of expf() + IEEE division.  FAST (1-pass, TF32-grade) skips it.
+__device__ __forceinline__ float rcp_approx(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
+}
 template <bool FAST>
 __device__ __forceinline__ float sigmoid_f(float x) {
-  if constexpr (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
-  return 1.0f / (1.0f + expf(-x));
+  const float d = 1.0f + __expf(fminf(-x, 80.0f));   // clamp keeps d finite (inf * 0 in the Newton step would be NaN)
+  float r = rcp_approx(d);
+  if constexpr (!FAST) r = r * fmaf(-d, r, 2.0f);
+  return r;
 }
 template <bool FAST>
-__device__ __forceinline__ float silu_f(float x) {
-  if constexpr (FAST) return __fdividef(x, 1.0f + __expf(-x));
-  return x / (1.0f + expf(-x));
-}
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f<FAST>(x); }
 
 template <bool FAST>
 __device__ __forceinline__ float apply_act(float y, int act) {
@@ -76,28 +91,38 @@ __device__ __forceinline__ void split_f32(float a, unsigned short& hi, unsigned 
   lo = f2h_sat((a - h2f(hi)) * kLoScale);
 }
 
+// two values at once: packed fp16x2 words (element 0 in the low half)
+__device__ __forceinline__ uint32_t f2h2_sat(float e0, float e1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+  return r;
+}
+__device__ __forceinline__ void split_f32x2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+  hi = f2h2_sat(e0, e1);
+  const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = f2h2_sat((e0 - back.x) * kLoScale, (e1 - back.y) * kLoScale);
+}
+
 template <int NV, bool FAST = false>
 __device__ __forceinline__ void store_planes(__half* hi_p, __half* lo_p, size_t off, const float (&y)[NV], int act) {
   static_assert(NV == 4 || NV == 8, "NV");
-  unsigned short h[NV], l[NV];
+  uint32_t h[NV / 2], l[NV / 2];
+  float t[NV];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) split_f32(apply_act<FAST>(y[j], act), h[j], l[j]);
-  if constexpr (NV == 8) {
-    uint4 ph = make_uint4(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16), h[4] | (uint32_t(h[5]) << 16),
-                          h[6] | (uint32_t(h[7]) << 16));
-    *reinterpret_cast<uint4*>(hi_p + off) = ph;
-    if (lo_p) {
-      uint4 pl = make_uint4(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16),
-                            l[4] | (uint32_t(l[5]) << 16), l[6] | (uint32_t(l[7]) << 16));
-      *reinterpret_cast<uint4*>(lo_p + off) = pl;
-    }
+  for (int j = 0; j < NV; ++j) t[j] = apply_act<FAST>(y[j], act);
+  if (lo_p) {
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) split_f32x2(t[2 * j], t[2 * j + 1], h[j], l[j]);
   } else {
-    uint2 ph = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
-    *reinterpret_cast<uint2*>(hi_p + off) = ph;
-    if (lo_p) {
-      uint2 pl = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
-      *reinterpret_cast<uint2*>(lo_p + off) = pl;
-    }
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) h[j] = f2h2_sat(t[2 * j], t[2 * j + 1]);
+  }
+  if constexpr (NV == 8) {
+    *reinterpret_cast<uint4*>(hi_p + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo_p) *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  } else {
+    *reinterpret_cast<uint2*>(hi_p + off) = make_uint2(h[0], h[1]);
+    if (lo_p) *reinterpret_cast<uint2*>(lo_p + off) = make_uint2(l[0], l[1]);
   }
 }
 

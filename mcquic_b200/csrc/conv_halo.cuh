@@ -29,6 +29,8 @@ struct HaloArgs {
   int box_w;        // TMA box width (= pitch)
   int a_bytes;      // bytes of one halo plane (1024-aligned)
   int na, nbs;      // A buffers, B stages
+  int tps;          // filter taps per weight stage (1 or 3): amortises the per-stage barrier round trip of the
+                    // single MMA-issuing thread when a tap is only 4 MMAs (1-pass)
   int base_mode;    // 0: descriptor base_offset = 0; 1: base_offset = (start >> 7) & 7
   int tiles_m;      // pixel tiles (n * tiles_y * tiles_x)
   int groups_m;     // ceil(tiles_m / CL)
@@ -80,7 +82,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   constexpr int NP = (PASSES == 3) ? 2 : 1;              // planes per operand
   const uint32_t a_buf_bytes = (uint32_t)hp.a_bytes * NP;
   const uint32_t b_plane = (uint32_t)bn * TC_BK * 2;
-  const uint32_t b_stage_bytes = b_plane * NP;
+  const uint32_t b_tap_bytes = b_plane * NP;             // one tap: [B_hi | B_lo]
+  const uint32_t b_stage_bytes = b_tap_bytes * hp.tps;
   const uint32_t b_slice = b_plane / CL;                 // bytes of one CTA's share of a weight plane
   const int na = hp.na, nbs = hp.nbs;
 
@@ -149,34 +152,51 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      int ab = 0, bs = 0;
+      // The halo of chunk g+na-1 is requested while the weights of chunk g stream: late enough that its buffer is
+      // certainly free (the MMA has passed tap t* - nbs >= 0 of chunk g, so chunk g-1 is done -> the wait below
+      // never blocks), early enough (>= one whole chunk of MMA time) to hide the TMA latency of the 23 KB box.
+      const int my_work = (total_work - cluster_id + num_clusters - 1) / num_clusters;   // work items of this cluster
+      const int total_chunks = my_work * kchunks;
+      const int spc = 9 / hp.tps;                          // weight stages per chunk
+      const int t_star = nbs < spc - 1 ? nbs : spc - 1;
+      int a_issue = 0, ab = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
+      auto issue_a = [&]() {
+        if (a_issue >= total_chunks) return;
+        const int wi = cluster_id + (a_issue / kchunks) * num_clusters, kc = a_issue % kchunks;
+        int ct, x0, y0, n;
+        decode_tile(wi, ct, x0, y0, n);
+        mbar_wait(a_empty(ab), aph ^ 1u, 11);
+        const uint32_t sa = a_base + a_buf_bytes * ab;
+        // the whole box is always transferred (out-of-image pixels are zero-filled): tx = box bytes
+        mbar_expect_tx(a_full(ab), (uint32_t)(hp.box_w * HALO_ROWS * 128) * NP);
+        tma_load_5d(&tmA_hi, sa, a_full(ab), kc * TC_BK, x0 - 1, 0, y0 - 1, n);
+        if (PASSES == 3) tma_load_5d(&tmA_lo, sa + hp.a_bytes, a_full(ab), kc * TC_BK, x0 - 1, 0, y0 - 1, n);
+        if (++ab == na) { ab = 0; aph ^= 1u; }
+        ++a_issue;
+      };
+      for (int i = 0; i < na - 1; ++i) issue_a();
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         int ct, x0, y0, n;
         decode_tile(w, ct, x0, y0, n);
+        const int row0 = ct * bn + (int)crank * (bn / CL);
         for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(a_empty(ab), aph ^ 1u, 11);
-          const uint32_t sa = a_base + a_buf_bytes * ab;
-          // whole box is always transferred (out-of-image pixels are zero-filled): tx = box bytes
-          const uint32_t a_tx = (uint32_t)(hp.box_w * HALO_ROWS * 128) * NP;
-          mbar_expect_tx(a_full(ab), a_tx);
-          tma_load_5d(&tmA_hi, sa, a_full(ab), kc * TC_BK, x0 - 1, 0, y0 - 1, n);
-          if (PASSES == 3) tma_load_5d(&tmA_lo, sa + hp.a_bytes, a_full(ab), kc * TC_BK, x0 - 1, 0, y0 - 1, n);
-          if (++ab == na) { ab = 0; aph ^= 1u; }
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int sg = 0; sg < spc; ++sg) {
             mbar_wait(b_empty(bs), bph ^ 1u, 12);
-            const uint32_t sb = b_base + b_stage_bytes * bs;
             mbar_expect_tx(b_full(bs), b_stage_bytes);
-            const int kb = tap * p.cin + kc * TC_BK;
-            const int row0 = ct * bn + (int)crank * (bn / CL);
-            if (CL > 1) {
-              tma_load_2d_mc(&tmB_hi, sb + crank * b_slice, b_full(bs), kb, row0, kMask);
-              if (PASSES == 3) tma_load_2d_mc(&tmB_lo, sb + b_plane + crank * b_slice, b_full(bs), kb, row0, kMask);
-            } else {
-              tma_load_2d(&tmB_hi, sb, b_full(bs), kb, row0);
-              if (PASSES == 3) tma_load_2d(&tmB_lo, sb + b_plane, b_full(bs), kb, row0);
+            for (int tt = 0; tt < hp.tps; ++tt) {
+              const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
+              const int kb = (sg * hp.tps + tt) * p.cin + kc * TC_BK;
+              if (CL > 1) {
+                tma_load_2d_mc(&tmB_hi, sb + crank * b_slice, b_full(bs), kb, row0, kMask);
+                if (PASSES == 3) tma_load_2d_mc(&tmB_lo, sb + b_plane + crank * b_slice, b_full(bs), kb, row0, kMask);
+              } else {
+                tma_load_2d(&tmB_hi, sb, b_full(bs), kb, row0);
+                if (PASSES == 3) tma_load_2d(&tmB_lo, sb + b_plane, b_full(bs), kb, row0);
+              }
             }
             if (++bs == nbs) { bs = 0; bph ^= 1u; }
+            if (sg == t_star) issue_a();
           }
         }
       }
@@ -185,6 +205,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t sbo = (uint32_t)hp.pitch * 128u;
+      const uint32_t idesc_wide = (1u << 4) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const bool wide = (PASSES == 3) && (2 * bn <= 256);
       int ab = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
@@ -197,24 +219,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(a_full(ab), aph, 14);
           const uint32_t sa = a_base + a_buf_bytes * ab;
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int sg = 0; sg < 9 / hp.tps; ++sg) {
             mbar_wait(b_full(bs), bph, 15);
             tc_fence_after();
-            const uint32_t sb = b_base + b_stage_bytes * bs;
-            const uint32_t a_off = (uint32_t)((tap / 3) * hp.pitch + (tap % 3)) * 128u;
-            const uint64_t b_hi = make_sdesc(sb);
-            const bool first = (kc == 0 && tap == 0);
+            for (int tt = 0; tt < hp.tps; ++tt) {
+              const int tap = sg * hp.tps + tt;
+              const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
+              const uint32_t a_off = (uint32_t)((tap / 3) * hp.pitch + (tap % 3)) * 128u;
+              const uint64_t b_hi = make_sdesc(sb);
+              const bool first = (kc == 0 && tap == 0);
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint32_t acc = (!first || k > 0) ? 1u : 0u;
-              const uint64_t a_hi = make_sdesc_halo(sa + a_off + k * 32, sbo, hp.base_mode);
-              const uint64_t ko = (uint64_t)(k * 2);
-              umma_f16(d_hh, a_hi, b_hi + ko, idesc, acc);
-              if (PASSES == 3) {
-                const uint64_t a_lo = make_sdesc_halo(sa + hp.a_bytes + a_off + k * 32, sbo, hp.base_mode);
-                const uint64_t b_lo = make_sdesc(sb + b_plane);
-                umma_f16(d_lo, a_hi, b_lo + ko, idesc, acc);
-                umma_f16(d_lo, a_lo, b_hi + ko, idesc, 1u);
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint32_t acc = (!first || k > 0) ? 1u : 0u;
+                const uint64_t a_hi = make_sdesc_halo(sa + a_off + k * 32, sbo, hp.base_mode);
+                const uint64_t ko = (uint64_t)(k * 2);
+                if (PASSES == 3) {
+                  const uint64_t a_lo = make_sdesc_halo(sa + hp.a_bytes + a_off + k * 32, sbo, hp.base_mode);
+                  if (wide) {   // one N = 2*bn MMA over the adjacent [B_hi; B_lo] stage: A_hi is fetched once
+                    umma_f16(d_hh, a_hi, b_hi + ko, idesc_wide, acc);
+                  } else {
+                    const uint64_t b_lo = make_sdesc(sb + b_plane);
+                    umma_f16(d_hh, a_hi, b_hi + ko, idesc, acc);
+                    umma_f16(d_lo, a_hi, b_lo + ko, idesc, acc);
+                  }
+                  umma_f16(d_lo, a_lo, b_hi + ko, idesc, 1u);
+                } else {
+                  umma_f16(d_hh, a_hi, b_hi + ko, idesc, acc);
+                }
               }
             }
             if (CL > 1) umma_commit_mc(b_empty(bs), kMask); else umma_commit(b_empty(bs));

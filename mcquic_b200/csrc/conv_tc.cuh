@@ -43,34 +43,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~the hint elapses)
+// instead of burning issue slots that the epilogue warps of the same SM sub-partition need
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug (wrong tx byte count, bad tensor map) traps instead of hanging the GPU.
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug (wrong tx byte count, bad tensor map) traps instead of hanging the GPU.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int code) {
   const unsigned long long t0 = global_ns();
   for (unsigned i = 1;; ++i) {
     if (mbar_try_wait(bar, parity)) return;
-    if ((i & 1023u) == 0 && global_ns() - t0 > TC_WATCHDOG_NS) {
+    if ((i & 63u) == 0 && global_ns() - t0 > TC_WATCHDOG_NS) {
       atomicExch(&g_watchdog_flag, code);
       __threadfence_system();
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, code);
 }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
@@ -148,6 +153,44 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
 #pragma unroll
   for (int it = 0; it < 2; ++it) ok_[it] = pix(q * 32 + it * 16 + (lane >> 1), n_[it], oy_[it], ox_[it]);
   const int col8 = (lane & 1) * 8;
+  if (p.mode == EPI_ARGMIN) {
+    // tensor-core VQ: this thread owns GEMM row q*32+lane (one latent point) and scans its columns (codewords):
+    // distance = (|x|^2 + |c_k|^2) - 2 x.c_k in the reference's order (quantizer.py:176); the running minimum is
+    // merged across column groups / N tiles with one 64-bit atomicMin per thread: (distance, index) lexicographic,
+    // i.e. the first index wins ties like torch.argmin.
+    int n, oy, ox;
+    const bool ok = pix(q * 32 + lane, n, oy, ox);
+    const size_t point = ((size_t)n * p.hout + oy) * p.wout + ox;
+    const float x2 = ok ? p.aux[point * p.argmin_stride] : 0.f;
+    float best = INFINITY;
+    int best_k = 0x7fffffff;
+    for (int cc = cg * 32; cc < bn; cc += 128) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int col0 = cc + half * 16;
+        if (col0 >= bn) break;
+        uint32_t r[16], l[16];
+        tmem_ld16(t_acc + (uint32_t)col0, r);
+        if (PASSES == 3) tmem_ld16(t_acc + (uint32_t)(bn + col0), l);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = ct * bn + col0 + j;
+          float v = __uint_as_float(r[j]);
+          if (PASSES == 3) v = fmaf(__uint_as_float(l[j]), kLoInv, v);
+          v *= p.w_scale;
+          if (col < p.cout) {
+            const float dist = (x2 + p.bias[col]) - 2.0f * v;
+            if (dist < best) { best = dist; best_k = col; }
+          }
+        }
+      }
+    }
+    if (ok && best_k != 0x7fffffff)
+      atomicMin(p.argmin_keys + point * p.argmin_stride,
+                ((unsigned long long)ordered_f32(best) << 32) | (unsigned long long)(uint32_t)best_k);
+    return;
+  }
   for (int cc = cg * 32; cc < bn; cc += 128) {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -279,7 +322,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(empty_bar(s), ph ^ 1u, 1);
             const uint32_t sa = smem_base + stage_bytes * s;
             mbar_expect_tx(full_bar(s), stage_bytes);
-            const int ca = p.tap_c[tap] + kc * TC_BK;
+            const int ca = p.ch_off + p.tap_c[tap] + kc * TC_BK;
             const int kb = tap * p.cin + kc * TC_BK;
             tma_load_5d(&tmA_hi, sa, full_bar(s), ca, x0 + p.tap_dx[tap], p.tap_py[tap], y0 + p.tap_dy[tap], n0);
             if (PASSES == 3) {
@@ -300,6 +343,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=f16, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc_wide = (1u << 4) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const bool wide = (PASSES == 3) && (2 * bn <= 256) && (bn % 8 == 0);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -323,8 +368,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int k = 0; k < TC_BK / 16; ++k) {
               const uint32_t acc = (ki > 0 || k > 0) ? 1u : 0u;
               const uint64_t ko = (uint64_t)(k * 2);  // +32 B per K=16 step, in 16 B units
-              umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc, acc);
-              umma_f16(d_lo, a_hi + ko, b_lo + ko, idesc, acc);
+              if (wide) {
+                // B_hi and B_lo are adjacent in smem and acc_hh / acc_lo adjacent in TMEM: one N = 2*bn MMA computes
+                // [A_hi*B_hi | A_hi*B_lo] and reads A_hi once (operand fetch from smem is the scarce resource)
+                umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc_wide, acc);
+              } else {
+                umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc, acc);
+                umma_f16(d_lo, a_hi + ko, b_lo + ko, idesc, acc);
+              }
               umma_f16(d_lo, a_lo + ko, b_hi + ko, idesc, 1u);
             }
           } else {

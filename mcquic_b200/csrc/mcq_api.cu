@@ -82,6 +82,7 @@ int num_sms() {
 //   stride 1: dims {C,  W,   1, H,   N}
 //   stride 2: dims {2C, W/2, 2, H/2, N}   (x parity folded into the channel axis, y parity its own axis)
 int encode_act_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int stride, int tw, int th, int tn) {
+  // c = channels of the tensor in memory (the kernel may read a slice of them)
   // box = {64 channels, tw, 1, th, tn}
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MCQ_ERR_DRIVER;
@@ -156,6 +157,7 @@ int fill_args(const mcq_conv_params* p, ConvArgs& a) {
   a.hout = p->hin / p->stride; a.wout = p->win / p->stride;
   a.cout = p->cout; a.cout_pad = p->cout_pad; a.ksize = p->ksize; a.stride = p->stride;
   a.ktotal = p->ksize * p->ksize * p->cin;
+  a.cin_total = p->cin; a.ch_off = 0;
   a.mode = p->mode; a.store = p->store; a.o0_act = p->out0_act; a.o1_act = p->out1_act; a.passes = p->passes;
   return 0;
 }
@@ -221,12 +223,12 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
 
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
-  int rc = encode_act_map(&tmA_hi, a.a_hi, a.n, a.hin, a.win, a.cin, a.stride, a.tw, a.th, a.tn);
+  int rc = encode_act_map(&tmA_hi, a.a_hi, a.n, a.hin, a.win, a.cin_total, a.stride, a.tw, a.th, a.tn);
   if (rc) return rc;
   rc = encode_weight_map(&tmB_hi, a.w_hi, a.cout_pad, a.ktotal, bn);
   if (rc) return rc;
   if (a.passes == 3) {
-    rc = encode_act_map(&tmA_lo, a.a_lo, a.n, a.hin, a.win, a.cin, a.stride, a.tw, a.th, a.tn);
+    rc = encode_act_map(&tmA_lo, a.a_lo, a.n, a.hin, a.win, a.cin_total, a.stride, a.tw, a.th, a.tn);
     if (rc) return rc;
     rc = encode_weight_map(&tmB_lo, a.w_lo, a.cout_pad, a.ktotal, bn);
     if (rc) return rc;
@@ -315,14 +317,18 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
   hp.groups_m = (hp.tiles_m + cl - 1) / cl;
   // smem budget: A buffers (double/triple) + as many weight stages as fit
   const size_t a_buf = (size_t)hp.a_bytes * np;
-  const size_t b_stage = (size_t)bn * TC_BK * 2 * np;
+  hp.tps = env_int("MCQ_HALO_TPS", a.passes == 3 ? 1 : 3);
+  if (hp.tps != 1 && hp.tps != 3) return MCQ_ERR_BAD_ARG;
+  const size_t b_stage = (size_t)bn * TC_BK * 2 * np * hp.tps;
   const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128;
   const size_t budget = 226 * 1024 - 1024 - 512 - epi_bytes;
   a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
   hp.na = (a.passes == 3) ? 2 : 3;
   int nbs = (int)((budget - a_buf * hp.na) / b_stage);
+  if (nbs < 3 && hp.na > 2) { hp.na = 2; nbs = (int)((budget - a_buf * hp.na) / b_stage); }
+  if (nbs < 2 && hp.tps > 1) return MCQ_ERR_UNSUPPORTED;
   if (nbs > 8) nbs = 8;
-  if (nbs < 2) { hp.na = 2; nbs = (int)((budget - a_buf * hp.na) / b_stage); }
+  if (env_int("MCQ_HALO_NBS", 0) > 0 && env_int("MCQ_HALO_NBS", 0) < nbs) nbs = env_int("MCQ_HALO_NBS", 0);
   if (nbs < 2) return MCQ_ERR_UNSUPPORTED;
   hp.nbs = nbs;
   const size_t smem = a_buf * hp.na + b_stage * nbs + 8 * (2 * hp.na + 2 * nbs + 4) + 16 + 1024 + epi_bytes;
@@ -379,7 +385,10 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
   if (p->impl == MCQ_IMPL_SIMT) return launch_simt(a, st);
   if (p->impl != MCQ_IMPL_TCGEN05) return MCQ_ERR_BAD_ARG;
   if (!tc_supported(a)) return MCQ_ERR_UNSUPPORTED;
-  if (halo_supported(a) && env_int("MCQ_HALO", 0)) return launch_halo(a, st);
+  if (halo_supported(a) && env_int("MCQ_HALO", 1)) {
+    rc = launch_halo(a, st);
+    if (rc != MCQ_ERR_UNSUPPORTED) return rc;
+  }
   return launch_tc(a, st);
 }
 
@@ -390,17 +399,15 @@ int mcq_stem_conv(const float* x, int32_t n, int32_t h, int32_t w, int32_t pad_t
   MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && hp >= h && wp >= w && hp % 2 == 0 && wp % 2 == 0);
   MCQ_CHECK_ARG(pad_top >= 0 && pad_left >= 0 && pad_top <= hp - h && pad_left <= wp - w);
   MCQ_CHECK_ARG(pad_top < h && (hp - h - pad_top) < h && pad_left < w && (wp - w - pad_left) < w);  // reflect pad limit
-  MCQ_CHECK_ARG(cout % 4 == 0 && cout / 4 <= 256 && 27 * cout * 4 <= 48 * 1024);
+  MCQ_CHECK_ARG(cout % 4 == 0 && (27 * cout + 9 * (2 * STEM_PIX + 1)) * 4 <= 48 * 1024);
   StemArgs a;
   a.x = x; a.w = wgt; a.bias = bias; a.out_f32 = out_f32; a.o_hi = (__half*)out_hi; a.o_lo = (__half*)out_lo;
   a.o_act = out_act; a.n = n; a.h = h; a.w_ = w; a.pad_top = pad_top; a.pad_left = pad_left; a.hp = hp; a.wp = wp;
   a.cout = cout; a.hout = hp / 2; a.wout = wp / 2;
-  const int cg = cout / 4;
-  const int ppb = 256 / cg > 0 ? 256 / cg : 1;
-  const int threads = ppb * cg;
-  const long long total = (long long)n * a.hout * a.wout;
-  const unsigned grid = (unsigned)((total + ppb - 1) / ppb);
-  stem_conv_kernel<<<grid, threads, 27 * cout * sizeof(float), (cudaStream_t)stream>>>(a);
+  const int strips = (a.wout + STEM_PIX - 1) / STEM_PIX;
+  const long long blocks = (long long)n * a.hout * strips;
+  const size_t smem = (27 * (size_t)cout + 9 * (2 * STEM_PIX + 1)) * sizeof(float);
+  stem_conv_kernel<<<(unsigned)blocks, STEM_THREADS, smem, (cudaStream_t)stream>>>(a);
   g_launches++;
   return cuda_status();
 }
@@ -424,6 +431,58 @@ int mcq_vq_assign(const float* x, const float* codebook, const float* c2, int64_
   }
   dim3 grid((unsigned)((a.P + VQ_TP - 1) / VQ_TP), (unsigned)m);
   vq_assign_kernel<<<grid, VQ_THREADS, smem, (cudaStream_t)stream>>>(a);
+  g_launches++;
+  return cuda_status();
+}
+
+int64_t mcq_vq_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t m, int32_t k, int32_t d) {
+  (void)k;
+  const int64_t P = (int64_t)n * h * w, C = (int64_t)m * d;
+  // [hi plane | lo plane] fp16, |x|^2 fp32 [P, m], keys u64 [P, m]; every section 256 B aligned
+  auto al = [](int64_t v) { return (v + 255) / 256 * 256; };
+  return al(P * C * 2) * 2 + al(P * m * 4) + al(P * m * 8);
+}
+
+int mcq_vq_assign_tc(const float* x, const void* cb_hi, const void* cb_lo, float cb_scale, const float* c2,
+                     int64_t* codes, int32_t* hist, int32_t n, int32_t h, int32_t w, int32_t m, int32_t k, int32_t d,
+                     void* workspace, int64_t workspace_bytes, mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && cb_hi && cb_lo && c2 && codes && workspace);
+  MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && m > 0 && k > 0 && d > 0);
+  if (d % TC_BK != 0 || k % 32 != 0) return MCQ_ERR_UNSUPPORTED;
+  MCQ_CHECK_ARG(workspace_bytes >= mcq_vq_workspace_bytes(n, h, w, m, k, d));
+  MCQ_CHECK_ARG(((uintptr_t)workspace & 255) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t P = (int64_t)n * h * w, C = (int64_t)m * d;
+  auto al = [](int64_t v) { return (v + 255) / 256 * 256; };
+  char* ws = (char*)workspace;
+  __half* hi = (__half*)ws;
+  __half* lo = (__half*)(ws + al(P * C * 2));
+  float* x2 = (float*)(ws + 2 * al(P * C * 2));
+  unsigned long long* keys = (unsigned long long*)(ws + 2 * al(P * C * 2) + al(P * m * 4));
+  vq_prep_kernel<<<(unsigned)((P * m + 127) / 128), 128, 0, st>>>(x, (int)P, m, d, hi, lo, x2, keys);
+  g_launches++;
+  int rc = cuda_status();
+  if (rc) return rc;
+  for (int mi = 0; mi < m; ++mi) {
+    ConvArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.a_hi = hi; a.a_lo = lo;
+    a.w_hi = (const __half*)cb_hi + (size_t)mi * k * d;   // packed codebook [m, k, d] fp16, value = c * 2^e
+    a.w_lo = (const __half*)cb_lo + (size_t)mi * k * d;
+    a.bias = c2 + (size_t)mi * k;                          // |c_k|^2
+    a.aux = x2 + mi;                                       // |x|^2, stride m
+    a.argmin_keys = keys + mi;
+    a.argmin_stride = m;
+    a.w_scale = cb_scale; a.res1_scale = 1.f;
+    a.n = n; a.hin = h; a.win = w; a.cin = d; a.cin_total = (int)C; a.ch_off = mi * d;
+    a.hout = h; a.wout = w;
+    a.cout = k; a.cout_pad = k; a.ksize = 1; a.stride = 1; a.ktotal = d;
+    a.mode = EPI_ARGMIN; a.store = MCQ_STORE_NHWC; a.passes = 3;
+    rc = launch_tc(a, st);
+    if (rc) return rc;
+  }
+  vq_finalize_kernel<<<(unsigned)((P * m + 127) / 128), 128, 0, st>>>(keys, (int)P, h * w, m, k, (long long*)codes,
+                                                                       hist);
   g_launches++;
   return cuda_status();
 }

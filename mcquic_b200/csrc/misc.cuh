@@ -22,51 +22,64 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
   return i;
 }
 
-// block = (cout/4 threads for channels) x (pixels): each thread 4 output channels of one pixel
-__global__ void __launch_bounds__(256) stem_conv_kernel(const StemArgs a) {
-  extern __shared__ float ws[];  // [27][cout] transposed weights
-  for (int i = threadIdx.x; i < 27 * a.cout; i += blockDim.x) {
+// One block = STEM_PIX consecutive output pixels of one output row x all cout.  The 3 x (2*STEM_PIX+1) x 3 input
+// patch (reflect pad / zero pad resolved while loading) and the transposed weights sit in shared memory; a warp owns
+// STEM_PIX/4 pixels, lane l the 4 output channels [4l, 4l+4) (+128 per further channel group): its 108 weights stay
+// in registers, the 27 inputs of a pixel are warp-uniform broadcasts, and every store is 512 contiguous bytes.
+constexpr int STEM_PIX = 64;
+constexpr int STEM_THREADS = 128;   // 156 registers/thread (108 weights): 3 blocks per SM
+
+__global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const StemArgs a) {
+  extern __shared__ float stem_smem[];
+  float* ws = stem_smem;                         // [27][cout]
+  float* patch = stem_smem + 27 * a.cout;        // [3 ch][3 rows][2*STEM_PIX + 1]
+  constexpr int PW = 2 * STEM_PIX + 1;
+  for (int i = threadIdx.x; i < 27 * a.cout; i += STEM_THREADS) {
     const int co = i % a.cout, t = i / a.cout;
     ws[t * a.cout + co] = a.w[co * 27 + t];
   }
+  const int strips = (a.wout + STEM_PIX - 1) / STEM_PIX;
+  const int strip = blockIdx.x % strips;
+  const int oy = (blockIdx.x / strips) % a.hout;
+  const int n = blockIdx.x / (strips * a.hout);
+  const int ox0 = strip * STEM_PIX;
+  for (int i = threadIdx.x; i < 9 * PW; i += STEM_THREADS) {
+    const int col = i % PW, rr = (i / PW) % 3, ci = i / (3 * PW);
+    const int Y = 2 * oy + rr - 1, X = 2 * ox0 + col - 1;   // coordinates in the padded image (zeros outside it)
+    float v = 0.f;
+    if (Y >= 0 && Y < a.hp && X >= 0 && X < a.wp) {
+      const int sy = reflect_idx(Y - a.pad_top, a.h), sx = reflect_idx(X - a.pad_left, a.w_);
+      v = a.x[(((size_t)n * 3 + ci) * a.h + sy) * a.w_ + sx];
+    }
+    patch[i] = v;
+  }
   __syncthreads();
-  const int cg = a.cout / 4;
-  const int pix_per_block = blockDim.x / cg;
-  const int lp = threadIdx.x / cg, c0 = (threadIdx.x % cg) * 4;
-  const long long pix = (long long)blockIdx.x * pix_per_block + lp;
-  const long long total = (long long)a.n * a.hout * a.wout;
-  if (lp >= pix_per_block || pix >= total) return;
-  const int ox = (int)(pix % a.wout);
-  const long long t = pix / a.wout;
-  const int oy = (int)(t % a.hout);
-  const int n = (int)(t / a.hout);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int ci = 0; ci < 3; ++ci) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c0 = lane * 4; c0 < a.cout; c0 += 128) {
+    float4 w[27];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int Y = 2 * oy + r - 1;  // coordinate in the padded image (zero padding outside it)
+    for (int t = 0; t < 27; ++t) w[t] = *reinterpret_cast<const float4*>(ws + t * a.cout + c0);
+    const float4 b = *reinterpret_cast<const float4*>(a.bias + c0);
+#pragma unroll 2
+    for (int pp = 0; pp < STEM_PIX / (STEM_THREADS / 32); ++pp) {
+      const int px = warp * (STEM_PIX / (STEM_THREADS / 32)) + pp;
+      const int ox = ox0 + px;
+      if (ox >= a.wout) break;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int X = 2 * ox + s - 1;
-        float v = 0.f;
-        if (Y >= 0 && Y < a.hp && X >= 0 && X < a.wp) {
-          const int sy = reflect_idx(Y - a.pad_top, a.h), sx = reflect_idx(X - a.pad_left, a.w_);
-          v = a.x[(((size_t)n * 3 + ci) * a.h + sy) * a.w_ + sx];
-        }
-        const float4 wv = *reinterpret_cast<const float4*>(ws + (ci * 9 + r * 3 + s) * a.cout + c0);
-        acc[0] = fmaf(v, wv.x, acc[0]);
-        acc[1] = fmaf(v, wv.y, acc[1]);
-        acc[2] = fmaf(v, wv.z, acc[2]);
-        acc[3] = fmaf(v, wv.w, acc[3]);
+      for (int t = 0; t < 27; ++t) {      // t = ci*9 + r*3 + s  (nn.Conv2d weight order)
+        const float v = patch[(t / 9) * 3 * PW + ((t / 3) % 3) * PW + 2 * px + (t % 3)];
+        acc[0] = fmaf(v, w[t].x, acc[0]);
+        acc[1] = fmaf(v, w[t].y, acc[1]);
+        acc[2] = fmaf(v, w[t].z, acc[2]);
+        acc[3] = fmaf(v, w[t].w, acc[3]);
       }
+      float y[4] = {acc[0] + b.x, acc[1] + b.y, acc[2] + b.z, acc[3] + b.w};
+      const size_t off = (((size_t)n * a.hout + oy) * a.wout + ox) * a.cout + c0;
+      if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + off) = make_float4(y[0], y[1], y[2], y[3]);
+      if (a.o_hi) store_planes<4>(a.o_hi, a.o_lo, off, y, a.o_act);
     }
   }
-  float y[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) y[j] = acc[j] + a.bias[c0 + j];
-  const size_t off = (size_t)pix * a.cout + c0;
-  if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + off) = make_float4(y[0], y[1], y[2], y[3]);
-  if (a.o_hi) store_planes<4>(a.o_hi, a.o_lo, off, y, a.o_act);
 }
 
 __global__ void split_planes_kernel(const float* x, long long count4, int act, __half* hi, __half* lo) {

@@ -143,6 +143,39 @@ __global__ void __launch_bounds__(VQ_THREADS) vq_assign_kernel(const VqArgs a) {
   }
 }
 
+// ---- tensor-core VQ helpers (vq_assign_tc): the x.c_k GEMM runs as a 1x1 tcgen05 'convolution' (3-pass split-fp16)
+// whose epilogue does the distance + argmin (conv_tc.cuh, EPI_ARGMIN).
+// prep: fp32 latents -> split-fp16 planes, |x|^2 per (point, codebook) summed in channel order, keys = +inf.
+__global__ void vq_prep_kernel(const float* x, int P, int m, int d, __half* hi, __half* lo, float* x2,
+                               unsigned long long* keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * m) return;
+  const int pt = i / m, mi = i - pt * m;
+  const size_t base = (size_t)pt * m * d + (size_t)mi * d;
+  float s = 0.f;
+  for (int j = 0; j < d; j += 4) {
+    float y[4];
+    load_f32v<4>(x, base + j, y);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s = fmaf(y[q], y[q], s);
+    store_planes<4>(hi, lo, base + j, y, MCQ_ACT_NONE);
+  }
+  x2[i] = s;
+  keys[i] = 0xFFFFFFFFFFFFFFFFull;
+}
+
+// finalize: packed minima -> int64 codes [n, m, hw] (+ histogram)
+__global__ void vq_finalize_kernel(const unsigned long long* keys, int P, int hw, int m, int k, long long* codes,
+                                   int* hist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * m) return;
+  const int pt = i / m, mi = i - pt * m;
+  const int code = (int)(keys[i] & 0xFFFFFFFFull);
+  const int nn = pt / hw, pix = pt - nn * hw;
+  codes[((size_t)nn * m + mi) * hw + pix] = code;
+  if (hist && code >= 0 && code < k) atomicAdd(hist + (size_t)mi * k + code, 1);
+}
+
 // codes [n, m, hw] -> codebook rows, NHWC [n, hw, m*d]; one thread per 4 channels
 struct DequantArgs {
   const long long* codes;

@@ -355,10 +355,23 @@ class Engine:
     # ------------------------------------------------------------------ VQ
     def vq_assign(self, x_nhwc: torch.Tensor, codebook: torch.Tensor, c2: torch.Tensor, n: int, h: int, w: int,
                   logits: bool = False, logit_scale: Optional[torch.Tensor] = None,
-                  hist: Optional[torch.Tensor] = None):
+                  hist: Optional[torch.Tensor] = None, packed=None):
+        """packed = (cb_hi, cb_lo, scale) split-fp16 codebook: enables the tensor-core path (d % 64 == 0)."""
         m, k, d = codebook.shape
-        codes = torch.empty((n, m, h, w), dtype=torch.int64, device=x_nhwc.device)
-        lg = torch.empty((n, m, h, w, k), dtype=torch.float32, device=x_nhwc.device) if logits else None
+        dev = x_nhwc.device
+        codes = torch.empty((n, m, h, w), dtype=torch.int64, device=dev)
+        use_tc = (packed is not None and not logits and d % 64 == 0 and k % 32 == 0 and not self.emulated
+                  and self.impl == _lib.IMPL_TCGEN05)
+        if use_tc:
+            nbytes = int(self.lib.mcq_vq_workspace_bytes(n, h, w, m, k, d))
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            off = (-ws.data_ptr()) % 256
+            _lib.check(self.lib.mcq_vq_assign_tc(_ptr(x_nhwc), _ptr(packed[0]), _ptr(packed[1]), packed[2], _ptr(c2),
+                                                 _ptr(codes), _ptr(hist), n, h, w, m, k, d,
+                                                 ctypes.c_void_p(ws.data_ptr() + off), nbytes, self._stream()),
+                       "mcq_vq_assign_tc")
+            return codes
+        lg = torch.empty((n, m, h, w, k), dtype=torch.float32, device=dev) if logits else None
         _lib.check(self.lib.mcq_vq_assign(_ptr(x_nhwc), _ptr(codebook), _ptr(c2), _ptr(codes), _ptr(lg),
                                           _ptr(logit_scale), _ptr(hist), n, h, w, m, k, d, self._stream()),
                    "mcq_vq_assign")

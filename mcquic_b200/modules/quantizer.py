@@ -58,20 +58,28 @@ class _multiCodebookQuantization(nn.Module):
         self._bound = LowerBound(_EPS)  # checkpoint key `_bound.bound` (quantizer.py:107)
         self._c2_cache = None
 
-    def _c2(self) -> torch.Tensor:
-        """|c_k|^2 per codeword, [m, k] (quantizer.py:165), cached per codebook version."""
+    def _tables(self):
+        """Per codebook version: fp32 codebook, |c_k|^2 [m, k] (quantizer.py:165) and the split-fp16 packing the
+        tensor-core kernel consumes."""
         ver = (self._codebook._version, self._codebook.data_ptr())
         if self._c2_cache is None or self._c2_cache[0] != ver:
+            from ..engine import split_weight
             with torch.no_grad():
-                self._c2_cache = (ver, (self._codebook.detach().float() ** 2).sum(-1).contiguous())
-        return self._c2_cache[1]
+                cb = self._codebook.detach().float().contiguous()
+                hi, lo, scale = split_weight(cb.reshape(-1, self._d))
+                self._c2_cache = (ver, cb, (cb ** 2).sum(-1).contiguous(), (hi, lo, scale))
+        return self._c2_cache[1:]
+
+    def _c2(self) -> torch.Tensor:
+        return self._tables()[1]
 
     def _cb(self) -> torch.Tensor:
-        return self._codebook.detach().float().contiguous()
+        return self._tables()[0]
 
     def encode_nhwc(self, x_f32: torch.Tensor, n: int, h: int, w: int, hist: Optional[torch.Tensor] = None,
                     engine: Optional[Engine] = None) -> torch.Tensor:
-        return (engine or default_engine()).vq_assign(x_f32, self._cb(), self._c2(), n, h, w, hist=hist)
+        cb, c2, packed = self._tables()
+        return (engine or default_engine()).vq_assign(x_f32, cb, c2, n, h, w, hist=hist, packed=packed)
 
     @torch.no_grad()
     def encode(self, x: torch.Tensor) -> torch.Tensor:

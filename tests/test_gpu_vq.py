@@ -50,6 +50,52 @@ def test_assign_matches_oracle(n, h, w, m, k, d):
     assert torch.equal(deq.cpu(), O.vq_dequantize(codes.cpu(), cb))
 
 
+@pytest.mark.parametrize("n,h,w,m,k,d", [
+    (2, 16, 16, 1, 8192, 128),   # qp=1 level 0
+    (64, 4, 4, 1, 512, 128),     # qp=1 level 2 at the benchmark batch (N tile narrowed to fill the SMs)
+    (2, 8, 8, 2, 2048, 64),      # qp=2-like: two codebooks, channel slices of the same latent
+    (1, 5, 7, 1, 96, 64),        # ragged point count, k = 96 (N tile 96)
+])
+def test_tensor_core_assign_matches_oracle(n, h, w, m, k, d):
+    """mcq_vq_assign_tc: x.c_k on tcgen05 (3-pass split fp16), distance + argmin in the GEMM epilogue."""
+    from mcquic_b200.engine import split_weight
+    x = uniform((n, m * d, h, w), "vqtc.x", 7) * 0.26
+    cb = uniform((m, k, d), "vqtc.cb", 7) * 0.19
+    eng = Engine()
+    xg = eng.from_nchw(x.cuda(), {"f32"}).f32
+    cbg = cb.cuda().contiguous()
+    c2 = (cbg ** 2).sum(-1).contiguous()
+    hist = torch.zeros(m * k, dtype=torch.int32, device="cuda")
+    packed = split_weight(cbg.reshape(-1, d))
+    before = eng.lib.mcq_kernel_launch_count()
+    codes = eng.vq_assign(xg, cbg, c2, n, h, w, hist=hist, packed=packed)
+    assert eng.lib.mcq_kernel_launch_count() - before == 2 + m      # prep + m GEMMs + finalize: the tcgen05 path ran
+    ref = O.vq_assign(x, cb)
+    mism = codes.cpu() != ref
+    if int(mism.sum()):
+        assert float(O.vq_margin(x, cb)[mism].max()) < 2e-6, "index flips only allowed at fp32 near-ties"
+    simt = eng.vq_assign(xg, cbg, c2, n, h, w)
+    mism2 = codes != simt
+    assert int(mism2.sum()) == 0 or float(O.vq_margin(x, cb)[mism2.cpu()].max()) < 2e-6
+    exp = torch.cat([h_.flatten() for h_ in O.code_histogram([codes.cpu()], [k])]).int()
+    assert torch.equal(hist.cpu(), exp)
+    assert eng.lib.mcq_device_error_flag() == 0
+
+
+def test_tensor_core_ties_pick_the_first_index():
+    from mcquic_b200.engine import split_weight
+    m, k, d = 1, 256, 64
+    cb = uniform((m, k, d), "tie.cb64", 2)
+    cb[:, 200] = cb[:, 17]
+    cb[:, 150] = cb[:, 17]
+    x = cb[:, 17].reshape(1, m * d, 1, 1).repeat(3, 1, 2, 2).clone()
+    eng = Engine()
+    cbg = cb.cuda().contiguous()
+    codes = eng.vq_assign(eng.from_nchw(x.cuda(), {"f32"}).f32, cbg, (cbg ** 2).sum(-1).contiguous(), 3, 2, 2,
+                          packed=split_weight(cbg.reshape(-1, d)))
+    assert (codes == 17).all()
+
+
 def test_exact_ties_pick_the_first_index():
     m, k, d = 2, 300, 8
     cb = uniform((m, k, d), "tie.cb", 2)
