@@ -226,7 +226,12 @@ def run_ours(args):
     launches_before = _lib.launch_count() + model.graph_launches
     with ClockSampler(local_rank) as clocks:
         barrier()
+        prof_range = bool(os.environ.get("MCQ_CUDA_PROFILER_RANGE"))   # `ncu --profile-from-start off` captures only this
+        if prof_range:
+            torch.cuda.cudart().cudaProfilerStart()
         ms = timed(step_device, args.steps)
+        if prof_range:
+            torch.cuda.cudart().cudaProfilerStop()
         barrier()
         launches = _lib.launch_count() + model.graph_launches - launches_before
         ms_e2e = timed(step_e2e, args.steps)
