@@ -75,6 +75,8 @@ typedef struct mcq_conv_params {
   int32_t out1_act;
   int32_t passes;   /* 1 or 3 */
   int32_t impl;     /* MCQ_IMPL_* */
+  void* ev_start;   /* optional cudaEvent_t recorded on the stream immediately before / after the kernel launch */
+  void* ev_stop;    /* (tight per-launch timing for bench.py's roofline leg); NULL = none */
 } mcq_conv_params;
 
 /* Replaces nn.Conv2d 3x3 / 1x1 (+ the elementwise ops around it) as used by mcquic/nn/blocks.py:62-288,

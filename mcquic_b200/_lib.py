@@ -25,6 +25,7 @@ class ConvParams(_c.Structure):
         ("out0_hi", _c.c_void_p), ("out0_lo", _c.c_void_p), ("out0_act", _c.c_int32),
         ("out1_hi", _c.c_void_p), ("out1_lo", _c.c_void_p), ("out1_act", _c.c_int32),
         ("passes", _c.c_int32), ("impl", _c.c_int32),
+        ("ev_start", _c.c_void_p), ("ev_stop", _c.c_void_p),
     ]
 
 

@@ -137,9 +137,13 @@ __device__ __forceinline__ void load_f32v(const float* p, size_t off, float (&r)
 
 // Fused epilogue for NV consecutive GEMM columns [c0, c0+NV) of output pixel (n, oy, ox).
 // v[] = accumulator * w_scale (bias NOT yet added).  c0 % NV == 0.
+// bias_src: where to read the bias from (the tensor-core kernels keep a copy in shared memory: with the whole
+// carve-out given to smem there is no L1, and a global bias fetch per call is a ~300-cycle stall)
 template <int NV, bool FAST = false>
-__device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy, int ox, int c0, float (&v)[NV]) {
+__device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy, int ox, int c0, float (&v)[NV],
+                                               const float* bias_src = nullptr) {
   if (c0 >= p.cout) return;
+  if (bias_src == nullptr) bias_src = p.bias;
   if (p.store == MCQ_STORE_SHUFFLE_NCHW) {
     // last layer (compressor.py:139): GEMM column 4c+2i+j -> out[n, c, 2oy+i, 2ox+j], fp32 NCHW
     const int cq = p.cout >> 2, H2 = p.hout * 2, W2 = p.wout * 2;
@@ -148,7 +152,7 @@ __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy,
       const int col = c0 + j;
       if (col < p.cout) {
         const int c = col >> 2, i = (col >> 1) & 1, jj = col & 1;
-        p.out_f32[(((size_t)n * cq + c) * H2 + (2 * oy + i)) * W2 + (2 * ox + jj)] = v[j] + p.bias[col];
+        p.out_f32[(((size_t)n * cq + c) * H2 + (2 * oy + i)) * W2 + (2 * ox + jj)] = v[j] + bias_src[col];
       }
     }
     return;
@@ -164,7 +168,7 @@ __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy,
   }
   const size_t off = (((size_t)n * H + py) * W + px) * C + c;
   float b[NV], y[NV];
-  load_f32v<NV>(p.bias, c0, b);
+  load_f32v<NV>(bias_src, c0, b);
 #pragma unroll
   for (int j = 0; j < NV; ++j) y[j] = v[j] + b[j];
   if (p.mode == MCQ_EPI_LINEAR) {

@@ -99,6 +99,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint32_t* tmem_slot =
       reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8u * (2 * na + 2 * nbs + 4));
   const uint32_t epi_base = (bar_base + 8u * (2 * na + 2 * nbs + 4) + 16u + 127u) & ~127u;
+  float* bias_smem = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + TC_EPI_WARPS * TC_EPI_STAGE_BYTES);
+  const bool bias_staged = p.cout <= TC_BIAS_SMEM_FLOATS;
+  if (bias_staged)
+    for (int i = threadIdx.x; i < p.cout; i += TC_THREADS) bias_smem[i] = p.bias[i];
 
   const int acc_cols = NP * bn;
   const int nbuf = (2 * acc_cols <= (int)TC_TMEM_COLS) ? 2 : 1;
@@ -276,7 +280,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       mbar_wait(tfull_bar(buf), use & 1u, 16);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix);
+      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));

@@ -28,6 +28,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;    // 16 KB
 constexpr uint32_t TC_TMEM_COLS = 512;
 constexpr unsigned long long TC_WATCHDOG_NS = 4ull * 1000 * 1000 * 1000;   // 4 s: far beyond any legitimate wait
 constexpr int TC_EPI_STAGE_BYTES = 2048;          // per epilogue warp: 32 rows x 16 fp32 columns
+constexpr int TC_BIAS_SMEM_FLOATS = 384;            // bias vectors up to this length are staged in shared memory
 
 __device__ int g_watchdog_flag = 0;
 
@@ -147,7 +148,7 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
 // pix(row, n, oy, ox) -> valid maps a tile row to its output pixel.
 template <int PASSES, class PixFn>
 __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, int bn, int ct, int cg, int q, int lane,
-                                           uint32_t stage, PixFn pix) {
+                                           uint32_t stage, PixFn pix, const float* bias_src) {
   int n_[2], oy_[2], ox_[2];
   bool ok_[2];
 #pragma unroll
@@ -234,7 +235,7 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
                        : "memory");
         }
         if (ok_[it] && !p.debug_skip_store)
-          epilogue_store<8, PASSES == 1>(p, n_[it], oy_[it], ox_[it], ct * bn + col0 + col8, vv);
+          epilogue_store<8, PASSES == 1>(p, n_[it], oy_[it], ox_[it], ct * bn + col0 + col8, vv, bias_src);
       }
       __syncwarp();
     }
@@ -266,6 +267,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * stages + 2 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + stage_bytes * stages + 8u * (2 * stages + 4));
   const uint32_t epi_base = (bar_base + 8u * (2 * stages + 4) + 16u + 127u) & ~127u;   // 16 x 2 KB transpose buffers
+  float* bias_smem = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + TC_EPI_WARPS * TC_EPI_STAGE_BYTES);
+  const bool bias_staged = (p.mode != EPI_ARGMIN) && (p.cout <= TC_BIAS_SMEM_FLOATS);
+  if (bias_staged)
+    for (int i = threadIdx.x; i < p.cout; i += TC_THREADS) bias_smem[i] = p.bias[i];
 
   const int acc_cols = (PASSES == 3 ? 2 : 1) * bn;   // TMEM columns per accumulator buffer
   const int nbuf = (2 * acc_cols <= (int)TC_TMEM_COLS) ? 2 : 1;
@@ -417,7 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(tfull_bar(buf), use & 1u, 4);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix);
+      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));

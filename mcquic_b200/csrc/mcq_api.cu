@@ -20,6 +20,13 @@ using namespace mcq;
 namespace {
 
 std::atomic<int> g_launches{0};
+// optional per-launch timing events of the current mcq_conv2d call (thread-local: the library is re-entrant per thread)
+thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+struct EvScope {
+  cudaStream_t st;
+  explicit EvScope(cudaStream_t s) : st(s) { if (g_ev_start) cudaEventRecord(g_ev_start, st); }
+  ~EvScope() { if (g_ev_stop) cudaEventRecord(g_ev_stop, st); }
+};
 
 #define MCQ_CHECK_ARG(cond)            \
   do {                                 \
@@ -165,6 +172,7 @@ int fill_args(const mcq_conv_params* p, ConvArgs& a) {
 int launch_simt(const ConvArgs& a, cudaStream_t st) {
   const long long M = (long long)a.n * a.hout * a.wout;
   dim3 grid((unsigned)((M + SIMT_TM - 1) / SIMT_TM), (unsigned)((a.cout + SIMT_TN - 1) / SIMT_TN));
+  EvScope ev(st);
   conv_simt_kernel<<<grid, SIMT_THREADS, 0, st>>>(a);
   g_launches++;
   return cuda_status();
@@ -214,8 +222,9 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   }
   // ---- pipeline depth
   const size_t stage_bytes = (size_t)(TC_A_BYTES + bn * TC_BK * 2) * (a.passes == 3 ? 2 : 1);
-  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128;
-  int stages = (int)((226 * 1024 - 1024 - 512 - epi_bytes) / stage_bytes);
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + TC_BIAS_SMEM_FLOATS * 4;
+  // 227 KB of dynamic smem per CTA: 1 KB alignment slack, 256 B barriers, epilogue staging, the rest = pipeline
+  int stages = (int)((227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return MCQ_ERR_UNSUPPORTED;
   a.stages = stages;
@@ -239,6 +248,7 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   const int total_tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.tiles_c;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   cudaError_t e;
+  EvScope ev(st);
   if (a.passes == 3) {
     static bool attr3 = false;
     if (!attr3) {
@@ -288,6 +298,7 @@ int launch_halo_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t sme
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  EvScope ev(st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], a, hp);
   g_launches++;
   return e == cudaSuccess ? cuda_status() : (int)e;
@@ -296,7 +307,7 @@ int launch_halo_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t sme
 int launch_halo(ConvArgs& a, cudaStream_t st) {
   int bn = (a.cout_pad <= 256 && a.cout_pad % 128 != 0) ? a.cout_pad : 128;
   if (a.cout_pad < 128) bn = a.cout_pad;
-  if (a.cout_pad % bn != 0 || bn % 32 != 0) return MCQ_ERR_UNSUPPORTED;
+  if (a.cout_pad % bn != 0 || (bn % 32 != 0 && bn != 16)) return MCQ_ERR_UNSUPPORTED;
   const int np = a.passes == 3 ? 2 : 1;
   if (np * bn > (int)TC_TMEM_COLS) return MCQ_ERR_UNSUPPORTED;
   a.bn = bn;
@@ -320,8 +331,8 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
   hp.tps = env_int("MCQ_HALO_TPS", a.passes == 3 ? 1 : 3);
   if (hp.tps != 1 && hp.tps != 3) return MCQ_ERR_BAD_ARG;
   const size_t b_stage = (size_t)bn * TC_BK * 2 * np * hp.tps;
-  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128;
-  const size_t budget = 226 * 1024 - 1024 - 512 - epi_bytes;
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + TC_BIAS_SMEM_FLOATS * 4;
+  const size_t budget = 227 * 1024 - 1024 - 256 - epi_bytes;
   a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
   hp.na = (a.passes == 3) ? 2 : 3;
   int nbs = (int)((budget - a_buf * hp.na) / b_stage);
@@ -382,14 +393,18 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
   int rc = fill_args(p, a);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->impl == MCQ_IMPL_SIMT) return launch_simt(a, st);
-  if (p->impl != MCQ_IMPL_TCGEN05) return MCQ_ERR_BAD_ARG;
-  if (!tc_supported(a)) return MCQ_ERR_UNSUPPORTED;
-  if (halo_supported(a) && env_int("MCQ_HALO", 1)) {
-    rc = launch_halo(a, st);
-    if (rc != MCQ_ERR_UNSUPPORTED) return rc;
+  g_ev_start = (cudaEvent_t)p->ev_start;
+  g_ev_stop = (cudaEvent_t)p->ev_stop;
+  if (p->impl == MCQ_IMPL_SIMT) rc = launch_simt(a, st);
+  else if (p->impl != MCQ_IMPL_TCGEN05) rc = MCQ_ERR_BAD_ARG;
+  else if (!tc_supported(a)) rc = MCQ_ERR_UNSUPPORTED;
+  else {
+    rc = MCQ_ERR_UNSUPPORTED;
+    if (halo_supported(a) && env_int("MCQ_HALO", 1)) rc = launch_halo(a, st);
+    if (rc == MCQ_ERR_UNSUPPORTED) rc = launch_tc(a, st);
   }
-  return launch_tc(a, st);
+  g_ev_start = g_ev_stop = nullptr;
+  return rc;
 }
 
 int mcq_stem_conv(const float* x, int32_t n, int32_t h, int32_t w, int32_t pad_top, int32_t pad_left, int32_t hp,

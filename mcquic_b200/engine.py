@@ -207,11 +207,13 @@ class Engine:
         p.passes = self.passes if a[1] is not None else 1
         p.impl = self.impl if (pc.cin % 64 == 0) else _lib.IMPL_SIMT
         if self.profile is not None:
+            # the library records these immediately around the kernel launch (after tensor-map encoding)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
+            ev1.record()   # forces creation of the underlying cudaEvent_t handles
+            p.ev_start, p.ev_stop = ev0.cuda_event, ev1.cuda_event
         _lib.check(self.lib.mcq_conv2d(ctypes.byref(p), self._stream()), "mcq_conv2d")
         if self.profile is not None:
-            ev1.record()
             self.profile.append({"flops": 2.0 * x.n * (x.h // pc.stride) * (x.w // pc.stride) * pc.cout * pc.cin * pc.ksize ** 2,
                                  "passes": p.passes, "impl": p.impl, "ev": (ev0, ev1),
                                  "shape": (x.n, x.h, x.w, pc.cin, pc.cout, pc.ksize, pc.stride)})

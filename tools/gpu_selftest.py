@@ -261,10 +261,10 @@ def g_halo():
               store=_lib.STORE_SHUFFLE_NHWC, want=("f32", "sq"))
     g = torch.Generator().manual_seed(0)
     for passes in (3, 1):
-        for (n, h, w, cin, cout) in [(64, 128, 128, 128, 128), (64, 64, 64, 128, 128), (64, 64, 64, 128, 512), (64, 32, 32, 128, 128), (64, 16, 16, 128, 128)]:
+        for (n, h, w, cin, cout) in [(64, 128, 128, 128, 128), (64, 64, 64, 128, 128), (64, 64, 64, 128, 512), (64, 32, 32, 128, 128), (64, 16, 16, 128, 128), (64, 8, 8, 128, 128), (64, 4, 4, 128, 128), (64, 128, 128, 128, 12)]:
             x = torch.randn(n, h, w, cin, generator=g).cuda()
             wt = ((torch.rand(cout, cin, 3, 3, generator=g) * 2 - 1) / (9 * cin) ** 0.5).cuda()
-            store = _lib.STORE_SHUFFLE_NHWC if cout == 512 else 0
+            store = _lib.STORE_SHUFFLE_NHWC if cout == 512 else (_lib.STORE_SHUFFLE_NCHW if cout == 12 else 0)
             pc = pack_conv(wt, torch.zeros(cout).cuda(), 1, store, "cuda")
             eng.passes = passes
             a = make_planes(x, passes)
