@@ -179,6 +179,32 @@ class BaseCompressor(nn.Module):
             raise RuntimeError("code index out of range for its codebook")
         return out
 
+    @torch.no_grad()
+    def compress(self, x: torch.Tensor):
+        """compressor.py:67-77: (codes, binaries [n][L] bytes, n FileHeader records).  encode on the GPU, rANS on the
+        host (one batched multi-threaded call per level)."""
+        from .. import __version__, entropy
+        n, c, h, w = x.shape
+        codes = self.encode(x)
+        binaries, sizes = self._quantizer._entropyCoder.compress(codes)
+        headers = [entropy.FileHeader(__version__, self._qp, size, entropy.ImageSize(height=h, width=w, channel=c))
+                   for size in sizes]
+        return codes, binaries, headers
+
+    @torch.no_grad()
+    def decompress(self, binaries, headers) -> torch.Tensor:
+        """compressor.py:90-112: rANS decode on the host, synthesis on the GPU, centre-crop to the header's image size."""
+        codes = self._quantizer._entropyCoder.decompress(binaries, [hd.CodeSize for hd in headers])
+        restored = self.decode(codes)
+        size = headers[0].ImageSize
+        H, W = restored.shape[-2], restored.shape[-1]
+        top, left = (H - size.height) // 2, (W - size.width) // 2
+        return restored[..., top:top + size.height, left:left + size.width]
+
+    @property
+    def CDFs(self):
+        return self._quantizer.CDFs
+
     def forward(self, x: torch.Tensor):
         raise NotImplementedError("mcquic_b200 accelerates inference (encode/decode); training forward is out of scope")
 

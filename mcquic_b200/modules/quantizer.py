@@ -21,9 +21,9 @@ _EPS = 1e-6  # mcquic/consts.py:25
 
 
 class CodeFrequency(nn.Module):
-    """The state the reference keeps in `EntropyCoder` (mcquic/modules/entropyCoder.py:15-63): per-level
-    [m, k] frequency EMA, initially uniform.  rANS coding itself stays on the host and is out of scope here;
-    this module keeps the `_entropyCoder._freqEMA.{l}` checkpoint keys and the histogram-driven update."""
+    """The reference's `EntropyCoder` (mcquic/modules/entropyCoder.py:15-154): per-level [m, k] frequency EMA (initially
+    uniform; checkpoint keys `_entropyCoder._freqEMA.{l}`), quantized CDF tables and per-image rANS streams.  The
+    coder itself is the host C++ library behind `mcquic_b200.entropy` (bit-identical streams to `mcquic.rans`)."""
 
     def __init__(self, m: int, k: List[int], ema: float = 0.9):
         super().__init__()
@@ -31,10 +31,22 @@ class CodeFrequency(nn.Module):
         self._k = list(k)
         self._m = m
         self._ema = ema
+        self._cdfs = None
 
     @property
     def NormalizedFreq(self) -> List[torch.Tensor]:
         return [(f / f.sum(-1, keepdim=True)).detach().clone() for f in self._freqEMA]
+
+    @property
+    def CDFs(self):
+        """per level uint32 [m, k_l + 1], quantized to 16 bits (entropyCoder.py:50-63)."""
+        ver = tuple(f._version for f in self._freqEMA)
+        if self._cdfs is None or self._cdfs[0] != ver:
+            from .. import entropy
+            import numpy as np
+            tables = [np.stack([entropy.pmf_to_quantized_cdf(row.tolist()) for row in fr.cpu()]) for fr in self.NormalizedFreq]
+            self._cdfs = (ver, tables)
+        return self._cdfs[1]
 
     @torch.no_grad()
     def update(self, flat_hist: torch.Tensor):
@@ -46,6 +58,44 @@ class CodeFrequency(nn.Module):
             off += self._m * ki
             normalized = total / total.sum(-1, keepdim=True)
             self._freqEMA[lv].copy_((1 - self._ema) * normalized + self._ema * self._freqEMA[lv])
+
+    def _check(self, codes: List[torch.Tensor]):
+        # same messages as entropyCoder.py:79-93
+        info = "Please give codes with correct shape, for example, [[1, 2, 24, 24], [1, 2, 12, 12], ...], which is a `level` length list. each code has shape [n, m, h, w]. "
+        if len(codes) < 1:
+            raise RuntimeError("Length of codes is 0.")
+        n, m = codes[0].shape[0], codes[0].shape[1]
+        for code in codes:
+            if n < 1:
+                raise RuntimeError(info + "Now `n` = 0.")
+            if code.shape[1] != m:
+                raise RuntimeError(info + "Now `m` is inconsisitent.")
+            if code.shape[0] != n:
+                raise RuntimeError(info + "Now `n` is inconsisitent.")
+        return n, m
+
+    @torch.no_grad()
+    def compress(self, codes: List[torch.Tensor]):
+        """codes: L x int64 [n, m, h, w] -> (binaries: n lists of L byte strings, n CodeSize records)
+        (entropyCoder.py:96-126; one batched, multi-threaded call per level instead of n Python-level calls)."""
+        from .. import entropy
+        n, m = self._check(codes)
+        per_level = [entropy.encode_level(code, cdf) for code, cdf in zip(codes, self.CDFs)]
+        binaries = [[per_level[lv][i] for lv in range(len(codes))] for i in range(n)]
+        size = entropy.CodeSize([m] * len(codes), [c.shape[2] for c in codes], [c.shape[3] for c in codes], list(self._k))
+        return binaries, [size for _ in range(n)]
+
+    @torch.no_grad()
+    def decompress(self, binaries, codeSizes) -> List[torch.Tensor]:
+        """inverse of `compress` (entropyCoder.py:128-154): L x int64 [n, m, h, w] on this module's device."""
+        from .. import entropy
+        size = codeSizes[0]
+        out = []
+        for lv, cdf in enumerate(self.CDFs):
+            streams = [b[lv] for b in binaries]
+            out.append(entropy.decode_level(streams, size.m[lv], size.heights[lv], size.widths[lv], cdf)
+                       .to(self._freqEMA[0].device))
+        return out
 
 
 class _multiCodebookQuantization(nn.Module):
@@ -243,6 +293,10 @@ class UMGMQuantizer(nn.Module):
     @property
     def NormalizedFreq(self):
         return self._entropyCoder.NormalizedFreq
+
+    @property
+    def CDFs(self):
+        return self._entropyCoder.CDFs
 
     def first_needs(self, eng: Engine):
         return eng.needs_of(self._encoders[0]._latentStageEncoder[0])

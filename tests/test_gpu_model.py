@@ -76,6 +76,22 @@ def test_unaligned_image_is_reflect_padded_like_the_reference():
     assert float((model.decode(codes).cpu() - O.decode(sd, [c.cpu() for c in codes])).abs().max()) <= PIXEL_TOL
 
 
+def test_compress_decompress_and_identical_bpp():
+    """compress()/decompress() on the CUDA path: the reference flow yields 424 + 96 + 24 bytes (0.0664 bpp) for the
+    qp=1 golden image under the uniform prior; identical codes + bit-identical rANS => identical bpp."""
+    from mcquic_b200 import entropy
+    g, cfg = load_golden("compressor_qp1_256")
+    sd, x = golden_inputs(cfg)
+    model = _model(cfg, sd)
+    codes, binaries, headers = model.compress(x.cuda())
+    assert [len(b) for b in binaries[0]] == [424, 96, 24]
+    assert entropy.bpp(binaries[0], headers[0].ImageSize) == pytest.approx(0.06640625)
+    out = model.decompress(binaries, headers)
+    assert torch.equal(out, model.decode(codes))                       # 256x256: no crop
+    s = cfg["stride"]
+    assert float((out.cpu()[..., ::s, ::s] - torch.from_numpy(g["xhat_sample"])).abs().max()) <= PIXEL_TOL
+
+
 def test_errors():
     cfg = dict(channel=64, m=2, k=[256, 128, 64])
     model = _model(cfg, synthetic_state_dict(64, 2, [256, 128, 64], seed=0))
