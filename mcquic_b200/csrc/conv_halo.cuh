@@ -138,6 +138,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias staging
+  // of constant weights) overlapped the tail of the previous kernel in the stream; from here on we read its outputs.
+  pdl_wait_prior_grids();
+  pdl_launch_dependents();
 
   const int kchunks = p.cin / TC_BK;
   const int total_work = hp.groups_m * p.tiles_c;        // one work item = CL neighbouring pixel tiles x one N tile
@@ -265,16 +269,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     const uint32_t stage = epi_base + (uint32_t)(warp - 2) * TC_EPI_STAGE_BYTES;
-    int it = 0;
-    for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
-      int ct, x0, y0, n0;
+    auto tile_pix = [&](int w, int& ct) {
+      int x0, y0, n0;
       decode_tile(w, ct, x0, y0, n0);
-      auto pix = [&](int row, int& n, int& oy, int& ox) {
+      return [=, &p](int row, int& n, int& oy, int& ox) {
         ox = x0 + (row & (HALO_TW - 1));
         oy = y0 + (row >> 3);
         n = n0;
         return (ox < p.wout) && (oy < p.hout) && (n < p.n);
       };
+    };
+    int it = 0;
+    for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
+      int ct;
+      auto pix = tile_pix(w, ct);
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
       mbar_wait(tfull_bar(buf), use & 1u, 16);

@@ -139,6 +139,9 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   return ((uint64_t)hi << 32) | lo;
 }
 
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- epilogue
 // Drain this warp's share (TMEM lanes 32q.., 32-column chunks cg, cg+4, ...) of one accumulator tile.
 // tcgen05.ld hands every thread one GEMM row (= pixel); storing from that layout would touch 32 cache lines per
@@ -302,6 +305,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias staging
+  // of constant weights) overlapped the tail of the previous kernel in the stream; from here on we read its outputs.
+  pdl_wait_prior_grids();
+  pdl_launch_dependents();
 
   const int tiles_m = p.tiles_n * p.tiles_y * p.tiles_x;
   const int total_tiles = tiles_m * p.tiles_c;
@@ -402,21 +409,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware rule: warp % 4)
     const int cg = (warp - 2) >> 2;     // column group: this warp handles 32-column chunks cg, cg+4, ...
     const uint32_t stage = epi_base + (uint32_t)(warp - 2) * TC_EPI_STAGE_BYTES;
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int ct = t / tiles_m;
+    // GEMM row inside a tile = pixel (x fastest, then y, then n)
+    auto tile_pix = [&](int t, int& ct) {
+      ct = t / tiles_m;
       int mt = t - ct * tiles_m;
       const int bx = mt % p.tiles_x;
       mt /= p.tiles_x;
       const int by = mt % p.tiles_y;
       const int bz = mt / p.tiles_y;
-      // GEMM row inside the tile = pixel (x fastest, then y, then n)
-      auto pix = [&](int row, int& n, int& oy, int& ox) {
+      return [=, &p](int row, int& n, int& oy, int& ox) {
         ox = bx * p.tw + row % p.tw;
         oy = by * p.th + (row / p.tw) % p.th;
         n = bz * p.tn + row / (p.tw * p.th);
         return (ox < p.wout) && (oy < p.hout) && (n < p.n);
       };
+    };
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int ct;
+      auto pix = tile_pix(t, ct);
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
       mbar_wait(tfull_bar(buf), use & 1u, 4);

@@ -248,6 +248,16 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   const int total_tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.tiles_c;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   cudaError_t e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = env_int("MCQ_PDL", 1) ? 1 : 0;
   EvScope ev(st);
   if (a.passes == 3) {
     static bool attr3 = false;
@@ -256,7 +266,7 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
       if (e != cudaSuccess) return (int)e;
       attr3 = true;
     }
-    conv_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
+    e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
   } else {
     static bool attr1 = false;
     if (!attr1) {
@@ -264,12 +274,11 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
       if (e != cudaSuccess) return (int)e;
       attr1 = true;
     }
-    conv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
+    e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
   }
   g_launches++;
-  return cuda_status();
+  return e == cudaSuccess ? cuda_status() : (int)e;
 }
-
 
 // ---- halo kernel (3x3, stride 1): tap reuse in smem + weight multicast across a cluster
 bool halo_supported(const ConvArgs& a) {
@@ -291,13 +300,15 @@ int launch_halo_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t sme
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = env_int("MCQ_PDL", 1) ? 2 : 1;
   EvScope ev(st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], a, hp);
   g_launches++;
