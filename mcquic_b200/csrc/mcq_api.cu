@@ -11,6 +11,7 @@
 
 #include "conv_simt.cuh"
 #include "conv_halo.cuh"
+#include "conv_pair.cuh"
 #include "conv_tc.cuh"
 #include "misc.cuh"
 #include "vq.cuh"
@@ -395,6 +396,107 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
   return launch_halo_t<1, 4>(a, hp, maps, smem, grid, st);
 }
 
+
+// ---- CTA-pair kernel (tcgen05.mma.cta_group::2): 3x3 stride-1 convs with a 128-column N tile
+template <int PASSES>
+int launch_pair_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t smem, int grid, cudaStream_t st) {
+  static bool attr = false;
+  auto kern = conv_pair_kernel<PASSES>;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = env_int("MCQ_PDL", 1) ? 2 : 1;
+  EvScope ev(st);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], a, hp);
+  g_launches++;
+  return e == cudaSuccess ? cuda_status() : (int)e;
+}
+
+int launch_pair(ConvArgs& a, cudaStream_t st) {
+  const int bn = 128;
+  if (a.cout_pad % bn != 0) return MCQ_ERR_UNSUPPORTED;
+  const int np = a.passes == 3 ? 2 : 1;
+  a.bn = bn;
+  a.tiles_c = a.cout_pad / bn;
+  a.tw = HALO_TW; a.th = HALO_TH; a.tn = 1;
+  a.tiles_x = (a.wout + HALO_TW - 1) / HALO_TW;
+  a.tiles_y = (a.hout + HALO_TH - 1) / HALO_TH;
+  a.tiles_n = a.n;
+  HaloArgs hp{};
+  hp.pitch = 10;
+  hp.box_w = 10;
+  hp.base_mode = 0;
+  hp.a_bytes = ((hp.pitch * HALO_ROWS * 128) + 1023) / 1024 * 1024;
+  hp.tiles_m = a.tiles_x * a.tiles_y * a.tiles_n;
+  if (hp.tiles_m < 2) return MCQ_ERR_UNSUPPORTED;
+  hp.groups_m = (hp.tiles_m + 1) / 2;
+  hp.tps = env_int("MCQ_HALO_TPS", a.passes == 3 ? 1 : 3);
+  if (hp.tps != 1 && hp.tps != 3) return MCQ_ERR_BAD_ARG;
+  const size_t a_buf = (size_t)hp.a_bytes * np;
+  const size_t b_plane = (size_t)bn * TC_BK * 2;
+  const size_t b_stage = (a.passes == 3 ? b_plane + b_plane / 2 : b_plane / 2) * hp.tps;
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + TC_BIAS_SMEM_FLOATS * 4;
+  const size_t budget = 227 * 1024 - 1024 - 256 - epi_bytes;
+  a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
+  hp.na = (a.passes == 3) ? 2 : 3;
+  int nbs = (int)((budget - a_buf * hp.na) / b_stage);
+  if (nbs > 8) nbs = 8;
+  if (nbs < 2) return MCQ_ERR_UNSUPPORTED;
+  hp.nbs = nbs;
+  const size_t smem = a_buf * hp.na + b_stage * nbs + 8 * (2 * hp.na + 2 * nbs + 4) + 16 + 1024 + epi_bytes;
+
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MCQ_ERR_DRIVER;
+  CUtensorMap maps[5];
+  auto enc_a = [&](CUtensorMap* m, const void* ptr) {
+    cuuint64_t dims[5] = {(cuuint64_t)a.cin, (cuuint64_t)a.win, 1, (cuuint64_t)a.hin, (cuuint64_t)a.n};
+    cuuint64_t strides[4] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.win * a.cin * 2, (cuuint64_t)a.win * a.cin * 2,
+                             (cuuint64_t)a.hin * a.win * a.cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)TC_BK, (cuuint32_t)hp.box_w, 1u, (cuuint32_t)HALO_ROWS, 1u};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : MCQ_ERR_DRIVER;
+  };
+  int rc = enc_a(&maps[0], a.a_hi);
+  if (rc) return rc;
+  rc = encode_weight_map(&maps[4], a.w_hi, a.cout_pad, a.ktotal, bn / 2);
+  if (rc) return rc;
+  if (a.passes == 3) {
+    rc = enc_a(&maps[1], a.a_lo);
+    if (rc) return rc;
+    rc = encode_weight_map(&maps[2], a.w_hi, a.cout_pad, a.ktotal, bn);
+    if (rc) return rc;
+    rc = encode_weight_map(&maps[3], a.w_lo, a.cout_pad, a.ktotal, bn);
+    if (rc) return rc;
+  } else {
+    maps[1] = maps[0];
+    maps[2] = maps[4];
+    maps[3] = maps[4];
+  }
+  const int work = hp.groups_m * a.tiles_c;
+  int clusters = num_sms() / 2;
+  if (work < clusters) clusters = work;
+  const int grid = clusters * 2;
+  if (a.passes == 3) return launch_pair_t<3>(a, hp, maps, smem, grid, st);
+  return launch_pair_t<1>(a, hp, maps, smem, grid, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -411,7 +513,9 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
   else if (!tc_supported(a)) rc = MCQ_ERR_UNSUPPORTED;
   else {
     rc = MCQ_ERR_UNSUPPORTED;
-    if (halo_supported(a) && env_int("MCQ_HALO", 1)) rc = launch_halo(a, st);
+    // CTA pairs (cta_group::2) pay off where the tensor pipe is the limiter (3-pass); the 1-pass path is epilogue-bound
+    if (halo_supported(a) && env_int("MCQ_PAIR", a.passes == 3 ? 1 : 0)) rc = launch_pair(a, st);
+    if (rc == MCQ_ERR_UNSUPPORTED && halo_supported(a) && env_int("MCQ_HALO", 1)) rc = launch_halo(a, st);
     if (rc == MCQ_ERR_UNSUPPORTED) rc = launch_tc(a, st);
   }
   g_ev_start = g_ev_stop = nullptr;
