@@ -159,7 +159,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      // (warp-uniform loop; one elected lane issues the TMA, see elect_one)
       // The halo of chunk g+na-1 is requested while the weights of chunk g stream: late enough that its buffer is
       // certainly free (the MMA has passed tap t* - nbs >= 0 of chunk g, so chunk g-1 is done -> the wait below
       // never blocks), early enough (>= one whole chunk of MMA time) to hide the TMA latency of the 23 KB box.
@@ -176,10 +177,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         decode_tile(wi, ct, x0, y0, n);
         mbar_wait(a_empty(ab), aph ^ 1u, 11);
         const uint32_t sa = a_base + a_buf_bytes * ab;
-        // the whole box is always transferred (out-of-image pixels are zero-filled): tx = box bytes
-        mbar_expect_tx(a_full(ab), (uint32_t)(hp.box_w * HALO_ROWS * 128) * NP);
-        tma_load_5d(&tmA_hi, sa, a_full(ab), kc * TC_BK, x0 - 1, 0, y0 - 1, n);
-        if (PASSES == 3) tma_load_5d(&tmA_lo, sa + hp.a_bytes, a_full(ab), kc * TC_BK, x0 - 1, 0, y0 - 1, n);
+        if (elect_one()) {
+          // the whole box is always transferred (out-of-image pixels are zero-filled): tx = box bytes
+          mbar_expect_tx(a_full(ab), (uint32_t)(hp.box_w * HALO_ROWS * 128) * NP);
+          tma_load_5d(&tmA_hi, sa, a_full(ab), kc * TC_BK, x0 - 1, 0, y0 - 1, n);
+          if (PASSES == 3) tma_load_5d(&tmA_lo, sa + hp.a_bytes, a_full(ab), kc * TC_BK, x0 - 1, 0, y0 - 1, n);
+        }
+        __syncwarp();
         if (++ab == na) { ab = 0; aph ^= 1u; }
         ++a_issue;
       };
@@ -191,18 +195,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int sg = 0; sg < spc; ++sg) {
             mbar_wait(b_empty(bs), bph ^ 1u, 12);
-            mbar_expect_tx(b_full(bs), b_stage_bytes);
-            for (int tt = 0; tt < hp.tps; ++tt) {
-              const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
-              const int kb = (sg * hp.tps + tt) * p.cin + kc * TC_BK;
-              if (CL > 1) {
-                tma_load_2d_mc(&tmB_hi, sb + crank * b_slice, b_full(bs), kb, row0, kMask);
-                if (PASSES == 3) tma_load_2d_mc(&tmB_lo, sb + b_plane + crank * b_slice, b_full(bs), kb, row0, kMask);
-              } else {
-                tma_load_2d(&tmB_hi, sb, b_full(bs), kb, row0);
-                if (PASSES == 3) tma_load_2d(&tmB_lo, sb + b_plane, b_full(bs), kb, row0);
+            if (elect_one()) {
+              mbar_expect_tx(b_full(bs), b_stage_bytes);
+              for (int tt = 0; tt < hp.tps; ++tt) {
+                const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
+                const int kb = (sg * hp.tps + tt) * p.cin + kc * TC_BK;
+                if (CL > 1) {
+                  tma_load_2d_mc(&tmB_hi, sb + crank * b_slice, b_full(bs), kb, row0, kMask);
+                  if (PASSES == 3) tma_load_2d_mc(&tmB_lo, sb + b_plane + crank * b_slice, b_full(bs), kb, row0, kMask);
+                } else {
+                  tma_load_2d(&tmB_hi, sb, b_full(bs), kb, row0);
+                  if (PASSES == 3) tma_load_2d(&tmB_lo, sb + b_plane, b_full(bs), kb, row0);
+                }
               }
             }
+            __syncwarp();
             if (++bs == nbs) { bs = 0; bph ^= 1u; }
             if (sg == t_star) issue_a();
           }
@@ -210,11 +217,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t sbo = (uint32_t)hp.pitch * 128u;
       const uint32_t idesc_wide = (1u << 4) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const bool wide = (PASSES == 3) && (2 * bn <= 256);
+      const int spc = 9 / hp.tps;
+      uint32_t tap_off16[9];   // halo offset of tap (r, s) in 16 B units: (r * pitch + s) pixels x 128 B
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_off16[t] = (uint32_t)((t / 3) * hp.pitch + (t % 3)) * 8u;
       int ab = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
@@ -224,45 +235,52 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         tc_fence_after();
         const uint32_t d_hh = tmem_base + (uint32_t)(buf * acc_cols);
         const uint32_t d_lo = d_hh + (uint32_t)bn;
+        uint32_t acc = 0;   // the first MMA of a tile overwrites the accumulator, all later ones add
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(a_full(ab), aph, 14);
-          const uint32_t sa = a_base + a_buf_bytes * ab;
-          for (int sg = 0; sg < 9 / hp.tps; ++sg) {
+          // descriptor arithmetic is hoisted out of the issue loop: a single thread feeds the tensor core, and every
+          // integer instruction between two tcgen05.mma costs issue latency (a 1-pass MMA lasts only 64 cycles)
+          const uint64_t a_hi0 = make_sdesc_halo(a_base + a_buf_bytes * ab, sbo, hp.base_mode);
+          const uint64_t a_lo0 = a_hi0 + (uint64_t)(hp.a_bytes >> 4);
+          for (int sg = 0; sg < spc; ++sg) {
             mbar_wait(b_full(bs), bph, 15);
             tc_fence_after();
+            const uint64_t b0 = make_sdesc(b_base + b_stage_bytes * bs);
+            if (elect_one()) {
+            uint32_t acc_i = acc;
+#pragma unroll 3
             for (int tt = 0; tt < hp.tps; ++tt) {
               const int tap = sg * hp.tps + tt;
-              const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
-              const uint32_t a_off = (uint32_t)((tap / 3) * hp.pitch + (tap % 3)) * 128u;
-              const uint64_t b_hi = make_sdesc(sb);
-              const bool first = (kc == 0 && tap == 0);
+              const uint64_t at = (uint64_t)tap_off16[tap];
+              const uint64_t bt = b0 + (uint64_t)(tt * (int)(b_tap_bytes >> 4));
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {
-                const uint32_t acc = (!first || k > 0) ? 1u : 0u;
-                const uint64_t a_hi = make_sdesc_halo(sa + a_off + k * 32, sbo, hp.base_mode);
-                const uint64_t ko = (uint64_t)(k * 2);
+                const uint64_t ko = (uint64_t)(k * 2);   // +32 B per K = 16, in 16 B units
                 if (PASSES == 3) {
-                  const uint64_t a_lo = make_sdesc_halo(sa + hp.a_bytes + a_off + k * 32, sbo, hp.base_mode);
                   if (wide) {   // one N = 2*bn MMA over the adjacent [B_hi; B_lo] stage: A_hi is fetched once
-                    umma_f16(d_hh, a_hi, b_hi + ko, idesc_wide, acc);
+                    umma_f16(d_hh, a_hi0 + at + ko, bt + ko, idesc_wide, acc_i);
                   } else {
-                    const uint64_t b_lo = make_sdesc(sb + b_plane);
-                    umma_f16(d_hh, a_hi, b_hi + ko, idesc, acc);
-                    umma_f16(d_lo, a_hi, b_lo + ko, idesc, acc);
+                    umma_f16(d_hh, a_hi0 + at + ko, bt + ko, idesc, acc_i);
+                    umma_f16(d_lo, a_hi0 + at + ko, bt + (uint64_t)(b_plane >> 4) + ko, idesc, acc_i);
                   }
-                  umma_f16(d_lo, a_lo, b_hi + ko, idesc, 1u);
+                  umma_f16(d_lo, a_lo0 + at + ko, bt + ko, idesc, 1u);
                 } else {
-                  umma_f16(d_hh, a_hi, b_hi + ko, idesc, acc);
+                  umma_f16(d_hh, a_hi0 + at + ko, bt + ko, idesc, acc_i);
                 }
+                acc_i = 1u;
               }
             }
             if (CL > 1) umma_commit_mc(b_empty(bs), kMask); else umma_commit(b_empty(bs));
+            if (sg == spc - 1) umma_commit(a_empty(ab));   // halo buffer free once the chunk's last tap has been read
+            }
+            __syncwarp();
+            acc = 1u;
             if (++bs == nbs) { bs = 0; bph ^= 1u; }
           }
-          umma_commit(a_empty(ab));
           if (++ab == na) { ab = 0; aph ^= 1u; }
         }
-        umma_commit(tfull_bar(buf));
+        if (elect_one()) umma_commit(tfull_bar(buf));
+        __syncwarp();
       }
     }
   } else {

@@ -164,8 +164,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const uint32_t a_tx = (uint32_t)(hp.box_w * HALO_ROWS * 128) * NP;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread per CTA; completion lands on the leader's barriers) ==========
-    if (lane == 0) {
+    // ===================== TMA producer (one elected lane per CTA; completion lands on the leader's barriers) =====
+    {
       const int my_work = (total_work - cluster_id + num_clusters - 1) / num_clusters;
       const int total_chunks = my_work * kchunks;
       const int t_star = nbs < spc - 1 ? nbs : spc - 1;
@@ -179,9 +179,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         mbar_wait(a_empty(ab), aph ^ 1u, 21);
         const uint32_t sa = a_base + a_buf_bytes * ab;
         const uint32_t lbar = map_to_cta(a_full(ab), 0);
-        if (leader) mbar_expect_tx(a_full(ab), 2u * a_tx);
-        tma2_load_5d(&tmA_hi, sa, lbar, kc * TC_BK, x0 - 1, 0, y0 - 1, n);
-        if (PASSES == 3) tma2_load_5d(&tmA_lo, sa + hp.a_bytes, lbar, kc * TC_BK, x0 - 1, 0, y0 - 1, n);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(a_full(ab), 2u * a_tx);
+          tma2_load_5d(&tmA_hi, sa, lbar, kc * TC_BK, x0 - 1, 0, y0 - 1, n);
+          if (PASSES == 3) tma2_load_5d(&tmA_lo, sa + hp.a_bytes, lbar, kc * TC_BK, x0 - 1, 0, y0 - 1, n);
+        }
+        __syncwarp();
         if (++ab == na) { ab = 0; aph ^= 1u; }
         ++a_issue;
       };
@@ -194,17 +197,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           for (int sg = 0; sg < spc; ++sg) {
             mbar_wait(b_empty(bs), bph ^ 1u, 22);
             const uint32_t lbar = map_to_cta(b_full(bs), 0);
-            if (leader) mbar_expect_tx(b_full(bs), 2u * b_stage_bytes);
-            for (int tt = 0; tt < hp.tps; ++tt) {
-              const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
-              const int kb = (sg * hp.tps + tt) * p.cin + kc * TC_BK;
-              if (PASSES == 3) {
-                tma2_load_2d(leader ? &tmB_hi_full : &tmB_lo_full, sb, lbar, kb, ct * bn);
-                tma2_load_2d(&tmB_hi_half, sb + b_plane, lbar, kb, row_half);
-              } else {
-                tma2_load_2d(&tmB_hi_half, sb, lbar, kb, row_half);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(b_full(bs), 2u * b_stage_bytes);
+              for (int tt = 0; tt < hp.tps; ++tt) {
+                const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
+                const int kb = (sg * hp.tps + tt) * p.cin + kc * TC_BK;
+                if (PASSES == 3) {
+                  tma2_load_2d(leader ? &tmB_hi_full : &tmB_lo_full, sb, lbar, kb, ct * bn);
+                  tma2_load_2d(&tmB_hi_half, sb + b_plane, lbar, kb, row_half);
+                } else {
+                  tma2_load_2d(&tmB_hi_half, sb, lbar, kb, row_half);
+                }
               }
             }
+            __syncwarp();
             if (++bs == nbs) { bs = 0; bph ^= 1u; }
             if (sg == t_star) issue_a();
           }
@@ -212,12 +218,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: one thread of the LEADER CTA, for the pair =====================
-    if (lane == 0 && leader) {
+    // ===================== MMA issuer: one elected lane of the LEADER CTA, for the pair =====================
+    if (leader) {
       // M = 256 (128 rows per CTA); N counts the rows both CTAs contribute together
       const uint32_t idesc_n = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t sbo = (uint32_t)hp.pitch * 128u;
+      uint32_t tap_off16[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_off16[t] = (uint32_t)((t / 3) * hp.pitch + (t % 3)) * 8u;
       int ab = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
@@ -227,38 +236,44 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         tc_fence_after();
         const uint32_t d_hh = tmem_base + (uint32_t)(buf * acc_cols);
         const uint32_t d_lo = d_hh + (uint32_t)bn;
+        uint32_t acc = 0;
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(a_full(ab), aph, 24);
-          const uint32_t sa = a_base + a_buf_bytes * ab;
+          const uint64_t a_hi0 = make_sdesc_halo(a_base + a_buf_bytes * ab, sbo, 0);
+          const uint64_t a_lo0 = a_hi0 + (uint64_t)(hp.a_bytes >> 4);
           for (int sg = 0; sg < spc; ++sg) {
             mbar_wait(b_full(bs), bph, 25);
             tc_fence_after();
+            const uint64_t b0 = make_sdesc(b_base + b_stage_bytes * bs);
+            if (elect_one()) {
+            uint32_t acc_i = acc;
+#pragma unroll 3
             for (int tt = 0; tt < hp.tps; ++tt) {
-              const int tap = sg * hp.tps + tt;
-              const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
-              const uint32_t a_off = (uint32_t)((tap / 3) * hp.pitch + (tap % 3)) * 128u;
-              const bool first = (kc == 0 && tap == 0);
+              const uint64_t at = (uint64_t)tap_off16[sg * hp.tps + tt];
+              const uint64_t bt = b0 + (uint64_t)(tt * (int)(b_tap_bytes >> 4));
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {
-                const uint32_t acc = (!first || k > 0) ? 1u : 0u;
                 const uint64_t ko = (uint64_t)(k * 2);
-                const uint64_t a_hi = make_sdesc_halo(sa + a_off + k * 32, sbo, 0);
                 if (PASSES == 3) {
-                  const uint64_t a_lo = make_sdesc_halo(sa + hp.a_bytes + a_off + k * 32, sbo, 0);
-                  umma2_f16(d_hh, a_hi, make_sdesc(sb) + ko, idesc_2n, acc);              // [hi*hi | hi*lo]
-                  umma2_f16(d_lo, a_lo, make_sdesc(sb + b_plane) + ko, idesc_n, 1u);      // += lo*hi
+                  umma2_f16(d_hh, a_hi0 + at + ko, bt + ko, idesc_2n, acc_i);                            // [hi*hi | hi*lo]
+                  umma2_f16(d_lo, a_lo0 + at + ko, bt + (uint64_t)(b_plane >> 4) + ko, idesc_n, 1u);     // += lo*hi
                 } else {
-                  umma2_f16(d_hh, a_hi, make_sdesc(sb) + ko, idesc_n, acc);
+                  umma2_f16(d_hh, a_hi0 + at + ko, bt + ko, idesc_n, acc_i);
                 }
+                acc_i = 1u;
               }
             }
             umma2_commit_mc(b_empty(bs), 3);
+            if (sg == spc - 1) umma2_commit_mc(a_empty(ab), 3);
+            }
+            __syncwarp();
+            acc = 1u;
             if (++bs == nbs) { bs = 0; bph ^= 1u; }
           }
-          umma2_commit_mc(a_empty(ab), 3);
           if (++ab == na) { ab = 0; aph ^= 1u; }
         }
-        umma2_commit_mc(tfull_bar(buf), 3);
+        if (elect_one()) umma2_commit_mc(tfull_bar(buf), 3);
+        __syncwarp();
       }
     }
   } else {

@@ -94,6 +94,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+// one lane of a converged warp; values computed warp-uniformly outside the guarded region stay in uniform registers,
+// which is what UTMALDG / UTCHMMA take (inside an `if (lane == 0)` region the compiler has to broadcast every operand
+// through R2UR in a loop: ~20 instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -317,8 +325,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int kiters = ntaps * kchunks;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -333,26 +341,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty_bar(s), ph ^ 1u, 1);
             const uint32_t sa = smem_base + stage_bytes * s;
-            mbar_expect_tx(full_bar(s), stage_bytes);
             const int ca = p.ch_off + p.tap_c[tap] + kc * TC_BK;
             const int kb = tap * p.cin + kc * TC_BK;
-            tma_load_5d(&tmA_hi, sa, full_bar(s), ca, x0 + p.tap_dx[tap], p.tap_py[tap], y0 + p.tap_dy[tap], n0);
-            if (PASSES == 3) {
-              tma_load_5d(&tmA_lo, sa + TC_A_BYTES, full_bar(s), ca, x0 + p.tap_dx[tap], p.tap_py[tap],
-                          y0 + p.tap_dy[tap], n0);
-              tma_load_2d(&tmB_hi, sa + 2 * TC_A_BYTES, full_bar(s), kb, c0);
-              tma_load_2d(&tmB_lo, sa + 2 * TC_A_BYTES + b_bytes, full_bar(s), kb, c0);
-            } else {
-              tma_load_2d(&tmB_hi, sa + TC_A_BYTES, full_bar(s), kb, c0);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(s), stage_bytes);
+              tma_load_5d(&tmA_hi, sa, full_bar(s), ca, x0 + p.tap_dx[tap], p.tap_py[tap], y0 + p.tap_dy[tap], n0);
+              if (PASSES == 3) {
+                tma_load_5d(&tmA_lo, sa + TC_A_BYTES, full_bar(s), ca, x0 + p.tap_dx[tap], p.tap_py[tap],
+                            y0 + p.tap_dy[tap], n0);
+                tma_load_2d(&tmB_hi, sa + 2 * TC_A_BYTES, full_bar(s), kb, c0);
+                tma_load_2d(&tmB_lo, sa + 2 * TC_A_BYTES + b_bytes, full_bar(s), kb, c0);
+              } else {
+                tma_load_2d(&tmB_hi, sa + TC_A_BYTES, full_bar(s), kb, c0);
+              }
             }
+            __syncwarp();
             if (++s == stages) { s = 0; ph ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       // instruction descriptor: D=f32, A=B=f16, both K-major, N = bn, M = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t idesc_wide = (1u << 4) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -372,36 +383,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_base + stage_bytes * s;
           const uint64_t a_hi = make_sdesc(sa);
-          if (PASSES == 3) {
-            const uint64_t a_lo = make_sdesc(sa + TC_A_BYTES);
-            const uint64_t b_hi = make_sdesc(sa + 2 * TC_A_BYTES);
-            const uint64_t b_lo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
+          const uint64_t a_lo = make_sdesc(sa + TC_A_BYTES);
+          const uint64_t b_hi = make_sdesc(sa + (PASSES == 3 ? 2 : 1) * TC_A_BYTES);
+          const uint64_t b_lo = make_sdesc(sa + 2 * TC_A_BYTES + b_bytes);
+          const uint32_t acc0 = ki > 0 ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint32_t acc = (ki > 0 || k > 0) ? 1u : 0u;
+              const uint32_t acc = k > 0 ? 1u : acc0;
               const uint64_t ko = (uint64_t)(k * 2);  // +32 B per K=16 step, in 16 B units
-              if (wide) {
-                // B_hi and B_lo are adjacent in smem and acc_hh / acc_lo adjacent in TMEM: one N = 2*bn MMA computes
-                // [A_hi*B_hi | A_hi*B_lo] and reads A_hi once (operand fetch from smem is the scarce resource)
-                umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc_wide, acc);
+              if (PASSES == 3) {
+                if (wide) {
+                  // B_hi and B_lo are adjacent in smem and acc_hh / acc_lo adjacent in TMEM: one N = 2*bn MMA computes
+                  // [A_hi*B_hi | A_hi*B_lo] and reads A_hi once (operand fetch from smem is the scarce resource)
+                  umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc_wide, acc);
+                } else {
+                  umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc, acc);
+                  umma_f16(d_lo, a_hi + ko, b_lo + ko, idesc, acc);
+                }
+                umma_f16(d_lo, a_lo + ko, b_hi + ko, idesc, 1u);
               } else {
                 umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc, acc);
-                umma_f16(d_lo, a_hi + ko, b_lo + ko, idesc, acc);
               }
-              umma_f16(d_lo, a_lo + ko, b_hi + ko, idesc, 1u);
             }
-          } else {
-            const uint64_t b_hi = make_sdesc(sa + TC_A_BYTES);
-#pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);
-              umma_f16(d_hh, a_hi + ko, b_hi + ko, idesc, (ki > 0 || k > 0) ? 1u : 0u);
-            }
+            umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above have read it
           }
-          umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above have read it
+          __syncwarp();
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {
