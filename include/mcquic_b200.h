@@ -83,6 +83,20 @@ typedef struct mcq_conv_params {
  * mcquic/nn/convs.py:77-100,221-276 and mcquic/nn/gdn.py:67-91. */
 int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream);
 
+/* `count` convolutions executed in order by ONE persistent launch (the low-resolution tail: 137 of the 165 convs per
+ * direction of mcquic/modules/compressor.py:122-176 run on <= 16x16 maps and are launch-latency-bound one by one).
+ * Semantics = calling mcq_conv2d(&params[i]) for i = 0..count-1 on `stream`, results bit-identical, provided that
+ * (1) all layers share n and passes and use MCQ_IMPL_TCGEN05, (2) distinct buffers do not overlap, (3) every layer
+ * is image-local (true of every conv: output image i depends on input image i only).  Dependencies between layers
+ * are derived from the pointers; independent neighbours (the two AttentionBlock branches, blocks.py:246-288) run
+ * without a barrier between them.  Returns MCQ_ERR_UNSUPPORTED (nothing launched) if the chain cannot be taken as
+ * a whole -- the caller then issues the layers one by one.  count <= mcq_conv_chain_max_layers(). */
+int mcq_conv_chain(const mcq_conv_params* params, int32_t count, mcq_stream_t stream);
+int32_t mcq_conv_chain_max_layers(void);
+/* development aid: when set (device int64[3072]), CTA 0 of every chain launch records clock64() samples of its TMA
+ * issues [0,1024), MMA stage arrivals [1024,2048) and epilogue tile begin/end pairs [2048,3072).  NULL = off. */
+void mcq_debug_timeline(void* device_i64_3072);
+
 /* First layer: conv3x3 stride 2, 3 -> cout, on the fp32 NCHW image, with AlignedPadding's reflect pad folded
  * into the gather (mcquic/data/transforms.py:86-99, mcquic/modules/compressor.py:124).
  * x: [n, 3, h, w] fp32; pad_top/pad_left: reflect padding already split as the reference does; hp, wp: padded size.

@@ -33,11 +33,15 @@ EPI_LINEAR, EPI_GATE, EPI_GDN, EPI_IGDN = 0, 1, 2, 3
 ACT_NONE, ACT_SILU, ACT_SQUARE = 0, 1, 2
 STORE_NHWC, STORE_SHUFFLE_NHWC, STORE_SHUFFLE_NCHW = 0, 1, 2
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
+ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_DRIVER, ERR_CODE_RANGE, ERR_WATCHDOG = -1, -2, -3, -4, -5
 
 # every symbol include/mcquic_b200.h declares: name -> (restype, argtypes)
 _i32, _i64, _p, _f = _c.c_int32, _c.c_int64, _c.c_void_p, _c.c_float
 SYMBOLS = {
     "mcq_conv2d": (_c.c_int, [_c.POINTER(ConvParams), _p]),
+    "mcq_conv_chain": (_c.c_int, [_c.POINTER(ConvParams), _i32, _p]),
+    "mcq_conv_chain_max_layers": (_i32, []),
+    "mcq_debug_timeline": (None, [_p]),
     "mcq_stem_conv": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _i32, _p]),
     "mcq_vq_assign": (_c.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mcq_vq_assign_tc": (_c.c_int, [_p, _p, _p, _f, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmcquic_b200.so")
 SOURCES = ["mcq_api.cu"]
-HEADERS = ["common.cuh", "conv_simt.cuh", "conv_tc.cuh", "vq.cuh", "misc.cuh", "../../include/mcquic_b200.h"]
+HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith(".cuh")) + ["../../include/mcquic_b200.h"]
 
 
 def _nvcc():
@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + SOURCES
+           "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + SOURCES + os.environ.get("MCQ_NVCC_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)

@@ -44,17 +44,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~the hint elapses)
-// instead of burning issue slots that the epilogue warps of the same SM sub-partition need
+// try_wait: the thread is suspended in hardware until the phase completes or a time limit elapses.
+// MCQ_WAIT_HINT_NS > 0 passes an explicit suspend-time hint (ptxas turns it into NANOSLEEP.SYNCS <ns>);
+// 0 = the plain form with the system-dependent limit.
+#ifndef MCQ_WAIT_HINT_NS
+#define MCQ_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if defined(MCQ_WAIT_SPIN)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#elif MCQ_WAIT_HINT_NS > 0
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(20000u)
+      : "r"(bar), "r"(parity), "r"((uint32_t)MCQ_WAIT_HINT_NS)
       : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ unsigned long long global_ns() {

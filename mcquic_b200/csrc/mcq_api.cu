@@ -13,6 +13,7 @@
 #include "conv_halo.cuh"
 #include "conv_pair.cuh"
 #include "conv_tc.cuh"
+#include "conv_chain.cuh"
 #include "misc.cuh"
 #include "vq.cuh"
 
@@ -21,6 +22,7 @@ using namespace mcq;
 namespace {
 
 std::atomic<int> g_launches{0};
+long long* g_chain_dbg = nullptr;   // mcq_debug_timeline(): device buffer for the chain kernel's clock samples
 // optional per-launch timing events of the current mcq_conv2d call (thread-local: the library is re-entrant per thread)
 thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 struct EvScope {
@@ -185,15 +187,8 @@ bool tc_supported(const ConvArgs& a) {
   return true;
 }
 
-int launch_tc(ConvArgs& a, cudaStream_t st) {
-  // ---- N tile: the whole (padded) cout when it fits one MMA, else 128-column tiles
-  int bn = (a.cout_pad <= 256 && a.cout_pad % 128 != 0) ? a.cout_pad : 128;
-  if (a.cout_pad < 128) bn = a.cout_pad;
-  if (a.cout_pad % bn != 0) return MCQ_ERR_UNSUPPORTED;
-  if (bn % 16 != 0 || bn > 256) return MCQ_ERR_UNSUPPORTED;
-  if (bn > 32 && bn % 32 != 0) return MCQ_ERR_UNSUPPORTED;
-  if ((a.passes == 3 ? 2 : 1) * bn > (int)TC_TMEM_COLS) return MCQ_ERR_UNSUPPORTED;
-  // ---- M tile: (tw x th x tn) box of output pixels, 128 rows
+// M tile of the per-tap kernels: a (tw x th x tn) box of output pixels, 128 GEMM rows
+void fill_mtile(ConvArgs& a) {
   a.tw = pow2_ceil(a.wout) < 16 ? pow2_ceil(a.wout) : 16;
   const int th_max = TC_BM / a.tw;
   a.th = pow2_ceil(a.hout) < th_max ? pow2_ceil(a.hout) : th_max;
@@ -201,13 +196,10 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   a.tiles_x = (a.wout + a.tw - 1) / a.tw;
   a.tiles_y = (a.hout + a.th - 1) / a.th;
   a.tiles_n = (a.n + a.tn - 1) / a.tn;
-  // small feature maps: narrow the N tile so that the few pixel tiles still spread over the SMs
-  // (these layers are latency-bound; re-reading A per N tile is free compared with idle SMs)
-  const int tiles_m = a.tiles_x * a.tiles_y * a.tiles_n;
-  while (tiles_m * (a.cout_pad / bn) < (num_sms() * 2) / 3 && bn >= 32 && (bn / 2) % 16 == 0) bn /= 2;
-  a.bn = bn;
-  a.tiles_c = a.cout_pad / bn;
-  // ---- taps
+}
+
+// per-tap TMA coordinate offsets in the 5-D activation view
+void fill_taps(ConvArgs& a) {
   const int pad = a.ksize / 2;
   for (int t = 0; t < a.ksize * a.ksize; ++t) {
     const int r = t / a.ksize - pad, s = t % a.ksize - pad;  // offsets in [-1, 1]
@@ -221,6 +213,24 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
       a.tap_dx[t] = (s < 0) ? -1 : 0;
     }
   }
+}
+
+int launch_tc(ConvArgs& a, cudaStream_t st) {
+  // ---- N tile: the whole (padded) cout when it fits one MMA, else 128-column tiles
+  int bn = (a.cout_pad <= 256 && a.cout_pad % 128 != 0) ? a.cout_pad : 128;
+  if (a.cout_pad < 128) bn = a.cout_pad;
+  if (a.cout_pad % bn != 0) return MCQ_ERR_UNSUPPORTED;
+  if (bn % 16 != 0 || bn > 256) return MCQ_ERR_UNSUPPORTED;
+  if (bn > 32 && bn % 32 != 0) return MCQ_ERR_UNSUPPORTED;
+  if ((a.passes == 3 ? 2 : 1) * bn > (int)TC_TMEM_COLS) return MCQ_ERR_UNSUPPORTED;
+  fill_mtile(a);
+  // small feature maps: narrow the N tile so that the few pixel tiles still spread over the SMs
+  // (these layers are latency-bound; re-reading A per N tile is free compared with idle SMs)
+  const int tiles_m = a.tiles_x * a.tiles_y * a.tiles_n;
+  while (tiles_m * (a.cout_pad / bn) < (num_sms() * 2) / 3 && bn >= 32 && (bn / 2) % 16 == 0) bn /= 2;
+  a.bn = bn;
+  a.tiles_c = a.cout_pad / bn;
+  fill_taps(a);
   // ---- pipeline depth
   const size_t stage_bytes = (size_t)(TC_A_BYTES + bn * TC_BK * 2) * (a.passes == 3 ? 2 : 1);
   const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + TC_BIAS_SMEM_FLOATS * 4;
@@ -497,6 +507,111 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
   return launch_pair_t<1>(a, hp, maps, smem, grid, st);
 }
 
+// ---- layer chain (conv_chain.cuh): `count` dependent convolutions on small maps in one persistent launch
+template <int PASSES>
+int launch_chain_t(const ChainParams& cp, size_t smem, int grid, cudaStream_t st) {
+  static bool attr = false;
+  auto kern = conv_chain_kernel<PASSES>;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CHAIN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CHAIN_CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = env_int("MCQ_PDL", 1) ? 2 : 1;
+  EvScope ev(st);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, cp);
+  g_launches++;
+  return e == cudaSuccess ? cuda_status() : (int)e;
+}
+
+int launch_chain(const mcq_conv_params* params, int count, cudaStream_t st) {
+  if (count < 1 || count > CHAIN_MAX_LAYERS) return MCQ_ERR_UNSUPPORTED;
+  static thread_local ChainParams cp;   // 27 KB: keep it off the stack
+  std::memset(&cp, 0, sizeof(cp));
+  const int passes = params[0].passes;
+  const int n = params[0].n;
+  const int bn_max = passes == 3 ? 64 : 128;
+  int ipc = env_int("MCQ_CHAIN_IPC", 0);
+  if (ipc <= 0) ipc = (n + 15) / 16;    // <= 16 clusters = 128 CTAs
+  const int nclusters = (n + ipc - 1) / ipc;
+  int bias_total = 0;
+  // buffers written since the last barrier (outputs of the layers after it)
+  const void* dirty[CHAIN_MAX_LAYERS * 5];
+  int ndirty = 0;
+  for (int l = 0; l < count; ++l) {
+    const mcq_conv_params* p = &params[l];
+    if (p->impl != MCQ_IMPL_TCGEN05 || p->passes != passes || p->n != n) return MCQ_ERR_UNSUPPORTED;
+    ChainLayer& L = cp.layers[l];
+    ConvArgs& a = L.p;
+    int rc = fill_args(p, a);
+    if (rc) return rc;
+    if (!tc_supported(a)) return MCQ_ERR_UNSUPPORTED;
+    fill_mtile(a);
+    fill_taps(a);
+    int bn = a.cout_pad < bn_max ? a.cout_pad : bn_max;
+    if (a.cout_pad % bn != 0 || bn % 16 != 0 || (bn > 32 && bn % 32 != 0)) return MCQ_ERR_UNSUPPORTED;
+    const int tiles_m = ((ipc + a.tn - 1) / a.tn) * a.tiles_y * a.tiles_x;
+    while (tiles_m * (a.cout_pad / bn) < CHAIN_CL && bn >= 32 && (bn / 2) % 16 == 0) bn /= 2;
+    a.bn = bn;
+    a.tiles_c = a.cout_pad / bn;
+    a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
+    // dependency on anything written since the last barrier?
+    const void* ins[5] = {p->a_hi, p->a_lo, p->res1, p->res2, p->aux};
+    int dep = 0;
+    for (int i = 0; i < 5 && !dep; ++i)
+      for (int j = 0; j < ndirty; ++j)
+        if (ins[i] && ins[i] == dirty[j]) { dep = 1; break; }
+    L.sync_before = (l > 0 && dep) ? 1 : 0;
+    if (L.sync_before) ndirty = 0;
+    const void* outs[5] = {p->out_f32, p->out0_hi, p->out0_lo, p->out1_hi, p->out1_lo};
+    for (int i = 0; i < 5; ++i)
+      if (outs[i]) dirty[ndirty++] = outs[i];
+    L.bias_off = bias_total;
+    bias_total += (a.cout + 3) / 4 * 4;
+    rc = encode_act_map(&L.tmA_hi, a.a_hi, a.n, a.hin, a.win, a.cin_total, a.stride, a.tw, a.th, a.tn);
+    if (rc) return rc;
+    rc = encode_weight_map(&L.tmB_hi, a.w_hi, a.cout_pad, a.ktotal, bn);
+    if (rc) return rc;
+    if (passes == 3) {
+      rc = encode_act_map(&L.tmA_lo, a.a_lo, a.n, a.hin, a.win, a.cin_total, a.stride, a.tw, a.th, a.tn);
+      if (rc) return rc;
+      rc = encode_weight_map(&L.tmB_lo, a.w_lo, a.cout_pad, a.ktotal, bn);
+      if (rc) return rc;
+    } else {
+      L.tmA_lo = L.tmA_hi;
+      L.tmB_lo = L.tmB_hi;
+    }
+  }
+  if (bias_total > CHAIN_BIAS_FLOATS) return MCQ_ERR_UNSUPPORTED;
+  const size_t stage_bytes = (size_t)(TC_A_BYTES + bn_max * TC_BK * 2) * (passes == 3 ? 2 : 1);
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + (size_t)bias_total * 4;
+  int stages = (int)((227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return MCQ_ERR_UNSUPPORTED;
+  cp.count = count;
+  cp.ipc = ipc;
+  cp.stages = stages;
+  cp.bias_total = bias_total;
+  cp.debug = (env_int("MCQ_CHAIN_NOSYNC", 0) ? 1 : 0) | (env_int("MCQ_CHAIN_SYNC_MODE", 0) << 1);
+  cp.dbg = g_chain_dbg;
+  const size_t smem = stage_bytes * stages + 8 * (2 * stages + 4) + 16 + 1024 + epi_bytes;
+  const int grid = nclusters * CHAIN_CL;
+  return passes == 3 ? launch_chain_t<3>(cp, smem, grid, st) : launch_chain_t<1>(cp, smem, grid, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -521,6 +636,20 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
   g_ev_start = g_ev_stop = nullptr;
   return rc;
 }
+
+int mcq_conv_chain(const mcq_conv_params* params, int32_t count, mcq_stream_t stream) {
+  MCQ_CHECK_ARG(params && count >= 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  g_ev_start = (cudaEvent_t)params[0].ev_start;
+  g_ev_stop = (cudaEvent_t)params[count - 1].ev_stop;
+  int rc = env_int("MCQ_CHAIN", 1) ? launch_chain(params, count, st) : MCQ_ERR_UNSUPPORTED;
+  g_ev_start = g_ev_stop = nullptr;
+  return rc;
+}
+
+int32_t mcq_conv_chain_max_layers(void) { return CHAIN_MAX_LAYERS; }
+
+void mcq_debug_timeline(void* device_i64_3072) { g_chain_dbg = (long long*)device_i64_3072; }
 
 int mcq_stem_conv(const float* x, int32_t n, int32_t h, int32_t w, int32_t pad_top, int32_t pad_left, int32_t hp,
                   int32_t wp, const float* wgt, const float* bias, int32_t cout, float* out_f32, void* out_hi,

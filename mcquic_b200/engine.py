@@ -105,6 +105,13 @@ class Engine:
         self._depth = 0
         # when a list, every conv launch is bracketed by CUDA events and logged (bench.py's roofline leg)
         self.profile: Optional[list] = None
+        # chain=True: convolutions on <= 16x16 maps are not launched one by one but collected and issued as one
+        # persistent layer-chain launch (mcq_conv_chain).  Measured on B200 a chained layer costs
+        # as much as a stand-alone launch that overlaps a second stream, so the default stays layer-by-layer launches
+        # on two streams; the emulated ABI keeps chains on so that the CPU tests cover the recording/merge logic.
+        self.chain = self.emulated
+        self._pending: list = []
+        self._rec_depth = 0
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -112,12 +119,35 @@ class Engine:
             return ctypes.c_void_p(0)
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def parallel(self, fa, fb):
-        """Run the independent closures fa and fb concurrently (fb on a side stream); returns (fa(), fb())."""
+    def can_chain(self, x: "Act") -> bool:
+        """True if every conv of a block fed with x goes into the pending layer chain."""
+        return (self.chain and self.impl == _lib.IMPL_TCGEN05 and x.h * x.w <= self.CHAIN_MAX_PIXELS
+                and x.c % 64 == 0)
+
+    def parallel(self, fa, fb, chain: bool = False):
+        """Run the independent closures fa and fb concurrently; returns (fa(), fb()).
+        chain=True (caller guarantees both consist of chainable convs only): their layers are interleaved in the
+        pending chain, so the kernel runs them without a barrier in between.  Otherwise fb goes to a side stream."""
+        if chain:
+            outer = self._pending
+            self._rec_depth += 1
+            try:
+                self._pending = la = []
+                ra = fa()
+                self._pending = lb = []
+                rb = fb()
+            finally:
+                self._pending = outer
+                self._rec_depth -= 1
+            for i in range(max(len(la), len(lb))):
+                outer.extend(la[i:i + 1])
+                outer.extend(lb[i:i + 1])
+            return ra, rb
         if not self.multistream:
             return fa(), fb()
         # one side stream per (nesting depth, parent stream): a side stream shared by two parents would let the
         # caching allocator hand a block to the second parent's branch while the first parent still reads it
+        self.flush()
         main = torch.cuda.current_stream()
         key = (self._depth, main.cuda_stream)
         side = self._side_streams.get(key)
@@ -128,11 +158,60 @@ class Engine:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 rb = fb()
+                self.flush()
             ra = fa()
+            self.flush()
             main.wait_stream(side)
         finally:
             self._depth -= 1
         return ra, rb
+
+    # ------------------------------------------------------------------ pending layer chain
+    CHAIN_MAX_PIXELS = 256   # conv output grids up to 16x16 go into chains
+
+    def _launch_one(self, item):
+        p, _keep, info = item
+        if self.profile is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            ev1.record()   # forces creation of the underlying cudaEvent_t handles
+            p.ev_start, p.ev_stop = ev0.cuda_event, ev1.cuda_event
+        _lib.check(self.lib.mcq_conv2d(ctypes.byref(p), self._stream()), "mcq_conv2d")
+        if self.profile is not None:
+            self.profile.append(dict(info, ev=(ev0, ev1)))
+
+    def _launch_group(self, items):
+        if len(items) == 1:
+            return self._launch_one(items[0])
+        arr = (_lib.ConvParams * len(items))(*[it[0] for it in items])
+        if self.profile is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            ev1.record()
+            arr[0].ev_start, arr[len(items) - 1].ev_stop = ev0.cuda_event, ev1.cuda_event
+        rc = self.lib.mcq_conv_chain(arr, len(items), self._stream())
+        if rc == _lib.ERR_UNSUPPORTED:      # nothing was launched: split (too many layers / bias pool) or go one by one
+            half = len(items) // 2
+            self._launch_group(items[:half])
+            self._launch_group(items[half:])
+            return
+        _lib.check(rc, "mcq_conv_chain")
+        if self.profile is not None:
+            self.profile.append({"flops": sum(it[2]["flops"] for it in items), "passes": items[0][2]["passes"],
+                                 "impl": _lib.IMPL_TCGEN05, "ev": (ev0, ev1),
+                                 "shape": ("chain", len(items)) + tuple(items[0][2]["shape"][1:3]),
+                                 "layers": [it[2]["shape"] for it in items]})
+
+    def flush(self):
+        """Issue the pending layer chain on the current stream."""
+        if self._rec_depth:
+            raise RuntimeError("mcquic_b200: non-chainable op inside a chain-recorded parallel region")
+        items, self._pending = self._pending, []
+        if not items:
+            return
+        maxl = int(self.lib.mcq_conv_chain_max_layers())
+        for i in range(0, len(items), maxl):
+            self._launch_group(items[i:i + maxl])
 
     def _planes(self, n, h, w, c, device) -> Planes:
         hi = torch.empty((n, h, w, c), dtype=torch.float16, device=device)
@@ -206,18 +285,16 @@ class Engine:
                 p.out1_hi, p.out1_lo, p.out1_act = _ptr(slots[1][0][0]), _ptr(slots[1][0][1]), slots[1][1]
         p.passes = self.passes if a[1] is not None else 1
         p.impl = self.impl if (pc.cin % 64 == 0) else _lib.IMPL_SIMT
-        if self.profile is not None:
-            # the library records these immediately around the kernel launch (after tensor-map encoding)
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            ev1.record()   # forces creation of the underlying cudaEvent_t handles
-            p.ev_start, p.ev_stop = ev0.cuda_event, ev1.cuda_event
-        _lib.check(self.lib.mcq_conv2d(ctypes.byref(p), self._stream()), "mcq_conv2d")
-        if self.profile is not None:
-            self.profile.append({"flops": 2.0 * x.n * (x.h // pc.stride) * (x.w // pc.stride) * pc.cout * pc.cin * pc.ksize ** 2,
-                                 "passes": p.passes, "impl": p.impl, "ev": (ev0, ev1),
-                                 "shape": (x.n, x.h, x.w, pc.cin, pc.cout, pc.ksize, pc.stride)})
-        del keep
+        info = {"flops": 2.0 * x.n * (x.h // pc.stride) * (x.w // pc.stride) * pc.cout * pc.cin * pc.ksize ** 2,
+                "passes": p.passes, "impl": p.impl, "shape": (x.n, x.h, x.w, pc.cin, pc.cout, pc.ksize, pc.stride)}
+        # everything the launch touches stays referenced until it has been issued (a freed block could otherwise be
+        # handed to a later layer of the same chain, whose clusters do not run in lock step)
+        item = (p, (keep, out, pc), info)
+        if (self.chain and p.impl == _lib.IMPL_TCGEN05 and (x.h // pc.stride) * (x.w // pc.stride) <= self.CHAIN_MAX_PIXELS):
+            self._pending.append(item)
+        else:
+            self.flush()
+            self._launch_one(item)
         return out
 
     # ------------------------------------------------------------------ blocks
@@ -262,7 +339,7 @@ class Engine:
                 b = self.residual_block(mod._sideBranch[i], b, {"f32", "silu"} if i < 2 else {"raw"})
             return b
 
-        a, b = self.parallel(main_branch, side_branch)
+        a, b = self.parallel(main_branch, side_branch, chain=self.can_chain(x))
         return self.conv(self._packed_for(mod._sideBranch[3]), b.raw, b, want, mode=_lib.EPI_GATE, res1=x.f32,
                          aux=a.f32)
 
@@ -298,6 +375,7 @@ class Engine:
     # ------------------------------------------------------------------ boundary ops
     def stem(self, conv: nn.Conv2d, x: torch.Tensor, pad: Tuple[int, int, int, int], want: Set[str]) -> Act:
         """conv3x3 s2 on the fp32 NCHW image; pad = (top, left, padded_h, padded_w) (AlignedPadding folded in)."""
+        self.flush()
         n, c, h, w = x.shape
         if c != 3 or conv.in_channels != 3 or conv.stride[0] != 2:
             raise RuntimeError("mcquic_b200: the stem expects [n, 3, h, w] input and conv3x3(3, C, stride=2)")
@@ -322,6 +400,7 @@ class Engine:
         return out
 
     def from_nchw(self, x: torch.Tensor, want: Set[str]) -> Act:
+        self.flush()
         n, c, h, w = x.shape
         out = Act(n, h, w, c)
         xc = x.contiguous().float()
@@ -341,6 +420,7 @@ class Engine:
         return out
 
     def to_nchw(self, x: Act) -> torch.Tensor:
+        self.flush()
         out = torch.empty((x.n, x.c, x.h, x.w), dtype=torch.float32, device=x.f32.device)
         _lib.check(self.lib.mcq_nhwc_to_nchw(_ptr(x.f32), x.n, x.c, x.h, x.w, _ptr(out), self._stream()),
                    "mcq_nhwc_to_nchw")
@@ -359,6 +439,7 @@ class Engine:
                   logits: bool = False, logit_scale: Optional[torch.Tensor] = None,
                   hist: Optional[torch.Tensor] = None, packed=None):
         """packed = (cb_hi, cb_lo, scale) split-fp16 codebook: enables the tensor-core path (d % 64 == 0)."""
+        self.flush()
         m, k, d = codebook.shape
         dev = x_nhwc.device
         codes = torch.empty((n, m, h, w), dtype=torch.int64, device=dev)
@@ -381,6 +462,7 @@ class Engine:
 
     def vq_dequant(self, codes: torch.Tensor, codebook: torch.Tensor, want: Set[str],
                    status: Optional[torch.Tensor] = None) -> Act:
+        self.flush()
         n, m, h, w = codes.shape
         _, k, d = codebook.shape
         out = Act(n, h, w, m * d)
@@ -402,6 +484,7 @@ class Engine:
 
     def code_histogram(self, codes: List[torch.Tensor], ks: Sequence[int], out: Optional[torch.Tensor] = None):
         """One flat int32 buffer [sum_l m*k_l] (level-major) -- the only thing that ever crosses NVLink."""
+        self.flush()
         m = codes[0].shape[1]
         total = sum(m * k for k in ks)
         if out is None:

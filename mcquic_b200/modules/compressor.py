@@ -92,13 +92,17 @@ class BaseCompressor(nn.Module):
         n, _, h, w = x.shape
         y0 = eng.stem(self._encoder[0], x, aligned_pad_amounts(h, w), eng.needs_of(self._encoder[1]))
         y = eng.run_seq(list(self._encoder)[1:], y0, self._quantizer.first_needs(eng))
-        return self._quantizer.encode_act(eng, y, hist)
+        codes = self._quantizer.encode_act(eng, y, hist)
+        eng.flush()
+        return codes
 
     def _decode_eager(self, codes: List[torch.Tensor], status: torch.Tensor) -> torch.Tensor:
         eng = self.engine
         eng.passes = self.decode_passes
         yHat = self._quantizer.decode_act(eng, codes, eng.needs_of(self._decoder[0]), status)
-        return eng.run_seq(list(self._decoder), yHat, set()).f32
+        out = eng.run_seq(list(self._decoder), yHat, set()).f32
+        eng.flush()
+        return out
 
     def _graph(self, key, make_static, body):
         """Capture `body(*static)` once per key; returns (graph, static inputs, static outputs, #launches)."""

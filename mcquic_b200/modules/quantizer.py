@@ -227,7 +227,14 @@ class _quantizerEncoder(nn.Module):
             return code, self._dequantizer.decode_act(code, {"f32"}, eng)
 
         # all of latentHead but its last conv is independent of the code (quantizer.py:313-316)
-        (code, deq), zl = eng.parallel(quantize, lambda: eng.run_seq(latent[:-1], z, eng.needs_of(latent[-1])))
+        if eng.can_chain(z):
+            # small maps: the layers of both heads are interleaved in one layer-chain launch, the VQ follows
+            head, zl = eng.parallel(lambda: eng.run_seq(self._quantizationHead, z, {"f32"}),
+                                    lambda: eng.run_seq(latent[:-1], z, eng.needs_of(latent[-1])), chain=True)
+            code = self._quantizer.encode_nhwc(head.f32, head.n, head.h, head.w, hist, eng)
+            deq = self._dequantizer.decode_act(code, {"f32"}, eng)
+        else:
+            (code, deq), zl = eng.parallel(quantize, lambda: eng.run_seq(latent[:-1], z, eng.needs_of(latent[-1])))
         return eng.run(latent[-1], zl, next_needs, tail=(deq.f32, -1.0)), code
 
 
@@ -247,7 +254,8 @@ class _quantizerDecoder(nn.Module):
         if self._sideHead is not None:
             head = list(self._dequantizationHead)
             qh, side = eng.parallel(lambda: eng.run_seq(head[:-1], q0, eng.needs_of(head[-1])),
-                                    lambda: eng.run_seq(self._sideHead, former, {"f32"}))
+                                    lambda: eng.run_seq(self._sideHead, former, {"f32"}),
+                                    chain=eng.can_chain(q0) and eng.can_chain(former))
             q = eng.run(head[-1], qh, head_needs, tail=(side.f32, 1.0))
         else:
             q = eng.run_seq(self._dequantizationHead, q0, head_needs)
@@ -326,7 +334,9 @@ class UMGMQuantizer(nn.Module):
     @torch.no_grad()
     def encode(self, x: torch.Tensor) -> List[torch.Tensor]:
         eng = default_engine()
-        return self.encode_act(eng, eng.from_nchw(x, self.first_needs(eng)))
+        codes = self.encode_act(eng, eng.from_nchw(x, self.first_needs(eng)))
+        eng.flush()
+        return codes
 
     @torch.no_grad()
     def decode(self, codes: List[torch.Tensor]) -> torch.Tensor:

