@@ -126,6 +126,19 @@ int mcq_vq_assign_tc(const float* x, const void* cb_hi, const void* cb_lo, float
                      void* workspace, int64_t workspace_bytes, mcq_stream_t stream);
 int64_t mcq_vq_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t m, int32_t k, int32_t d);
 
+/* Single-launch fused VQ for the multi-codebook shapes (d = 32 or 64, k % 128 == 0, h*w a multiple or a divisor of
+ * 32; BASELINE configs[2]: M=6, K=2048, d=32): replaces _distance + encode AND the soft-logit half of forward
+ * (mcquic/modules/quantizer.py:144-183,204) in one pass.  The fp32 latents are read once, split to fp16 hi/lo on
+ * the fly and multiplied on tcgen05 (3 passes, fp32-grade) against the TMA-streamed codebook; the epilogue forms
+ * (|x|^2 + |c_k|^2) - 2 x.c_k in the reference's order, keeps the first-index argmin, and (logits != NULL) writes
+ * the soft logits with TMA stores -- the only HBM-sized stream.  cb_lohi: fp16 [m*k, 2d], row = [lo(d) | hi(d)] of
+ * c * 2^e (cb_scale = 2^-e).  Other arguments as mcq_vq_assign.  MCQ_ERR_UNSUPPORTED for other shapes
+ * (mcq_vq_fused_supported() == 0): use mcq_vq_assign. */
+int mcq_vq_assign_fused(const float* x, const void* cb_lohi, float cb_scale, const float* c2, int64_t* codes,
+                        float* logits, const float* logit_scale, int32_t* hist, int32_t n, int32_t h, int32_t w,
+                        int32_t m, int32_t k, int32_t d, mcq_stream_t stream);
+int mcq_vq_fused_supported(int32_t h, int32_t w, int32_t k, int32_t d);
+
 /* Replaces _multiCodebookDeQuantization.decode (mcquic/modules/quantizer.py:249-259): gather codebook[m, code].
  * codes int64 [n,m,h,w] -> fp32 NHWC [n,h,w,m*d] and/or split-fp16 plane pairs (raw and/or act). Returns
  * MCQ_ERR_CODE_RANGE via *status (device int32, optional) if a code is outside [0,k). */

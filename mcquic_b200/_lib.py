@@ -45,6 +45,8 @@ SYMBOLS = {
     "mcq_stem_conv": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _i32, _p]),
     "mcq_vq_assign": (_c.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mcq_vq_assign_tc": (_c.c_int, [_p, _p, _p, _f, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
+    "mcq_vq_assign_fused": (_c.c_int, [_p, _p, _f, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "mcq_vq_fused_supported": (_c.c_int, [_i32, _i32, _i32, _i32]),
     "mcq_vq_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "mcq_vq_dequant": (_c.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _i32, _p, _p]),
     "mcq_code_histogram": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),

@@ -16,6 +16,7 @@
 #include "conv_chain.cuh"
 #include "misc.cuh"
 #include "vq.cuh"
+#include "vq_fused.cuh"
 
 using namespace mcq;
 
@@ -690,6 +691,80 @@ int mcq_vq_assign(const float* x, const float* codebook, const float* c2, int64_
   }
   dim3 grid((unsigned)((a.P + VQ_TP - 1) / VQ_TP), (unsigned)m);
   vq_assign_kernel<<<grid, VQ_THREADS, smem, (cudaStream_t)stream>>>(a);
+  g_launches++;
+  return cuda_status();
+}
+
+int mcq_vq_fused_supported(int32_t h, int32_t w, int32_t k, int32_t d) {
+  const int hw = h * w;
+  return (d == 32 || d == 64) && k > 0 && k % VQF_BN == 0 && hw > 0 && (hw % 32 == 0 || 32 % hw == 0);
+}
+
+int mcq_vq_assign_fused(const float* x, const void* cb_lohi, float cb_scale, const float* c2, int64_t* codes,
+                        float* logits, const float* logit_scale, int32_t* hist, int32_t n, int32_t h, int32_t w,
+                        int32_t m, int32_t k, int32_t d, mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && cb_lohi && c2 && codes);
+  MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && m > 0 && k > 0 && d > 0);
+  if (!mcq_vq_fused_supported(h, w, k, d)) return MCQ_ERR_UNSUPPORTED;
+  MCQ_CHECK_ARG(((uintptr_t)cb_lohi & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)c2 & 15) == 0);
+  if (logits) MCQ_CHECK_ARG(((uintptr_t)logits & 15) == 0);
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MCQ_ERR_DRIVER;
+  const int hw = h * w;
+  VqFusedArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.x = x; a.c2 = c2; a.codes = (long long*)codes; a.hist = hist; a.hist_on = hist ? 1 : 0;
+  a.logit_scale = logit_scale;
+  a.P = n * hw; a.hw = hw; a.m = m; a.k = k; a.d = d;
+  a.tiles_p = (a.P + VQF_BM - 1) / VQF_BM;
+  a.has_logits = logits ? 1 : 0;
+  a.cb_scale = cb_scale;
+  a.inv_sqrt_k = 1.0f / sqrtf((float)k);
+  const int kch = 2 * d / TC_BK;
+  const size_t op_bytes = (size_t)kch * VQF_CHUNK_BYTES;
+  const size_t st_bytes = logits ? (size_t)VQF_EPI_WARPS * 2 * VQF_STAGE_BYTES : 0;
+  const size_t fixed = 1024 + 2 * op_bytes + st_bytes + 2 * VQF_BM * 4 + 2 * VQF_BM * 8 + 64;
+  const size_t smem_max = 227 * 1024;
+  int nb = (int)((smem_max - fixed - 8 * 16) / op_bytes);
+  if (nb > 4) nb = 4;
+  if (nb < 2) return MCQ_ERR_UNSUPPORTED;
+  a.nb = nb;
+  const size_t smem = fixed + nb * op_bytes + 8 * (8 + 2 * nb);
+
+  CUtensorMap tmB, tmL;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(2 * d), (cuuint64_t)m * k};
+    cuuint64_t strides[1] = {(cuuint64_t)(2 * d) * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)VQF_BN};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(cb_lohi), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MCQ_ERR_DRIVER;
+  }
+  if (logits) {
+    // logits [n, m, hw, k] fp32; a store box = 32 codewords x 32 consecutive latent points of one codebook
+    const int blk_pix = hw >= 32 ? 32 : hw, blk_img = hw >= 32 ? 1 : 32 / hw;
+    cuuint64_t dims[4] = {(cuuint64_t)k, (cuuint64_t)hw, (cuuint64_t)m, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)k * 4, (cuuint64_t)hw * k * 4, (cuuint64_t)m * hw * k * 4};
+    cuuint32_t box[4] = {32u, (cuuint32_t)blk_pix, 1u, (cuuint32_t)blk_img};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tmL, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, logits, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+        CUDA_SUCCESS)
+      return MCQ_ERR_DRIVER;
+  } else {
+    tmL = tmB;
+  }
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(vq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
+  }
+  int grid = a.tiles_p * m;
+  if (grid > num_sms()) grid = num_sms();
+  vq_fused_kernel<<<grid, VQF_THREADS, smem, (cudaStream_t)stream>>>(tmB, tmL, a);
   g_launches++;
   return cuda_status();
 }

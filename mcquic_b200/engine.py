@@ -69,6 +69,14 @@ def split_weight(w2d: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, float]:
     return hi.contiguous(), lo.contiguous(), float(2.0 ** (-e))
 
 
+def pack_codebook(codebook: torch.Tensor):
+    """[m, k, d] fp32 -> (hi, lo, scale, lohi): split-fp16 planes [m*k, d] of c * 2^e and the fused-VQ operand
+    [m*k, 2d] whose rows are [lo | hi] (csrc/vq_fused.cuh)."""
+    d = codebook.shape[-1]
+    hi, lo, scale = split_weight(codebook.detach().float().reshape(-1, d))
+    return hi, lo, scale, torch.cat([lo, hi], dim=1).contiguous()
+
+
 def pack_conv(weight: torch.Tensor, bias: torch.Tensor, stride: int, store: int, device) -> PackedConv:
     """nn.Conv2d weight [cout, cin, k, k] -> K-major GEMM matrix [cout_pad, (r, s, cin)] (split fp16)."""
     cout, cin, k, _ = weight.shape
@@ -438,13 +446,23 @@ class Engine:
     def vq_assign(self, x_nhwc: torch.Tensor, codebook: torch.Tensor, c2: torch.Tensor, n: int, h: int, w: int,
                   logits: bool = False, logit_scale: Optional[torch.Tensor] = None,
                   hist: Optional[torch.Tensor] = None, packed=None):
-        """packed = (cb_hi, cb_lo, scale) split-fp16 codebook: enables the tensor-core path (d % 64 == 0)."""
+        """packed = pack_codebook(codebook): split-fp16 codebook for the tensor-core paths.
+        Routing: fused tcgen05 kernel (d in {32, 64}: hard codes and soft logits in one launch) -> GEMM-epilogue
+        argmin on the conv kernel (d % 64 == 0, hard codes only, needs `packed`) -> SIMT kernel (any shape)."""
         self.flush()
         m, k, d = codebook.shape
         dev = x_nhwc.device
         codes = torch.empty((n, m, h, w), dtype=torch.int64, device=dev)
-        use_tc = (packed is not None and not logits and d % 64 == 0 and k % 32 == 0 and not self.emulated
-                  and self.impl == _lib.IMPL_TCGEN05)
+        on_tc = not self.emulated and self.impl == _lib.IMPL_TCGEN05
+        if on_tc and self.lib.mcq_vq_fused_supported(h, w, k, d):
+            if packed is None or len(packed) < 4:
+                packed = pack_codebook(codebook)
+            lg = torch.empty((n, m, h, w, k), dtype=torch.float32, device=dev) if logits else None
+            _lib.check(self.lib.mcq_vq_assign_fused(_ptr(x_nhwc), _ptr(packed[3]), packed[2], _ptr(c2), _ptr(codes),
+                                                    _ptr(lg), _ptr(logit_scale), _ptr(hist), n, h, w, m, k, d,
+                                                    self._stream()), "mcq_vq_assign_fused")
+            return (codes, lg) if logits else codes
+        use_tc = packed is not None and not logits and d % 64 == 0 and k % 32 == 0 and on_tc
         if use_tc:
             nbytes = int(self.lib.mcq_vq_workspace_bytes(n, h, w, m, k, d))
             ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)

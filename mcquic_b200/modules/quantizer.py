@@ -113,11 +113,10 @@ class _multiCodebookQuantization(nn.Module):
         tensor-core kernel consumes."""
         ver = (self._codebook._version, self._codebook.data_ptr())
         if self._c2_cache is None or self._c2_cache[0] != ver:
-            from ..engine import split_weight
+            from ..engine import pack_codebook
             with torch.no_grad():
                 cb = self._codebook.detach().float().contiguous()
-                hi, lo, scale = split_weight(cb.reshape(-1, self._d))
-                self._c2_cache = (ver, cb, (cb ** 2).sum(-1).contiguous(), (hi, lo, scale))
+                self._c2_cache = (ver, cb, (cb ** 2).sum(-1).contiguous(), pack_codebook(cb))
         return self._c2_cache[1:]
 
     def _c2(self) -> torch.Tensor:
@@ -147,8 +146,9 @@ class _multiCodebookQuantization(nn.Module):
         n, c, h, w = x.shape
         eng = default_engine()
         scale = self._bound(self._temperature.detach().float()).reshape(-1).contiguous()
-        return eng.vq_assign(eng.from_nchw(x, {"f32"}).f32, self._cb(), self._c2(), n, h, w, logits=True,
-                             logit_scale=scale)
+        cb, c2, packed = self._tables()
+        return eng.vq_assign(eng.from_nchw(x, {"f32"}).f32, cb, c2, n, h, w, logits=True, logit_scale=scale,
+                             packed=packed)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor):

@@ -53,7 +53,7 @@ def test_assign_matches_oracle(n, h, w, m, k, d):
 @pytest.mark.parametrize("n,h,w,m,k,d", [
     (2, 16, 16, 1, 8192, 128),   # qp=1 level 0
     (64, 4, 4, 1, 512, 128),     # qp=1 level 2 at the benchmark batch (N tile narrowed to fill the SMs)
-    (2, 8, 8, 2, 2048, 64),      # qp=2-like: two codebooks, channel slices of the same latent
+    (2, 5, 7, 2, 2048, 64),      # qp=2-like: two codebooks, channel slices of the same latent (35 points/image: not fused)
     (1, 5, 7, 1, 96, 64),        # ragged point count, k = 96 (N tile 96)
 ])
 def test_tensor_core_assign_matches_oracle(n, h, w, m, k, d):
@@ -80,6 +80,61 @@ def test_tensor_core_assign_matches_oracle(n, h, w, m, k, d):
     exp = torch.cat([h_.flatten() for h_ in O.code_histogram([codes.cpu()], [k])]).int()
     assert torch.equal(hist.cpu(), exp)
     assert eng.lib.mcq_device_error_flag() == 0
+
+
+@pytest.mark.parametrize("n,h,w,m,k,d", [
+    (2, 32, 32, 6, 2048, 32),    # BASELINE configs[2] shape (qp=3-like: M=6, K=2048, d=32), 2 images
+    (2, 8, 8, 2, 2048, 64),      # qp=2-like: d=64 (two 64-element K chunks per operand row)
+    (3, 4, 4, 6, 256, 32),       # 16-point images: a 32-row store box spans two images; ragged last tile (48 points)
+    (5, 16, 16, 3, 128, 32),     # single codeword chunk per tile (k = 128)
+    (1, 1, 1, 2, 384, 64),       # one point
+    (40, 16, 16, 6, 512, 32),    # 480 tiles: several tiles per persistent CTA
+])
+@pytest.mark.parametrize("logits", [False, True])
+def test_fused_assign_matches_oracle(n, h, w, m, k, d, logits):
+    """mcq_vq_assign_fused (csrc/vq_fused.cuh): one launch = split + tcgen05 x.c + distance + argmin (+ logits via TMA
+    store) + histogram.  Codes bit-exact (flips only at fp32 near-ties), logits to 1e-5, histogram exact."""
+    from mcquic_b200.engine import pack_codebook
+    x = uniform((n, m * d, h, w), "vqf.x", 13) * 0.26
+    cb = uniform((m, k, d), "vqf.cb", 13) * 0.19
+    temp = (uniform((m,), "vqf.t", 13).abs() + 0.5).cuda()
+    eng = Engine()
+    xg = eng.from_nchw(x.cuda(), {"f32"}).f32
+    cbg = cb.cuda().contiguous()
+    c2 = (cbg ** 2).sum(-1).contiguous()
+    hist = torch.zeros(m * k, dtype=torch.int32, device="cuda")
+    assert eng.lib.mcq_vq_fused_supported(h, w, k, d) == 1
+    before = eng.lib.mcq_kernel_launch_count()
+    out = eng.vq_assign(xg, cbg, c2, n, h, w, logits=logits, logit_scale=temp if logits else None, hist=hist,
+                        packed=pack_codebook(cbg))
+    torch.cuda.synchronize()
+    assert eng.lib.mcq_kernel_launch_count() - before == 1
+    assert eng.lib.mcq_device_error_flag() == 0
+    codes = out[0] if logits else out
+    ref = O.vq_assign(x, cb)
+    mism = codes.cpu() != ref
+    if int(mism.sum()):
+        assert float(O.vq_margin(x, cb)[mism].max()) < 2e-6, "index flips only allowed at fp32 near-ties"
+    assert codes.dtype == torch.int64 and codes.shape == (n, m, h, w)
+    if logits:
+        lref = O.vq_logits(x, cb, temp.cpu().reshape(m, 1, 1, 1))
+        assert out[1].shape == (n, m, h, w, k)
+        assert float((out[1].cpu() - lref).abs().max()) <= 1e-5 * max(1.0, float(lref.abs().max()))
+    exp = torch.cat([h_.flatten() for h_ in O.code_histogram([codes.cpu()], [k])]).int()
+    assert torch.equal(hist.cpu(), exp)
+
+
+def test_fused_ties_pick_the_first_index():
+    m, k, d = 2, 256, 32
+    cb = uniform((m, k, d), "tie.cb32", 2)
+    cb[:, 200] = cb[:, 17]          # duplicates in the other column half / a later chunk: the first index must win
+    cb[:, 150] = cb[:, 17]
+    cb[:, 90] = cb[:, 17]
+    x = cb[:, 17].reshape(1, m * d, 1, 1).repeat(4, 1, 4, 4).clone()
+    eng = Engine()
+    cbg = cb.cuda().contiguous()
+    codes = eng.vq_assign(eng.from_nchw(x.cuda(), {"f32"}).f32, cbg, (cbg ** 2).sum(-1).contiguous(), 4, 4, 4)
+    assert (codes == 17).all()
 
 
 def test_tensor_core_ties_pick_the_first_index():

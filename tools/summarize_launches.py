@@ -39,7 +39,7 @@ def main(path, steps, out_json=None):
                                 "dram_write_bytes_per_step": a[3] / steps}
     ours = {k: v for k, v in out["kernels"].items() if k.startswith("mcq::")}
     out["dram_bytes_per_step"] = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"] for v in ours.values())
-    conv = {k: v for k, v in ours.items() if "conv_halo" in k or "conv_tc" in k}
+    conv = {k: v for k, v in ours.items() if "conv_halo" in k or "conv_tc" in k or "conv_pair" in k or "conv_chain" in k}
     out["conv_dram_bytes_per_step"] = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"] for v in conv.values())
     out["conv_share"] = sum(v["share"] for v in conv.values())
     print(f"# tcgen05 conv kernels: {100*out['conv_share']:.1f}% of the step, DRAM traffic {out['conv_dram_bytes_per_step']/1e9:.2f} GB per step")
