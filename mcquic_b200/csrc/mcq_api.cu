@@ -722,13 +722,19 @@ int mcq_vq_assign_fused(const float* x, const void* cb_lohi, float cb_scale, con
   a.inv_sqrt_k = 1.0f / sqrtf((float)k);
   const int kch = 2 * d / TC_BK;
   const size_t op_bytes = (size_t)kch * VQF_CHUNK_BYTES;
-  const size_t st_bytes = logits ? (size_t)VQF_EPI_WARPS * 2 * VQF_STAGE_BYTES : 0;
-  const size_t fixed = 1024 + 2 * op_bytes + st_bytes + 2 * VQF_BM * 4 + 2 * VQF_BM * 8 + 64;
   const size_t smem_max = 227 * 1024;
-  int nb = (int)((smem_max - fixed - 8 * 16) / op_bytes);
-  if (nb > 4) nb = 4;
+  int nst = 2, nb = 0;
+  size_t fixed = 0;
+  for (; nst >= 1; --nst) {   // prefer double-buffered logits staging; d=64 only has room for one buffer per warp
+    const size_t st_bytes = logits ? (size_t)VQF_EPI_WARPS * nst * VQF_STAGE_BYTES : 0;
+    fixed = 1024 + 2 * op_bytes + st_bytes + 2 * VQF_BM * 4 + 6 * VQF_BM * 8 + VQF_C2_SLOTS * VQF_BN * 4 + 64;
+    nb = fixed + 8 * 16 < smem_max ? (int)((smem_max - fixed - 8 * 16) / op_bytes) : 0;
+    if (nb >= 2) break;
+  }
   if (nb < 2) return MCQ_ERR_UNSUPPORTED;
+  if (nb > 4) nb = 4;
   a.nb = nb;
+  a.nst = nst;
   const size_t smem = fixed + nb * op_bytes + 8 * (8 + 2 * nb);
 
   CUtensorMap tmB, tmL;
@@ -756,15 +762,16 @@ int mcq_vq_assign_fused(const float* x, const void* cb_lohi, float cb_scale, con
   } else {
     tmL = tmB;
   }
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(vq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t smem_set[2] = {0, 0};
+  auto kern = logits ? vq_fused_kernel<true> : vq_fused_kernel<false>;
+  if (smem > smem_set[logits ? 1 : 0]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    smem_set = smem;
+    smem_set[logits ? 1 : 0] = smem;
   }
   int grid = a.tiles_p * m;
   if (grid > num_sms()) grid = num_sms();
-  vq_fused_kernel<<<grid, VQF_THREADS, smem, (cudaStream_t)stream>>>(tmB, tmL, a);
+  kern<<<grid, VQF_THREADS, smem, (cudaStream_t)stream>>>(tmB, tmL, a);
   g_launches++;
   return cuda_status();
 }

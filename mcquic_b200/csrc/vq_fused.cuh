@@ -12,10 +12,11 @@
 //   MMA     = D_hh = x_hi.c_hi  (K-steps [0, d/16) of A against K-steps [d/16, 2d/16) of B)
 //             D_lo = x_hi.c_lo + x_lo.c_hi  (all 2d/16 K-steps, same offsets in A and B)   -> 3 fp16 passes, fp32-grade
 //   TMEM    = 2 x (128 + 128) columns: chunk c+1 is multiplied while chunk c is drained
-//   drain   = 8 warps (4 lane quarters x 2 column halves): tcgen05.ld -> dist = (|x|^2 + |c|^2) - 2 x.c in the
+//   drain   = 16 warps (4 lane quarters x 4 column quarters): tcgen05.ld -> dist = (|x|^2 + |c|^2) - 2 x.c in the
 //             reference's operation order -> running (distance, index) minimum (strict <: first index wins ties) ->
 //             logits = dist * (-temperature / sqrt(k)) -> swizzled smem staging -> TMA store of a 32 x 32 fp32 box
-//   finish  = the two column halves are merged through shared memory; int64 codes and the histogram are written.
+//   |c|^2   = 512 B per chunk, bulk-copied (cp.async.bulk) into an 8-slot shared-memory ring with the codebook stage
+//   finish  = the four column quarters are merged through shared memory; int64 codes and the histogram are written.
 //
 // Supported: d in {32, 64}, k % 128 == 0, (h*w) % 32 == 0 or 32 % (h*w) == 0; everything else -> vq_assign_kernel.
 #pragma once
@@ -26,12 +27,13 @@ namespace mcq {
 constexpr int VQF_BM = 128;
 constexpr int VQF_BN = 128;
 constexpr int VQF_PROD_WARPS = 4;
-constexpr int VQF_EPI_WARPS = 8;
+constexpr int VQF_EPI_WARPS = 16;                                                // 4 TMEM lane quarters x 4 column quarters
 constexpr int VQF_FIRST_PROD = 2;
 constexpr int VQF_FIRST_EPI = VQF_FIRST_PROD + VQF_PROD_WARPS;                 // 6 (6 % 4 == 2: quarters 2,3,0,1)
-constexpr int VQF_THREADS = 32 * (VQF_FIRST_EPI + VQF_EPI_WARPS);               // 448
+constexpr int VQF_THREADS = 32 * (VQF_FIRST_EPI + VQF_EPI_WARPS);               // 704
 constexpr int VQF_CHUNK_BYTES = VQF_BM * 128;                                    // one 64-element K chunk of 128 rows
 constexpr int VQF_STAGE_BYTES = 4096;                                            // 32 rows x 32 fp32
+constexpr int VQF_C2_SLOTS = 8;   // ring of |c_k|^2 chunks (128 floats); > codebook stages + TMEM buffers + 1, see below
 
 struct VqFusedArgs {
   const float* x;            // [P, m*d] NHWC latents
@@ -46,6 +48,7 @@ struct VqFusedArgs {
   float cb_scale;            // 2^-e of the packed codebook
   float inv_sqrt_k;
   int hist_on;
+  int nst;                   // logits staging buffers per drain warp (2, or 1 when shared memory is short)
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -58,10 +61,32 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Wait for warps that are off the critical path (codebook stream, MMA issue, latent producer): between polls the warp
+// sleeps, so its spin loop does not take issue slots from the drain warps sharing its scheduler (ncu: 45 % of all
+// executed instructions were wait loops before this).  Same 4 s watchdog as mbar_wait.
+__device__ __noinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, int code, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  for (unsigned i = 1;; ++i) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((i & 1023u) == 0 && global_ns() - t0 > TC_WATCHDOG_NS) {
+      atomicExch(&g_watchdog_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void named_bar(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+template <bool LOGITS>
 __global__ void __launch_bounds__(VQF_THREADS, 1)
 vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmL, const VqFusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -75,10 +100,12 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + 2u * op_bytes;
   const uint32_t st_base = b_base + (uint32_t)nb * op_bytes;                       // logits staging (1024-aligned)
-  const uint32_t st_bytes = a.has_logits ? (uint32_t)(VQF_EPI_WARPS * 2 * VQF_STAGE_BYTES) : 0u;
+  const uint32_t st_bytes = LOGITS ? (uint32_t)(VQF_EPI_WARPS * a.nst * VQF_STAGE_BYTES) : 0u;
   const uint32_t x2_off = (st_base - smem_base) + st_bytes;                        // float [2][128]
-  const uint32_t red_off = x2_off + 2u * VQF_BM * 4u;                              // u64 [2][128]
-  const uint32_t bar_base = smem_base + red_off + 2u * VQF_BM * 8u;
+  const uint32_t red_off = x2_off + 2u * VQF_BM * 4u;                              // u64 [2][3][128]
+  const uint32_t c2_off = red_off + 6u * VQF_BM * 8u;                              // float [VQF_C2_SLOTS][128]
+  const uint32_t bar_base = smem_base + c2_off + (uint32_t)VQF_C2_SLOTS * VQF_BN * 4u;
+  const uint32_t c2_base = smem_base + c2_off;
   float* x2buf = reinterpret_cast<float*>(smem_gen + x2_off);
   unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_gen + red_off);
   auto a_full = [&](int i) { return bar_base + 8u * i; };
@@ -91,7 +118,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmB);
-    if (a.has_logits) tma_prefetch_desc(&tmL);
+    if (LOGITS) tma_prefetch_desc(&tmL);
     for (int i = 0; i < 2; ++i) {
       mbar_init(a_full(i), VQF_PROD_WARPS * 32);
       mbar_init(a_empty(i), 1 + VQF_EPI_WARPS);
@@ -126,13 +153,18 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mi = t / a.tiles_p;
       for (int c = 0; c < chunks; ++c, ++gc) {
-        const int s = gc % nb;
-        mbar_wait(b_empty(s), (((uint32_t)(gc / nb)) & 1u) ^ 1u, 31);
+        // |c_k|^2 of the chunk rides on the codebook stage's barrier but lives in its own ring: the drain warps read it
+        // after the MMA has released the stage.  Slot gc % 8 was last read by the drain of chunk gc - 8; this point is
+        // only reached after MMA(gc - nb) completed, hence after drain(gc - nb - 2) handed its accumulator back (its
+        // |c|^2 reads precede that hand-over), and nb + 2 <= 6 < 8.
+        const int s = gc % nb, cs = gc % VQF_C2_SLOTS;
+        mbar_wait_sleep(b_empty(s), (((uint32_t)(gc / nb)) & 1u) ^ 1u, 31, 200);
         if (elect_one()) {
-          mbar_expect_tx(b_full(s), op_bytes);
+          mbar_expect_tx(b_full(s), op_bytes + VQF_BN * 4u);
           for (int kc = 0; kc < kch; ++kc)
             tma_load_2d(&tmB, b_base + (uint32_t)s * op_bytes + (uint32_t)kc * VQF_CHUNK_BYTES, b_full(s), kc * TC_BK,
                         mi * a.k + c * VQF_BN);
+          bulk_load_1d(c2_base + (uint32_t)cs * VQF_BN * 4u, a.c2 + (size_t)mi * a.k + c * VQF_BN, VQF_BN * 4u, b_full(s));
         }
         __syncwarp();
       }
@@ -144,12 +176,12 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
     int gc = 0, i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
       const int ab = i & 1;
-      mbar_wait(a_full(ab), ((uint32_t)(i >> 1)) & 1u, 32);
+      mbar_wait_sleep(a_full(ab), ((uint32_t)(i >> 1)) & 1u, 32, 100);
       const uint64_t a0 = make_sdesc(a_base + (uint32_t)ab * op_bytes);
       for (int c = 0; c < chunks; ++c, ++gc) {
         const int s = gc % nb, buf = gc & 1;
-        mbar_wait(tempty(buf), (((uint32_t)(gc >> 1)) & 1u) ^ 1u, 33);
-        mbar_wait(b_full(s), ((uint32_t)(gc / nb)) & 1u, 34);
+        mbar_wait_sleep(tempty(buf), (((uint32_t)(gc >> 1)) & 1u) ^ 1u, 33, 60);
+        mbar_wait_sleep(b_full(s), ((uint32_t)(gc / nb)) & 1u, 34, 60);
         tc_fence_after();
         const uint64_t b0 = make_sdesc(b_base + (uint32_t)s * op_bytes);
         const uint32_t d_hh = tmem_base + (uint32_t)(buf * 2 * VQF_BN);
@@ -176,7 +208,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
       const int ab = i & 1;
       const int mi = t / a.tiles_p, p0 = (t - mi * a.tiles_p) * VQF_BM;
-      mbar_wait(a_empty(ab), (((uint32_t)(i >> 1)) & 1u) ^ 1u, 35);
+      mbar_wait_sleep(a_empty(ab), (((uint32_t)(i >> 1)) & 1u) ^ 1u, 35, 1000);
       const uint32_t abuf = a_base + (uint32_t)ab * op_bytes;
       for (int r0 = 0; r0 < VQF_BM; r0 += rows_per_pass) {
         const int row = r0 + ptid / g, j = ptid % g;
@@ -216,13 +248,22 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
     // ===================== drain: distance, argmin, logits =====================
     const int q = warp & 3;
     const int ew = warp - VQF_FIRST_EPI;
-    const int cg = ew >> 2;                                // column half of every chunk
+    const int cg = ew >> 2;                                // column quarter of every chunk: columns [32 cg, 32 cg + 32)
     const int row = q * 32 + lane;
-    const uint32_t stage = st_base + (uint32_t)ew * (2u * VQF_STAGE_BYTES);
     const float neg2s = -2.0f * a.cb_scale;
     const int per = a.hw >= 32 ? a.hw / 32 : 1;            // 32-row blocks per image (hw >= 32)
     const int ib = a.hw >= 32 ? 1 : 32 / a.hw;             // images per 32-row block (hw < 32)
-    int gc = 0, i = 0;
+    const int col0 = cg * 32;
+    // loop-invariant addresses.  Staging row `lane`, 16 B chunk j is stored at chunk j ^ (lane & 7) (the 128B swizzle
+    // the store tensor map expects); with the base below that is simply base ^ (j << 4).
+    const uint32_t stage0 = st_base + (uint32_t)ew * (uint32_t)(a.nst * VQF_STAGE_BYTES);
+    const uint32_t stage_flip = a.nst == 2 ? (uint32_t)VQF_STAGE_BYTES : 0u;
+    const uint32_t wlane = (uint32_t)lane * 128u + ((uint32_t)(lane & 7) << 4);
+    const uint32_t t_acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+    const uint32_t c2_mine = c2_base + (uint32_t)col0 * 4u;
+    const uint32_t tfull0 = tfull(0), tempty0 = tempty(0);
+    uint32_t gc = 0;
+    int i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
       const int ab = i & 1;
       const int mi = t / a.tiles_p, p0 = (t - mi * a.tiles_p) * VQF_BM;
@@ -231,81 +272,83 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(a_empty(ab));
       const float lscale = -a.inv_sqrt_k * (a.logit_scale ? a.logit_scale[mi] : 1.0f);
-      const float* c2m = a.c2 + (size_t)mi * a.k;
       const int rb = (p0 + q * 32) >> 5;                   // global 32-row block of this warp
       const int nn0 = a.hw >= 32 ? rb / per : rb * ib;
       const int pix0 = a.hw >= 32 ? (rb - nn0 * per) * 32 : 0;
       const bool blk_live = (p0 + q * 32) < a.P;
       float best = INFINITY;
       int best_k = 0x7fffffff;
-      for (int c = 0; c < chunks; ++c, ++gc) {
-        const int buf = gc & 1;
-        mbar_wait(tfull(buf), ((uint32_t)(gc >> 1)) & 1u, 37);
+      int kcol = col0;                                     // codeword index of this warp's first column in the chunk
+      for (int c = 0; c < chunks; ++c, ++gc, kcol += VQF_BN) {
+        const uint32_t buf = gc & 1u;
+        const uint32_t sbuf = stage0 + buf * stage_flip;
+        const uint32_t c2a = c2_mine + (gc & (uint32_t)(VQF_C2_SLOTS - 1)) * (uint32_t)(VQF_BN * 4);
+        mbar_wait(tfull0 + 8u * buf, (gc >> 1) & 1u, 37);
         tc_fence_after();
-        const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * VQF_BN);
+        const uint32_t t_acc = t_acc0 + buf * (uint32_t)(2 * VQF_BN);
+        if (LOGITS) {
+          // the TMA store that last read this staging buffer must have drained it
+          if (lane == 0) { if (a.nst == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+          __syncwarp();
+        }
+        const uint32_t wb = sbuf + wlane;
+        int best_e = -1;
 #pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-          const int col0 = cg * 64 + blk * 32;             // column inside the chunk
-          const uint32_t sbuf = stage + (uint32_t)blk * VQF_STAGE_BYTES;
-          if (a.has_logits) {
-            if (lane == 0) bulk_wait_read<1>();            // the store that last read this staging buffer is done
+        for (int half = 0; half < 2; ++half) {
+          uint32_t hh[16], ll[16];
+          tmem_ld16(t_acc + (uint32_t)(half * 16), hh);
+          tmem_ld16(t_acc + (uint32_t)(VQF_BN + half * 16), ll);
+          float cc[16];                                     // |c_k|^2: broadcast reads from the shared-memory ring
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(cc[e]), "=f"(cc[e + 1]), "=f"(cc[e + 2]), "=f"(cc[e + 3])
+                         : "r"(c2a + (uint32_t)((half * 16 + e) * 4)));
+          tmem_ld_wait();
+          if (half == 1) {                                  // accumulator fully read: hand the buffer back to the MMA
+            tc_fence_before();
             __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8u * buf);
           }
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int cs = col0 + sub * 16;
-            uint32_t hh[16], ll[16];
-            tmem_ld16(t_acc + (uint32_t)cs, hh);
-            tmem_ld16(t_acc + (uint32_t)(VQF_BN + cs), ll);
-            float cc[16];
+          for (int e4 = 0; e4 < 16; e4 += 4) {
+            float lg[4];
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(c2m + c * VQF_BN + cs + e));
-              cc[e] = v.x; cc[e + 1] = v.y; cc[e + 2] = v.z; cc[e + 3] = v.w;
-            }
-            tmem_ld_wait();
-            if (blk == 1 && sub == 1) {                     // accumulator fully read: hand the buffer back to the MMA
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty(buf));
-            }
-            float lg[16];
-            const int kbase = c * VQF_BN + cs;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
+            for (int u = 0; u < 4; ++u) {
+              const int e = e4 + u;
               const float tt = fmaf(__uint_as_float(ll[e]), kLoInv, __uint_as_float(hh[e]));
               const float dist = fmaf(tt, neg2s, x2 + cc[e]);    // (|x|^2 + |c|^2) - 2 x.c  (quantizer.py:176)
-              if (dist < best) { best = dist; best_k = kbase + e; }
-              lg[e] = dist * lscale;
+              if (dist < best) { best = dist; best_e = half * 16 + e; }   // strict <: the first index wins ties
+              if (LOGITS) lg[u] = dist * lscale;
             }
-            if (a.has_logits) {
-              const uint32_t wb = sbuf + (uint32_t)lane * 128u;
-              const uint32_t sw = (uint32_t)(lane & 7);
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wb + ((((uint32_t)(sub * 4 + ch)) ^ sw) << 4)),
-                             "f"(lg[4 * ch]), "f"(lg[4 * ch + 1]), "f"(lg[4 * ch + 2]), "f"(lg[4 * ch + 3])
-                             : "memory");
-            }
+            if (LOGITS)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(wb ^ (uint32_t)((half * 4 + (e4 >> 2)) << 4)),
+                           "f"(lg[0]), "f"(lg[1]), "f"(lg[2]), "f"(lg[3])
+                           : "memory");
           }
-          if (a.has_logits) {
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (blk_live) tma_store_4d(&tmL, sbuf, c * VQF_BN + col0, pix0, mi, nn0);
-              bulk_commit();
-            }
+        }
+        if (best_e >= 0) best_k = kcol + best_e;
+        if (LOGITS) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (blk_live) tma_store_4d(&tmL, sbuf, kcol, pix0, mi, nn0);
+            bulk_commit();
           }
         }
       }
-      // merge the two column halves: (distance, index) lexicographic minimum = first index on ties
+      // merge the four column quarters: (distance, index) lexicographic minimum = first index on ties
       unsigned long long key = ((unsigned long long)ordered_f32(best) << 32) | (unsigned long long)(uint32_t)best_k;
-      unsigned long long* rbuf = red + (i & 1) * VQF_BM;
-      if (cg == 1) rbuf[row] = key;
-      named_bar(1 + q, 64);
+      unsigned long long* rbuf = red + (size_t)(i & 1) * 3 * VQF_BM;
+      if (cg > 0) rbuf[(cg - 1) * VQF_BM + row] = key;
+      named_bar(1 + q, 128);
       if (cg == 0) {
-        const unsigned long long other = rbuf[row];
-        if (other < key) key = other;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const unsigned long long other = rbuf[o * VQF_BM + row];
+          if (other < key) key = other;
+        }
         const int pnt = p0 + row;
         if (pnt < a.P) {
           int code = (int)(key & 0xFFFFFFFFull);
@@ -316,7 +359,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
         }
       }
     }
-    if (a.has_logits && lane == 0) bulk_wait_all();
+    if (LOGITS && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
