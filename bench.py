@@ -12,8 +12,9 @@ own batch of 64 images (weak scaling; images are independent).  Prints ONE JSON 
 
 value      device time of K steps (CUDA events per step on the launching stream, L2 flushed between steps,
            max over ranks), inputs resident in HBM.
-e2e        same steps through the public API from pinned HOST memory: H2D of the images, encode, D2H of the
-           codes, decode, D2H of the pixels -- all inside the timed region.
+e2e        same steps through the public API with pinned HOST buffers: encode(host batch) (chunked H2D overlapping the
+           first layers), D2H of the codes, decode(codes, out=host batch) (chunked D2H overlapping the last layers) --
+           all inside the timed region.
 roofline   every tcgen05 convolution launch of one step bracketed by CUDA events (eager pass after the timed
            region): achieved = sum(algorithmic FLOPs) / sum(durations) against the measured dense bf16/fp16 peak.
 cpu_baseline / --impl reference: the oracle restatement of the reference's PyTorch CPU path (oracle/mcquic_oracle.py;
@@ -46,7 +47,7 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -59,7 +60,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -189,15 +190,15 @@ def run_ours(args):
     codes_host = [torch.empty((BATCH, M, H >> (4 + l), W >> (4 + l)), dtype=torch.int64).pin_memory() for l in range(len(K))]
 
     def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
+        # public API with HOST buffers: the pinned image batch goes in, codes and pixels come back to pinned host memory.
+        # encode(host) / decode(out=host) stream the batch in chunks that overlap the first / last layers.
         hist = torch.zeros(hist_total, dtype=torch.int32, device=dev)
-        codes = model.encode(xd, hist=hist)
+        codes = model.encode(x_host, hist=hist)
         if world > 1:
             gather_histograms(hist)
         for dst, src in zip(codes_host, codes):
             dst.copy_(src, non_blocking=True)
-        xhat = model.decode(codes)
-        xhat_host.copy_(xhat, non_blocking=True)
+        model.decode(codes, out=xhat_host)
         torch.cuda.current_stream().synchronize()
         return float(xhat_host[0, 0, 0, 0])
 

@@ -40,6 +40,14 @@ class Act:
     silu: Optional[Planes] = None
     sq: Optional[Planes] = None
 
+    def batch_slice(self, n0: int, n1: int) -> "Act":
+        """Images [n0, n1) of this activation (NHWC: a contiguous view of every representation)."""
+        def cut(t):
+            return None if t is None else t[n0:n1]
+        def cut2(pl):
+            return None if pl is None else (cut(pl[0]), cut(pl[1]))
+        return Act(n1 - n0, self.h, self.w, self.c, cut(self.f32), cut2(self.raw), cut2(self.silu), cut2(self.sq))
+
 
 @dataclass
 class PackedConv:
@@ -226,6 +234,16 @@ class Engine:
         lo = torch.empty((n, h, w, c), dtype=torch.float16, device=device) if self.passes == 3 else None
         return hi, lo
 
+    def alloc_act(self, n, h, w, c, want: Set[str], device) -> Act:
+        """Caller-owned output buffers for `conv(..., into=)` (chunked execution writes batch slices of them)."""
+        out = Act(n, h, w, c)
+        if "f32" in want:
+            out.f32 = torch.empty((n, h, w, c), dtype=torch.float32, device=device)
+        for name in ("raw", "silu", "sq"):
+            if name in want:
+                setattr(out, name, self._planes(n, h, w, c, device))
+        return out
+
     def _packed_for(self, mod: nn.Module, store: int = _lib.STORE_NHWC) -> PackedConv:
         key = (id(mod), store)
         if isinstance(mod, GenDivNorm):
@@ -255,7 +273,9 @@ class Engine:
     # ------------------------------------------------------------------ one fused conv launch
     def conv(self, pc: PackedConv, a: Planes, x: Act, want: Set[str], *, mode: int = _lib.EPI_LINEAR,
              res1: Optional[torch.Tensor] = None, res1_scale: float = 1.0, res2: Optional[torch.Tensor] = None,
-             aux: Optional[torch.Tensor] = None) -> Act:
+             aux: Optional[torch.Tensor] = None, into: Optional[Act] = None) -> Act:
+        """into: write the outputs into these caller-owned tensors (same shapes / representations as `want`) instead
+        of allocating them -- used when a batch is processed in chunks that fill slices of one full-batch tensor."""
         assert pc.cin == x.c, (pc.cin, x.c)
         dev = a[0].device
         ho, wo = x.h // pc.stride, x.w // pc.stride
@@ -273,17 +293,38 @@ class Engine:
         p.mode, p.store = mode, pc.store
         p.res1, p.res1_scale, p.res2, p.aux = _ptr(res1), res1_scale, _ptr(res2), _ptr(aux)
         keep = [a, res1, res2, aux]
+        def given(t, shape, dtype):
+            if t is None or tuple(t.shape) != shape or t.dtype != dtype or not t.is_contiguous():
+                raise RuntimeError("mcquic_b200: `into` buffers do not match the convolution's outputs")
+            return t
+
         if pc.store == _lib.STORE_SHUFFLE_NCHW:
-            out.f32 = torch.empty((x.n, co, ho, wo), dtype=torch.float32, device=dev)  # NCHW pixels
+            if into is not None:
+                out.f32 = given(into.f32, (x.n, co, ho, wo), torch.float32)
+            else:
+                out.f32 = torch.empty((x.n, co, ho, wo), dtype=torch.float32, device=dev)  # NCHW pixels
             p.out_f32 = _ptr(out.f32)
         else:
             if "f32" in want:
-                out.f32 = torch.empty((x.n, ho, wo, co), dtype=torch.float32, device=dev)
+                if into is not None:
+                    out.f32 = given(into.f32, (x.n, ho, wo, co), torch.float32)
+                else:
+                    out.f32 = torch.empty((x.n, ho, wo, co), dtype=torch.float32, device=dev)
                 p.out_f32 = _ptr(out.f32)
             slots = []
             for name, act in (("raw", _lib.ACT_NONE), ("silu", _lib.ACT_SILU), ("sq", _lib.ACT_SQUARE)):
                 if name in want:
-                    pl = self._planes(x.n, ho, wo, co, dev)
+                    if into is not None:
+                        pl = getattr(into, name)
+                        if pl is None:
+                            raise RuntimeError(f"mcquic_b200: `into` lacks the '{name}' planes")
+                        given(pl[0], (x.n, ho, wo, co), torch.float16)
+                        if self.passes == 3:
+                            given(pl[1], (x.n, ho, wo, co), torch.float16)
+                        else:
+                            pl = (pl[0], None)
+                    else:
+                        pl = self._planes(x.n, ho, wo, co, dev)
                     setattr(out, name, pl)
                     slots.append((pl, act))
             assert len(slots) <= 2, want
@@ -297,7 +338,7 @@ class Engine:
                 "passes": p.passes, "impl": p.impl, "shape": (x.n, x.h, x.w, pc.cin, pc.cout, pc.ksize, pc.stride)}
         # everything the launch touches stays referenced until it has been issued (a freed block could otherwise be
         # handed to a later layer of the same chain, whose clusters do not run in lock step)
-        item = (p, (keep, out, pc), info)
+        item = (p, (keep, out, pc, into), info)
         if (self.chain and p.impl == _lib.IMPL_TCGEN05 and (x.h // pc.stride) * (x.w // pc.stride) <= self.CHAIN_MAX_PIXELS):
             self._pending.append(item)
         else:
@@ -317,9 +358,10 @@ class Engine:
             return {"raw"}
         raise NotImplementedError(f"mcquic_b200: no accelerated path for {type(mod).__name__}")
 
-    def residual_block(self, mod: ResidualBlock, x: Act, want: Set[str], res2: Optional[torch.Tensor] = None) -> Act:
+    def residual_block(self, mod: ResidualBlock, x: Act, want: Set[str], res2: Optional[torch.Tensor] = None,
+                       into: Optional[Act] = None) -> Act:
         t = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"silu"})
-        return self.conv(self._packed_for(mod._branch[3]), t.silu, t, want, res1=x.f32, res2=res2)
+        return self.conv(self._packed_for(mod._branch[3]), t.silu, t, want, res1=x.f32, res2=res2, into=into)
 
     def residual_block_stride(self, mod: ResidualBlockWithStride, x: Act, want: Set[str]) -> Act:
         u = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"f32", "sq"})
@@ -351,11 +393,15 @@ class Engine:
         return self.conv(self._packed_for(mod._sideBranch[3]), b.raw, b, want, mode=_lib.EPI_GATE, res1=x.f32,
                          aux=a.f32)
 
-    def run(self, mod: nn.Module, x: Act, want: Set[str], tail: Optional[Tuple[torch.Tensor, float]] = None) -> Act:
-        """tail = (tensor, scale): an extra fp32 NHWC term added by the module's last epilogue."""
+    def run(self, mod: nn.Module, x: Act, want: Set[str], tail: Optional[Tuple[torch.Tensor, float]] = None,
+            into: Optional[Act] = None) -> Act:
+        """tail = (tensor, scale): an extra fp32 NHWC term added by the module's last epilogue.
+        into (ResidualBlock and the final pixel-shuffle conv only): caller-owned output buffers, see conv()."""
         if isinstance(mod, ResidualBlock):
             assert tail is None or tail[1] == 1.0
-            return self.residual_block(mod, x, want, None if tail is None else tail[0])
+            return self.residual_block(mod, x, want, None if tail is None else tail[0], into=into)
+        if into is not None and not (isinstance(mod, nn.Sequential) and len(mod) == 2):
+            raise NotImplementedError("mcquic_b200: `into` is supported for ResidualBlock and the final conv only")
         if isinstance(mod, nn.Conv2d):
             if tail is None:
                 return self.conv(self._packed_for(mod), x.raw, x, want)
@@ -369,7 +415,7 @@ class Engine:
             return self.attention_block(mod, x, want)
         if isinstance(mod, nn.Sequential) and len(mod) == 2 and isinstance(mod[1], nn.PixelShuffle):
             # pixelShuffle3x3 used stand-alone = last decoder layer -> fp32 NCHW pixels
-            return self.conv(self._packed_for(mod[0], _lib.STORE_SHUFFLE_NCHW), x.raw, x, want)
+            return self.conv(self._packed_for(mod[0], _lib.STORE_SHUFFLE_NCHW), x.raw, x, want, into=into)
         raise NotImplementedError(f"mcquic_b200: no accelerated path for {type(mod).__name__}")
 
     def run_seq(self, mods: Sequence[nn.Module], x: Act, want: Set[str],
@@ -382,7 +428,8 @@ class Engine:
 
     # ------------------------------------------------------------------ boundary ops
     def stem(self, conv: nn.Conv2d, x: torch.Tensor, pad: Tuple[int, int, int, int], want: Set[str]) -> Act:
-        """conv3x3 s2 on the fp32 NCHW image; pad = (top, left, padded_h, padded_w) (AlignedPadding folded in)."""
+        """conv3x3 s2 on the fp32 NCHW image; pad = (top, left, padded_h, padded_w) (AlignedPadding folded in).
+        (Chunked execution calls this on batch slices of the image tensor; the outputs are chunk-local.)"""
         self.flush()
         n, c, h, w = x.shape
         if c != 3 or conv.in_channels != 3 or conv.stride[0] != 2:

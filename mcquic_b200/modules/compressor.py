@@ -10,7 +10,7 @@ from typing import List, Optional, Tuple
 import torch
 from torch import nn
 
-from ..engine import Engine
+from ..engine import Act, Engine
 from ..nn import AttentionBlock, ResidualBlock, ResidualBlockShuffle, ResidualBlockWithStride, conv3x3, pixelShuffle3x3
 from .quantizer import UMGMQuantizer
 
@@ -38,6 +38,10 @@ class BaseCompressor(nn.Module):
         self.use_graphs = True
         self._graphs = {}
         self.graph_launches = 0  # kernels launched through graph replays (the library counts eager launches)
+        # host I/O pipeline: a pinned host batch is processed in HOST_CHUNKS slices through the first (encode) / last
+        # (decode) full-resolution layers so that the PCIe copies overlap the convolutions
+        self._pipes = {}
+        self._copy_stream = None
 
     @property
     def QuantizationParameter(self) -> str:
@@ -68,12 +72,26 @@ class BaseCompressor(nn.Module):
     def _check_image(self, x: torch.Tensor):
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError(f"expected an image batch [n, 3, h, w], got {tuple(x.shape)}")
-        if not x.is_cuda and not self.engine.emulated:
-            raise RuntimeError("mcquic_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        if not x.is_cuda and not self.engine.emulated and not self._host_batch_ok(x):
+            raise RuntimeError("mcquic_b200 runs on CUDA tensors (or pinned fp32 host batches a CUDA-resident model "
+                               "streams in); there is no CPU fallback")
+
+    HOST_CHUNKS = 4
+
+    def _device(self) -> torch.device:
+        return self._encoder[0].weight.device
+
+    def _host_batch_ok(self, t: torch.Tensor) -> bool:
+        """A pinned, contiguous fp32 host batch that the chunked copy/compute pipeline can stream."""
+        return (not t.is_cuda and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4
+                and self.use_graphs and not self.engine.emulated and self._device().type == "cuda"
+                and t.shape[0] % self.HOST_CHUNKS == 0 and t.shape[0] // self.HOST_CHUNKS >= 4
+                and isinstance(self._encoder[1], ResidualBlock) and isinstance(self._decoder[5], ResidualBlock))
 
     def invalidate(self):
         """Drop captured graphs and repacked weights (call after changing parameters in place)."""
         self._graphs.clear()
+        self._pipes.clear()
         if self._engine is not None:
             self._engine._packed.clear()
 
@@ -125,11 +143,148 @@ class BaseCompressor(nn.Module):
             self._graphs[key] = entry
         return entry
 
+    # ------------------------------------------------------------------ host I/O pipeline
+    def _encode_head(self, x_chunk: torch.Tensor, into: Act):
+        """stem + first ResidualBlock (full resolution) on a batch slice, written into the full-batch activation."""
+        eng = self.engine
+        eng.passes = self.encode_passes
+        _, _, h, w = x_chunk.shape
+        y0 = eng.stem(self._encoder[0], x_chunk, aligned_pad_amounts(h, w), eng.needs_of(self._encoder[1]))
+        eng.run(self._encoder[1], y0, eng.needs_of(self._encoder[2]), into=into)
+        eng.flush()
+
+    def _encode_tail(self, y1: Act, hist: Optional[torch.Tensor]) -> List[torch.Tensor]:
+        eng = self.engine
+        eng.passes = self.encode_passes
+        y = eng.run_seq(list(self._encoder)[2:], y1, self._quantizer.first_needs(eng))
+        codes = self._quantizer.encode_act(eng, y, hist)
+        eng.flush()
+        return codes
+
+    def _decode_main(self, codes: List[torch.Tensor], status: torch.Tensor) -> Act:
+        eng = self.engine
+        eng.passes = self.decode_passes
+        yHat = self._quantizer.decode_act(eng, codes, eng.needs_of(self._decoder[0]), status)
+        y = eng.run_seq(list(self._decoder)[:5], yHat, eng.needs_of(self._decoder[5]))
+        eng.flush()
+        return y
+
+    def _decode_tail(self, y4_chunk: Act, out_chunk: torch.Tensor):
+        """last ResidualBlock + final pixel-shuffle conv on a batch slice -> NCHW pixels of that slice."""
+        eng = self.engine
+        eng.passes = self.decode_passes
+        y5 = eng.run(self._decoder[5], y4_chunk, eng.needs_of(self._decoder[6]))
+        n, c, h, w = out_chunk.shape
+        eng.run(self._decoder[6], y5, set(), into=Act(n, h, w, c, f32=out_chunk))
+        eng.flush()
+
+    def _streams(self, dev):
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        return torch.cuda.current_stream(dev), self._copy_stream
+
+    def _encode_pipelined(self, x: torch.Tensor, hist: Optional[torch.Tensor]) -> List[torch.Tensor]:
+        """x: pinned host batch.  Chunk c is copied on the copy stream while chunk c-1 runs stem + first block."""
+        dev = self._device()
+        n, _, h, w = x.shape
+        ch, nc = self.HOST_CHUNKS, n // self.HOST_CHUNKS
+        key = ("enc", tuple(x.shape), self.encode_passes, dev)
+        pipe = self._pipes.get(key)
+        with torch.cuda.device(dev):
+            if pipe is None:
+                eng = self.engine
+                eng.passes = self.encode_passes
+                total = sum(self._quantizer._m * k for k in self._quantizer._k)
+                sx = torch.empty(tuple(x.shape), dtype=torch.float32, device=dev)
+                sh = torch.zeros(total, dtype=torch.int32, device=dev)
+                _, _, hp, wp = aligned_pad_amounts(h, w)
+                y1 = eng.alloc_act(n, hp // 2, wp // 2, self._encoder[0].out_channels, eng.needs_of(self._encoder[2]), dev)
+                sx.zero_()
+                heads, launches = [], 0
+                for c in range(ch):
+                    g, _, _, l = self._graph(key + ("head", c), list,
+                                             lambda c=c: self._encode_head(sx[c * nc:(c + 1) * nc],
+                                                                           y1.batch_slice(c * nc, (c + 1) * nc)))
+                    heads.append(g)
+                    launches += l
+
+                def tail():
+                    sh.zero_()
+                    return self._encode_tail(y1, sh)
+
+                gt, _, codes, l = self._graph(key + ("tail",), list, tail)
+                pipe = self._pipes[key] = dict(sx=sx, sh=sh, y1=y1, heads=heads, tail=gt, codes=codes,
+                                               launches=launches + l,
+                                               events=[torch.cuda.Event() for _ in range(ch)])
+            main, copy = self._streams(dev)
+            copy.wait_stream(main)          # the previous step's graphs may still read the staging buffer
+            with torch.cuda.stream(copy):
+                for c in range(ch):
+                    pipe["sx"][c * nc:(c + 1) * nc].copy_(x[c * nc:(c + 1) * nc], non_blocking=True)
+                    pipe["events"][c].record(copy)
+            for c in range(ch):
+                main.wait_event(pipe["events"][c])
+                pipe["heads"][c].replay()
+            pipe["tail"].replay()
+            self.graph_launches += pipe["launches"]
+            if hist is not None:
+                hist += pipe["sh"]
+            return [c.clone() for c in pipe["codes"]]
+
+    def _decode_pipelined(self, codes: List[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+        """out: pinned host batch.  The pixels of chunk c travel to the host while chunk c+1 runs the last layers."""
+        dev = codes[0].device
+        n = codes[0].shape[0]
+        ch, nc = self.HOST_CHUNKS, n // self.HOST_CHUNKS
+        key = ("dec", tuple(tuple(c.shape) for c in codes), tuple(out.shape), self.decode_passes, dev)
+        pipe = self._pipes.get(key)
+        with torch.cuda.device(dev):
+            if pipe is None:
+                sc = [torch.zeros_like(c) for c in codes]
+                status = torch.zeros(1, dtype=torch.int32, device=dev)
+                sout = torch.empty(tuple(out.shape), dtype=torch.float32, device=dev)
+
+                def main_body():
+                    status.zero_()
+                    return self._decode_main(sc, status)
+
+                gm, _, y4, launches = self._graph(key + ("main",), list, main_body)
+                if (y4.n, 2 * y4.h, 2 * y4.w) != (out.shape[0], out.shape[2], out.shape[3]) or out.shape[1] != 3:
+                    raise RuntimeError(f"`out` must be [n, 3, H_pad, W_pad] = [{y4.n}, 3, {2 * y4.h}, {2 * y4.w}]")
+                tails = []
+                for c in range(ch):
+                    g, _, _, l = self._graph(key + ("tail", c), list,
+                                             lambda c=c: self._decode_tail(y4.batch_slice(c * nc, (c + 1) * nc),
+                                                                           sout[c * nc:(c + 1) * nc]))
+                    tails.append(g)
+                    launches += l
+                pipe = self._pipes[key] = dict(sc=sc, status=status, sout=sout, main=gm, tails=tails, y4=y4,
+                                               launches=launches, events=[torch.cuda.Event() for _ in range(ch)])
+            main, copy = self._streams(dev)
+            for dst, src in zip(pipe["sc"], codes):
+                dst.copy_(src)
+            pipe["main"].replay()
+            for c in range(ch):
+                pipe["tails"][c].replay()
+                pipe["events"][c].record(main)
+                with torch.cuda.stream(copy):
+                    copy.wait_event(pipe["events"][c])
+                    out[c * nc:(c + 1) * nc].copy_(pipe["sout"][c * nc:(c + 1) * nc], non_blocking=True)
+            main.wait_stream(copy)
+            self.graph_launches += pipe["launches"]
+            if int(pipe["status"].item()) != 0:      # also the synchronisation point: `out` is complete on return
+                raise RuntimeError("code index out of range for its codebook")
+        return out
+
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
     def encode(self, x: torch.Tensor, hist: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
-        """compressor.py:79-88.  `hist`: optional flat int32 [sum_l m*k_l] code histogram, accumulated in place."""
+        """compressor.py:79-88.  `hist`: optional flat int32 [sum_l m*k_l] code histogram, accumulated in place.
+        x may also be a pinned fp32 host batch: it is then streamed to the GPU in chunks that overlap the first layers
+        (codes are returned on the model's device)."""
         self._check_image(x)
+        if not x.is_cuda and self._host_batch_ok(x):
+            return self._encode_pipelined(x, hist)
         if not (self.use_graphs and x.is_cuda):
             return self._encode_eager(x, hist)
         x = x.contiguous().float()
@@ -151,11 +306,21 @@ class BaseCompressor(nn.Module):
         return [c.clone() for c in codes]
 
     @torch.no_grad()
-    def decode(self, codes: List[torch.Tensor]) -> torch.Tensor:
-        """compressor.py:114-117 (no crop; `decompress` crops upstream)."""
+    def decode(self, codes: List[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """compressor.py:114-117 (no crop; `decompress` crops upstream).
+        out (extension): a pinned fp32 host tensor [n, 3, H_pad, W_pad]; the pixels are then streamed into it in chunks
+        that overlap the last layers, and `out` is returned (complete when the call returns)."""
         if len(codes) == 0:
             raise RuntimeError("Length of codes is 0.")
         dev = codes[0].device
+        if out is not None:
+            ok = all(c.is_cuda and c.dtype == torch.int64 and c.dim() == 4 and c.is_contiguous() for c in codes)
+            if not (ok and self._host_batch_ok(out) and out.shape[0] == codes[0].shape[0]):
+                raise RuntimeError("decode(out=): needs CUDA int64 codes and a pinned contiguous fp32 host tensor "
+                                   f"[n, 3, H, W] with n a multiple of {self.HOST_CHUNKS} (>= {4 * self.HOST_CHUNKS})")
+            if len(codes) != len(self._quantizer._k):
+                raise RuntimeError(f"expected {len(self._quantizer._k)} code levels, got {len(codes)}")
+            return self._decode_pipelined(codes, out)
         if not (self.use_graphs and codes[0].is_cuda):
             status = torch.zeros(1, dtype=torch.int32, device=dev)
             out = self._decode_eager(codes, status)

@@ -134,3 +134,35 @@ def test_benchmark_size_properties():
     assert flips == 0 or (flips <= 2 and max(at) < 2e-6), (flips, at)
     if flips == 0:
         assert float((xhat[:2].cpu() - O.decode(sd, ref)).abs().max()) <= PIXEL_TOL
+
+
+@pytest.mark.parametrize("hw", [(128, 128), (100, 72)])
+def test_host_pipeline_matches_device_path(hw):
+    """encode(pinned host batch) / decode(out=pinned host tensor): the chunked copy/compute pipeline (first and last
+    full-resolution layers run per batch slice while PCIe moves the next / previous slice) must give the very same codes
+    and pixels as the device-resident path, every step (replays reuse the staging buffers)."""
+    cfg = dict(channel=128, m=1, k=[8192, 2048, 512])
+    sd = synthetic_state_dict(cfg["channel"], cfg["m"], cfg["k"], seed=0)
+    model = _model(cfg, sd)
+    n = 16
+    total = sum(cfg["m"] * k for k in cfg["k"])
+    for step in range(3):
+        x = uniform((n, 3) + hw, f"pipe.image.{step}", 0)
+        xh = x.pin_memory()
+        hist_d = torch.zeros(total, dtype=torch.int32, device="cuda")
+        hist_h = torch.zeros(total, dtype=torch.int32, device="cuda")
+        ref_codes = model.encode(x.cuda(), hist=hist_d)
+        codes = model.encode(xh, hist=hist_h)
+        assert all(c.is_cuda for c in codes)
+        assert all(torch.equal(a, b) for a, b in zip(codes, ref_codes))
+        assert torch.equal(hist_d, hist_h)
+        ref_x = model.decode(ref_codes)
+        out = torch.empty(tuple(ref_x.shape), dtype=torch.float32).pin_memory()
+        got = model.decode(codes, out=out)
+        assert got is out
+        assert torch.equal(out, ref_x.cpu())
+    assert model.engine.lib.mcq_device_error_flag() == 0
+    with pytest.raises(RuntimeError):
+        model.decode(codes, out=torch.empty(tuple(ref_x.shape)))           # not pinned
+    with pytest.raises(RuntimeError):
+        model.encode(uniform((2, 3) + hw, "pipe.unpinned", 0))             # plain CPU tensor: no CPU fallback

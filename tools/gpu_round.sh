@@ -12,6 +12,7 @@ cat $o/bench_n1.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $o/bench_ref.json 2> $o/bench_ref.err
 cat $o/bench_ref.json
 timeout 200 python tools/prof_vq.py > $o/vq_timing.json 2> $o/vq_timing.err
+timeout 100 python tools/probe_write_bw.py > $o/write_bw.json 2>&1; cat $o/write_bw.json
 cat $o/vq_timing.json
 if [ "$2" != "noncu" ]; then
 MCQ_CUDA_PROFILER_RANGE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
