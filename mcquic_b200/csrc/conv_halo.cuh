@@ -34,6 +34,8 @@ struct HaloArgs {
   int base_mode;    // 0: descriptor base_offset = 0; 1: base_offset = (start >> 7) & 7
   int tiles_m;      // pixel tiles (n * tiles_y * tiles_x)
   int groups_m;     // ceil(tiles_m / CL)
+  int resident;     // pair kernel, 1-pass: the whole weight matrix of the N tile stays in shared memory (nbs = all stages)
+  int per_ct;       // resident mode with several N tiles: clusters per N tile (cluster c serves N tile c % tiles_c only)
 };
 
 __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1,
@@ -303,6 +305,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       auto pix = tile_pix(w, ct);
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+      prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
       mbar_wait(tfull_bar(buf), use & 1u, 16);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);

@@ -10,6 +10,11 @@
 //            D[:, N:2N]  += A_lo * B_hi            rows [64r, 64r+64) of B_hi again in CTA r     14 KB / 192 clk / SM
 //            (accumulator columns [0,N) = hi*hi, [N,2N) = hi*lo + lo*hi, same layout as the single-CTA kernels)
 //
+// Weight-stationary mode (hp.resident, 1-pass with a single N tile): half of B_hi for ALL taps and chunks is 144 KB per
+// CTA and fits next to two halo buffers, so it is loaded once per launch instead of once per pixel tile.  That removes
+// 295 KB of shared-memory writes per tile -- with the operand fetch of the MMA already at 96 B/clk of the 128 B/clk port,
+// the weight refills were what kept the 1-pass layers at ~55 % of the tensor peak.
+//
 // Synchronisation (per stage, barriers at identical offsets in both CTAs):
 //   * every CTA's TMA producer loads its own operands but signals the LEADER's (rank 0) full barrier
 //     (cp.async.bulk.tensor ... .cta_group::2 with the barrier address mapped into CTA 0); only the leader arms
@@ -149,6 +154,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const int total_work = hp.groups_m * p.tiles_c;        // one work item = 2 neighbouring pixel tiles x one N tile
   const int cluster_id = blockIdx.x / 2, num_clusters = gridDim.x / 2;
   const int spc = 9 / hp.tps;                            // weight stages per 64-channel chunk
+  // work items of this cluster.  Default: round-robin over all (N tile, pixel-tile pair) items.  Weight-stationary mode
+  // with several N tiles: cluster c keeps N tile c % tiles_c resident and walks that tile's pixel groups only.
+  const int per_ct = hp.per_ct;
+  const int my_ct = per_ct ? cluster_id % p.tiles_c : 0, my_lane = per_ct ? cluster_id / p.tiles_c : 0;
+  const int my_work = per_ct ? (hp.groups_m - my_lane + per_ct - 1) / per_ct
+                             : (total_work - cluster_id + num_clusters - 1) / num_clusters;
+  auto work_item = [&](int i) {
+    return per_ct ? my_ct * hp.groups_m + my_lane + i * per_ct : cluster_id + i * num_clusters;
+  };
 
   auto decode_tile = [&](int w, int& ct, int& x0, int& y0, int& n) {
     ct = w / hp.groups_m;
@@ -166,14 +180,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer (one elected lane per CTA; completion lands on the leader's barriers) =====
     {
-      const int my_work = (total_work - cluster_id + num_clusters - 1) / num_clusters;
       const int total_chunks = my_work * kchunks;
       const int t_star = nbs < spc - 1 ? nbs : spc - 1;
       int a_issue = 0, ab = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       auto issue_a = [&]() {
         if (a_issue >= total_chunks) return;
-        const int wi = cluster_id + (a_issue / kchunks) * num_clusters, kc = a_issue % kchunks;
+        const int wi = work_item(a_issue / kchunks), kc = a_issue % kchunks;
         int ct, x0, y0, n;
         decode_tile(wi, ct, x0, y0, n);
         mbar_wait(a_empty(ab), aph ^ 1u, 21);
@@ -189,15 +202,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         ++a_issue;
       };
       for (int i = 0; i < na - 1; ++i) issue_a();
-      for (int w = cluster_id; w < total_work; w += num_clusters) {
+      bool load_b = true;
+      for (int wi_ = 0; wi_ < my_work; ++wi_) {
+        const int w = work_item(wi_);
         int ct, x0, y0, n;
         decode_tile(w, ct, x0, y0, n);
         const int row_half = ct * bn + (int)crank * (bn / 2);
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int sg = 0; sg < spc; ++sg) {
-            mbar_wait(b_empty(bs), bph ^ 1u, 22);
+            if (!hp.resident) mbar_wait(b_empty(bs), bph ^ 1u, 22);
             const uint32_t lbar = map_to_cta(b_full(bs), 0);
-            if (elect_one()) {
+            if (load_b && elect_one()) {
               if (leader) mbar_expect_tx(b_full(bs), 2u * b_stage_bytes);
               for (int tt = 0; tt < hp.tps; ++tt) {
                 const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
@@ -215,6 +230,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             if (sg == t_star) issue_a();
           }
         }
+        if (hp.resident) load_b = false;   // every later work item reuses the weights already in shared memory
       }
     }
   } else if (warp == 1) {
@@ -229,7 +245,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       for (int t = 0; t < 9; ++t) tap_off16[t] = (uint32_t)((t / 3) * hp.pitch + (t % 3)) * 8u;
       int ab = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
-      for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
+      for (; it < my_work; ++it) {
         const int buf = (nbuf == 2) ? (it & 1) : 0;
         const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
         mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u, 23);
@@ -242,7 +258,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const uint64_t a_hi0 = make_sdesc_halo(a_base + a_buf_bytes * ab, sbo, 0);
           const uint64_t a_lo0 = a_hi0 + (uint64_t)(hp.a_bytes >> 4);
           for (int sg = 0; sg < spc; ++sg) {
-            mbar_wait(b_full(bs), bph, 25);
+            if (!hp.resident || it == 0) mbar_wait(b_full(bs), bph, 25);
             tc_fence_after();
             const uint64_t b0 = make_sdesc(b_base + b_stage_bytes * bs);
             if (elect_one()) {
@@ -263,7 +279,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 acc_i = 1u;
               }
             }
-            umma2_commit_mc(b_empty(bs), 3);
+            if (!hp.resident) umma2_commit_mc(b_empty(bs), 3);
             if (sg == spc - 1) umma2_commit_mc(a_empty(ab), 3);
             }
             __syncwarp();
@@ -281,8 +297,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     const uint32_t stage = epi_base + (uint32_t)(warp - 2) * TC_EPI_STAGE_BYTES;
-    int it = 0;
-    for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
+    for (int it = 0; it < my_work; ++it) {
+      const int w = work_item(it);
       int ct, x0, y0, n0;
       decode_tile(w, ct, x0, y0, n0);
       auto pix = [&](int row, int& n, int& oy, int& ox) {
@@ -293,6 +309,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       };
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+      prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
       mbar_wait(tfull_bar(buf), use & 1u, 26);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);

@@ -275,6 +275,30 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
   }
 }
 
+// The fp32 operands of the fused epilogue (residuals, GDN/gate operand) were written two or more launches ago and
+// have left L2 at batch 64.  A drain warp reads them 32 B per lane with the loads right in front of their use, so one
+// SM has ~16 KB in flight against ~1 us of DRAM latency: 16 GB/s per SM, a third of its HBM share.  Requesting the
+// warp's 32 rows x 128 B into L2 before it blocks on the accumulator turns those loads into L2 hits.
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+template <class PixFn>
+__device__ __forceinline__ void prefetch_epilogue_operands(const ConvArgs& p, int bn, int ct, int cg, int q, int lane,
+                                                           PixFn pix) {
+  if (p.store != MCQ_STORE_NHWC || p.mode == EPI_ARGMIN) return;
+  if (!p.res1 && !p.res2 && !p.aux) return;
+  int n, oy, ox;
+  if (!pix(q * 32 + lane, n, oy, ox)) return;
+  const size_t pixoff = (((size_t)n * p.hout + oy) * p.wout + ox) * p.cout;
+  for (int cc = cg * 32; cc < bn; cc += 128) {
+    const int c = ct * bn + cc;
+    if (c >= p.cout) break;
+    if (p.res1) prefetch_l2(p.res1 + pixoff + c);
+    if (p.res2) prefetch_l2(p.res2 + pixoff + c);
+    if (p.aux) prefetch_l2(p.aux + pixoff + c);
+  }
+}
+
 // ---------------------------------------------------------------- kernel
 template <int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -463,6 +487,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       auto pix = tile_pix(t, ct);
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+      prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
       mbar_wait(tfull_bar(buf), use & 1u, 4);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);

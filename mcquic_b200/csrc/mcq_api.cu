@@ -228,7 +228,8 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   // small feature maps: narrow the N tile so that the few pixel tiles still spread over the SMs
   // (these layers are latency-bound; re-reading A per N tile is free compared with idle SMs)
   const int tiles_m = a.tiles_x * a.tiles_y * a.tiles_n;
-  while (tiles_m * (a.cout_pad / bn) < (num_sms() * 2) / 3 && bn >= 32 && (bn / 2) % 16 == 0) bn /= 2;
+  static const int spread_pct = env_int("MCQ_TC_SPREAD", 33);
+  while (tiles_m * (a.cout_pad / bn) < num_sms() * spread_pct / 100 && bn >= 32 && (bn / 2) % 16 == 0) bn /= 2;
   a.bn = bn;
   a.tiles_c = a.cout_pad / bn;
   fill_taps(a);
@@ -395,7 +396,10 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
   }
   const int work = hp.groups_m * a.tiles_c;
   int clusters = num_sms() / cl;
-  if (work < clusters) clusters = work;
+  if (work < clusters) {
+    static const int small_pct = env_int("MCQ_SMALL_GRID_PCT", 100);
+    clusters = work < clusters * small_pct / 100 ? work : clusters * small_pct / 100;
+  }
   const int grid = clusters * cl;
   if (a.passes == 3) {
     if (cl == 1) return launch_halo_t<3, 1>(a, hp, maps, smem, grid, st);
@@ -467,6 +471,14 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
   hp.na = (a.passes == 3) ? 2 : 3;
   int nbs = (int)((budget - a_buf * hp.na) / b_stage);
   if (nbs > 8) nbs = 8;
+  // weight-stationary mode: 1-pass, one N tile, and all (cin / 64) * (9 / tps) weight stages fit beside two halo buffers
+  const int all_stages = (a.cin / TC_BK) * (9 / hp.tps);
+  if (a.passes == 1 && a.tiles_c <= num_sms() / 2 && all_stages <= 8 && a_buf * 2 + b_stage * all_stages <= budget &&
+      env_int("MCQ_PAIR_RESIDENT", 1)) {
+    hp.resident = 1;
+    hp.na = 2;
+    nbs = all_stages;
+  }
   if (nbs < 2) return MCQ_ERR_UNSUPPORTED;
   hp.nbs = nbs;
   const size_t smem = a_buf * hp.na + b_stage * nbs + 8 * (2 * hp.na + 2 * nbs + 4) + 16 + 1024 + epi_bytes;
@@ -502,7 +514,18 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
   }
   const int work = hp.groups_m * a.tiles_c;
   int clusters = num_sms() / 2;
-  if (work < clusters) clusters = work;
+  if (work < clusters) {
+    // small layer (<= one work item per cluster): experiment knob -- leave SMs to the sibling branch's launch
+    static const int small_pct = env_int("MCQ_SMALL_GRID_PCT", 100);
+    clusters = work < clusters * small_pct / 100 ? work : clusters * small_pct / 100;
+  }
+  if (hp.resident && a.tiles_c > 1) {
+    // several N tiles: a cluster keeps ONE of them resident, so the clusters are divided evenly among the N tiles
+    hp.per_ct = clusters / a.tiles_c;
+    if (hp.per_ct > hp.groups_m) hp.per_ct = hp.groups_m;
+    if (hp.per_ct < 1) return MCQ_ERR_UNSUPPORTED;
+    clusters = hp.per_ct * a.tiles_c;
+  }
   const int grid = clusters * 2;
   if (a.passes == 3) return launch_pair_t<3>(a, hp, maps, smem, grid, st);
   return launch_pair_t<1>(a, hp, maps, smem, grid, st);
@@ -630,7 +653,10 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
   else {
     rc = MCQ_ERR_UNSUPPORTED;
     // CTA pairs (cta_group::2) pay off where the tensor pipe is the limiter (3-pass); the 1-pass path is epilogue-bound
-    if (halo_supported(a) && env_int("MCQ_PAIR", a.passes == 3 ? 1 : 0)) rc = launch_pair(a, st);
+    // (streaming weights); with a single 128-column N tile the weights stay resident in the pair's shared memory instead
+    const bool pair_resident = a.passes == 1 && a.cout_pad % 128 == 0 && a.cout_pad <= 512 && a.cin == 128 &&
+                               env_int("MCQ_PAIR_RESIDENT", 1);
+    if (halo_supported(a) && env_int("MCQ_PAIR", (a.passes == 3 || pair_resident) ? 1 : 0)) rc = launch_pair(a, st);
     if (rc == MCQ_ERR_UNSUPPORTED && halo_supported(a) && env_int("MCQ_HALO", 1)) rc = launch_halo(a, st);
     if (rc == MCQ_ERR_UNSUPPORTED) rc = launch_tc(a, st);
   }

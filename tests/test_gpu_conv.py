@@ -67,6 +67,17 @@ def test_epilogue_modes(impl):
     _check(impl, n=2, h=32, w=32, cin=128, cout=12, store=_lib.STORE_SHUFFLE_NCHW, passes=1)
 
 
+def test_weight_stationary_pair_kernel():
+    """1-pass 3x3 convs with cin = 128 run on the CTA-pair kernel with the weights resident in shared memory
+    (conv_pair.cuh): many pixel tiles per cluster (the weights are loaded for the first one only), ragged maps, and the
+    512-column PixelShuffle convs where every cluster serves one of the four N tiles."""
+    _check("tcgen05", passes=1, want=("f32", "silu"), use_res1=True, n=24, h=64, w=64, cin=128, cout=128)
+    _check("tcgen05", passes=1, want=("silu",), n=3, h=40, w=24, cin=128, cout=128)
+    _check("tcgen05", passes=1, want=("f32", "sq"), n=20, h=32, w=32, cin=128, cout=512, store=_lib.STORE_SHUFFLE_NHWC)
+    _check("tcgen05", passes=1, want=("f32",), n=1, h=16, w=16, cin=128, cout=512, store=_lib.STORE_SHUFFLE_NHWC)
+    _check("tcgen05", passes=1, want=("raw",), n=2, h=16, w=24, cin=128, cout=256)
+
+
 def test_simt_serves_channel_counts_the_tensor_core_tiling_does_not():
     _check("simt", n=1, h=9, w=7, cin=32, cout=40)
     _check("simt", n=2, h=16, w=24, cin=64, cout=64, stride=2)
