@@ -61,15 +61,33 @@ __device__ __forceinline__ float rcp_approx(float d) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
   return r;
 }
-template <bool FAST>
-__device__ __forceinline__ float sigmoid_f(float x) {
-  const float d = 1.0f + __expf(fminf(-x, 80.0f));   // clamp keeps d finite (inf * 0 in the Newton step would be NaN)
-  float r = rcp_approx(d);
-  if constexpr (!FAST) r = r * fmaf(-d, r, 2.0f);
+__device__ __forceinline__ float tanh_approx(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// FAST (1-pass path, whose operands are rounded to fp16 anyway): one SFU op, sigmoid(x) = 0.5 + 0.5 tanh(x / 2) with
+// tanh.approx's 2^-11 relative error -- 3 instructions instead of 6 and half the SFU traffic of the ex2 + rcp form.
 template <bool FAST>
-__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f<FAST>(x); }
+__device__ __forceinline__ float sigmoid_f(float x) {
+  if constexpr (FAST) {
+    return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f);
+  } else {
+    const float d = 1.0f + __expf(fminf(-x, 80.0f));   // clamp keeps d finite (inf * 0 in the Newton step would be NaN)
+    float r = rcp_approx(d);
+    r = r * fmaf(-d, r, 2.0f);
+    return r;
+  }
+}
+template <bool FAST>
+__device__ __forceinline__ float silu_f(float x) {
+  if constexpr (FAST) {
+    const float h = 0.5f * x;
+    return fmaf(h, tanh_approx(h), h);                   // x sigmoid(x) = h + h tanh(h)
+  } else {
+    return x * sigmoid_f<false>(x);
+  }
+}
 
 template <bool FAST>
 __device__ __forceinline__ float apply_act(float y, int act) {
@@ -103,26 +121,46 @@ __device__ __forceinline__ void split_f32x2(float e0, float e1, uint32_t& hi, ui
   lo = f2h2_sat((e0 - back.x) * kLoScale, (e1 - back.y) * kLoScale);
 }
 
+// The activation selector is launch-uniform: branch on it ONCE per group of NV values, not per element (the per-element
+// form cost two compare+branch pairs per value and plane -- a third of all instructions the drain warps executed).
+template <int NV, bool FAST>
+__device__ __forceinline__ void act_group(const float (&y)[NV], float (&t)[NV], int act) {
+  if (act == MCQ_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) t[j] = silu_f<FAST>(y[j]);
+  } else if (act == MCQ_ACT_SQUARE) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) t[j] = y[j] * y[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) t[j] = y[j];
+  }
+}
+
 template <int NV, bool FAST = false>
 __device__ __forceinline__ void store_planes(__half* hi_p, __half* lo_p, size_t off, const float (&y)[NV], int act) {
   static_assert(NV == 4 || NV == 8, "NV");
   uint32_t h[NV / 2], l[NV / 2];
   float t[NV];
-#pragma unroll
-  for (int j = 0; j < NV; ++j) t[j] = apply_act<FAST>(y[j], act);
+  act_group<NV, FAST>(y, t, act);
   if (lo_p) {
 #pragma unroll
     for (int j = 0; j < NV / 2; ++j) split_f32x2(t[2 * j], t[2 * j + 1], h[j], l[j]);
+    if constexpr (NV == 8) {
+      *reinterpret_cast<uint4*>(hi_p + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    } else {
+      *reinterpret_cast<uint2*>(hi_p + off) = make_uint2(h[0], h[1]);
+      *reinterpret_cast<uint2*>(lo_p + off) = make_uint2(l[0], l[1]);
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < NV / 2; ++j) h[j] = f2h2_sat(t[2 * j], t[2 * j + 1]);
-  }
-  if constexpr (NV == 8) {
-    *reinterpret_cast<uint4*>(hi_p + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    if (lo_p) *reinterpret_cast<uint4*>(lo_p + off) = make_uint4(l[0], l[1], l[2], l[3]);
-  } else {
-    *reinterpret_cast<uint2*>(hi_p + off) = make_uint2(h[0], h[1]);
-    if (lo_p) *reinterpret_cast<uint2*>(lo_p + off) = make_uint2(l[0], l[1]);
+    if constexpr (NV == 8) {
+      *reinterpret_cast<uint4*>(hi_p + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    } else {
+      *reinterpret_cast<uint2*>(hi_p + off) = make_uint2(h[0], h[1]);
+    }
   }
 }
 
@@ -136,12 +174,13 @@ __device__ __forceinline__ void load_f32v(const float* p, size_t off, float (&r)
 }
 
 // Fused epilogue for NV consecutive GEMM columns [c0, c0+NV) of output pixel (n, oy, ox).
-// v[] = accumulator * w_scale (bias NOT yet added).  c0 % NV == 0.
+// v[] * scale = accumulator * w_scale (bias NOT yet added; scale is a power of two, so folding it into the bias FFMA
+// rounds exactly like multiplying first).  c0 % NV == 0.
 // bias_src: where to read the bias from (the tensor-core kernels keep a copy in shared memory: with the whole
 // carve-out given to smem there is no L1, and a global bias fetch per call is a ~300-cycle stall)
 template <int NV, bool FAST = false>
 __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy, int ox, int c0, float (&v)[NV],
-                                               const float* bias_src = nullptr) {
+                                               const float* bias_src = nullptr, float scale = 1.0f) {
   if (c0 >= p.cout) return;
   if (bias_src == nullptr) bias_src = p.bias;
   if (p.store == MCQ_STORE_SHUFFLE_NCHW) {
@@ -152,7 +191,7 @@ __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy,
       const int col = c0 + j;
       if (col < p.cout) {
         const int c = col >> 2, i = (col >> 1) & 1, jj = col & 1;
-        p.out_f32[(((size_t)n * cq + c) * H2 + (2 * oy + i)) * W2 + (2 * ox + jj)] = v[j] + bias_src[col];
+        p.out_f32[(((size_t)n * cq + c) * H2 + (2 * oy + i)) * W2 + (2 * ox + jj)] = fmaf(v[j], scale, bias_src[col]);
       }
     }
     return;
@@ -170,7 +209,7 @@ __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy,
   float b[NV], y[NV];
   load_f32v<NV>(bias_src, c0, b);
 #pragma unroll
-  for (int j = 0; j < NV; ++j) y[j] = v[j] + b[j];
+  for (int j = 0; j < NV; ++j) y[j] = fmaf(v[j], scale, b[j]);
   if (p.mode == MCQ_EPI_LINEAR) {
     if (p.res1) {
       float r[NV];
@@ -193,14 +232,17 @@ __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy,
   } else {
     float a[NV];
     load_f32v<NV>(p.aux, off, a);
+    if (p.mode == MCQ_EPI_GDN) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      if constexpr (FAST) {
-        const float rs = rsqrtf(y[j]);
-        y[j] = (p.mode == MCQ_EPI_GDN) ? a[j] * rs : a[j] * (y[j] * rs);
-      } else {
-        const float s = sqrtf(y[j]);
-        y[j] = (p.mode == MCQ_EPI_GDN) ? a[j] * (1.0f / s) : a[j] * s;
+      for (int j = 0; j < NV; ++j) {
+        if constexpr (FAST) y[j] = a[j] * rsqrtf(y[j]);
+        else y[j] = a[j] * (1.0f / sqrtf(y[j]));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if constexpr (FAST) y[j] = a[j] * (y[j] * rsqrtf(y[j]));
+        else y[j] = a[j] * sqrtf(y[j]);
       }
     }
   }

@@ -238,11 +238,11 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
         tmem_ld16(t_acc + (uint32_t)(bn + col0), l);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(l[j]), kLoInv, __uint_as_float(r[j])) * p.w_scale;
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(l[j]), kLoInv, __uint_as_float(r[j]));
       } else {
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * p.w_scale;
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);   // w_scale is applied with the bias (one FFMA)
       }
       // row-per-lane -> smem (64 B per row; 16 B chunk c stored at c ^ ((row >> 1) & 3))
       const uint32_t wbase = stage + (uint32_t)lane * 64u;
@@ -268,7 +268,7 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
                        : "memory");
         }
         if (ok_[it] && !p.debug_skip_store)
-          epilogue_store<8, PASSES == 1>(p, n_[it], oy_[it], ox_[it], ct * bn + col0 + col8, vv, bias_src);
+          epilogue_store<8, PASSES == 1>(p, n_[it], oy_[it], ox_[it], ct * bn + col0 + col8, vv, bias_src, p.w_scale);
       }
       __syncwarp();
     }
