@@ -246,10 +246,16 @@ class Engine:
 
     def _packed_for(self, mod: nn.Module, store: int = _lib.STORE_NHWC) -> PackedConv:
         key = (id(mod), store)
+        def version(t):          # tensors created under torch.inference_mode() (the reference CLI runs that way,
+            try:                 # mcquic/cli.py:60) have no version counter: they are immutable, so 0 is exact
+                return t._version
+            except RuntimeError:
+                return 0
+
         if isinstance(mod, GenDivNorm):
-            ver = (mod.beta._version, mod.gamma._version, mod.beta.data_ptr(), mod.gamma.data_ptr())
+            ver = (version(mod.beta), version(mod.gamma), mod.beta.data_ptr(), mod.gamma.data_ptr())
         else:
-            ver = (mod.weight._version, mod.bias._version, mod.weight.data_ptr(), mod.bias.data_ptr())
+            ver = (version(mod.weight), version(mod.bias), mod.weight.data_ptr(), mod.bias.data_ptr())
         hit = self._packed.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]

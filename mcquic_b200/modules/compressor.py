@@ -352,7 +352,8 @@ class BaseCompressor(nn.Module):
     def compress(self, x: torch.Tensor):
         """compressor.py:67-77: (codes, binaries [n][L] bytes, n FileHeader records).  encode on the GPU, rANS on the
         host (one batched multi-threaded call per level)."""
-        from .. import __version__, entropy
+        from .. import entropy
+        from ..container import REFERENCE_VERSION as __version__   # header version = the reference release we interoperate with
         n, c, h, w = x.shape
         codes = self.encode(x)
         binaries, sizes = self._quantizer._entropyCoder.compress(codes)

@@ -40,7 +40,12 @@ class CodeFrequency(nn.Module):
     @property
     def CDFs(self):
         """per level uint32 [m, k_l + 1], quantized to 16 bits (entropyCoder.py:50-63)."""
-        ver = tuple(f._version for f in self._freqEMA)
+        def version(t):
+            try:
+                return t._version
+            except RuntimeError:      # inference tensor: immutable
+                return 0
+        ver = tuple((version(f), f.data_ptr()) for f in self._freqEMA)
         if self._cdfs is None or self._cdfs[0] != ver:
             from .. import entropy
             import numpy as np
@@ -111,7 +116,11 @@ class _multiCodebookQuantization(nn.Module):
     def _tables(self):
         """Per codebook version: fp32 codebook, |c_k|^2 [m, k] (quantizer.py:165) and the split-fp16 packing the
         tensor-core kernel consumes."""
-        ver = (self._codebook._version, self._codebook.data_ptr())
+        try:
+            cbv = self._codebook._version
+        except RuntimeError:          # inference tensor (model built under torch.inference_mode()): immutable
+            cbv = 0
+        ver = (cbv, self._codebook.data_ptr())
         if self._c2_cache is None or self._c2_cache[0] != ver:
             from ..engine import pack_codebook
             with torch.no_grad():
