@@ -27,13 +27,19 @@ def is_stale():
 def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
+    # compile to a private name and rename: several ranks of one torchrun job may find the library stale at once, and a
+    # reader must never see a half-written .so
+    tmp = f"{LIB}.{os.getpid()}.tmp"
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + SOURCES + os.environ.get("MCQ_NVCC_FLAGS", "").split()
+           "-shared", "-Xcompiler", "-fPIC", "-o", tmp] + SOURCES + os.environ.get("MCQ_NVCC_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB)
     if verbose:
         print(res.stdout + res.stderr)
     return LIB

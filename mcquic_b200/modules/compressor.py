@@ -38,7 +38,7 @@ class BaseCompressor(nn.Module):
         self.use_graphs = True
         self._graphs = {}
         self.graph_launches = 0  # kernels launched through graph replays (the library counts eager launches)
-        # host I/O pipeline: a pinned host batch is processed in HOST_CHUNKS slices through the first (encode) / last
+        # host I/O pipeline: a pinned host batch is processed in up to 4 slices through the first (encode) / last
         # (decode) full-resolution layers so that the PCIe copies overlap the convolutions
         self._pipes = {}
         self._copy_stream = None
@@ -76,7 +76,14 @@ class BaseCompressor(nn.Module):
             raise RuntimeError("mcquic_b200 runs on CUDA tensors (or pinned fp32 host batches a CUDA-resident model "
                                "streams in); there is no CPU fallback")
 
-    HOST_CHUNKS = 4
+    @staticmethod
+    def host_chunks(n: int) -> int:
+        """Slices a host batch of n images is streamed in: at most 4 (measured: with 8 the extra dependent launches of
+        the per-slice layers cost what the shorter exposed copy saves), at least 8 images per slice."""
+        for ch in (4, 2):
+            if n % ch == 0 and n // ch >= 8:
+                return ch
+        return 1
 
     def _device(self) -> torch.device:
         return self._encoder[0].weight.device
@@ -85,7 +92,6 @@ class BaseCompressor(nn.Module):
         """A pinned, contiguous fp32 host batch that the chunked copy/compute pipeline can stream."""
         return (not t.is_cuda and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4
                 and self.use_graphs and not self.engine.emulated and self._device().type == "cuda"
-                and t.shape[0] % self.HOST_CHUNKS == 0 and t.shape[0] // self.HOST_CHUNKS >= 4
                 and isinstance(self._encoder[1], ResidualBlock) and isinstance(self._decoder[5], ResidualBlock))
 
     def invalidate(self):
@@ -187,7 +193,8 @@ class BaseCompressor(nn.Module):
         """x: pinned host batch.  Chunk c is copied on the copy stream while chunk c-1 runs stem + first block."""
         dev = self._device()
         n, _, h, w = x.shape
-        ch, nc = self.HOST_CHUNKS, n // self.HOST_CHUNKS
+        ch = self.host_chunks(n)
+        nc = n // ch
         key = ("enc", tuple(x.shape), self.encode_passes, dev)
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
@@ -235,7 +242,8 @@ class BaseCompressor(nn.Module):
         """out: pinned host batch.  The pixels of chunk c travel to the host while chunk c+1 runs the last layers."""
         dev = codes[0].device
         n = codes[0].shape[0]
-        ch, nc = self.HOST_CHUNKS, n // self.HOST_CHUNKS
+        ch = self.host_chunks(n)
+        nc = n // ch
         key = ("dec", tuple(tuple(c.shape) for c in codes), tuple(out.shape), self.decode_passes, dev)
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
@@ -317,7 +325,7 @@ class BaseCompressor(nn.Module):
             ok = all(c.is_cuda and c.dtype == torch.int64 and c.dim() == 4 and c.is_contiguous() for c in codes)
             if not (ok and self._host_batch_ok(out) and out.shape[0] == codes[0].shape[0]):
                 raise RuntimeError("decode(out=): needs CUDA int64 codes and a pinned contiguous fp32 host tensor "
-                                   f"[n, 3, H, W] with n a multiple of {self.HOST_CHUNKS} (>= {4 * self.HOST_CHUNKS})")
+                                   "[n, 3, H_pad, W_pad]")
             if len(codes) != len(self._quantizer._k):
                 raise RuntimeError(f"expected {len(self._quantizer._k)} code levels, got {len(codes)}")
             return self._decode_pipelined(codes, out)

@@ -136,15 +136,15 @@ def test_benchmark_size_properties():
         assert float((xhat[:2].cpu() - O.decode(sd, ref)).abs().max()) <= PIXEL_TOL
 
 
-@pytest.mark.parametrize("hw", [(128, 128), (100, 72)])
-def test_host_pipeline_matches_device_path(hw):
+@pytest.mark.parametrize("hw,n", [((128, 128), 16), ((100, 72), 6), ((64, 128), 32)])
+def test_host_pipeline_matches_device_path(hw, n):
     """encode(pinned host batch) / decode(out=pinned host tensor): the chunked copy/compute pipeline (first and last
     full-resolution layers run per batch slice while PCIe moves the next / previous slice) must give the very same codes
     and pixels as the device-resident path, every step (replays reuse the staging buffers)."""
     cfg = dict(channel=128, m=1, k=[8192, 2048, 512])
     sd = synthetic_state_dict(cfg["channel"], cfg["m"], cfg["k"], seed=0)
     model = _model(cfg, sd)
-    n = 16
+    assert [model.host_chunks(v) for v in (64, 32, 16, 6, 1)] == [4, 4, 2, 1, 1]
     total = sum(cfg["m"] * k for k in cfg["k"])
     for step in range(3):
         x = uniform((n, 3) + hw, f"pipe.image.{step}", 0)
