@@ -12,6 +12,7 @@ runs in libmcquic_b200.so (`_lib.py`).  Fusion map (reference op -> where it wen
   AlignedPadding (transforms.py:86)  -> index arithmetic of the stem kernel
 """
 import ctypes
+import os
 import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Set, Tuple
@@ -125,7 +126,7 @@ class Engine:
         # persistent layer-chain launch (mcq_conv_chain).  Measured on B200 a chained layer costs
         # as much as a stand-alone launch that overlaps a second stream, so the default stays layer-by-layer launches
         # on two streams; the emulated ABI keeps chains on so that the CPU tests cover the recording/merge logic.
-        self.chain = self.emulated
+        self.chain = self.emulated or os.environ.get("MCQ_CHAIN", "0") == "1"
         self._pending: list = []
         self._rec_depth = 0
 

@@ -77,13 +77,20 @@ class BaseCompressor(nn.Module):
                                "streams in); there is no CPU fallback")
 
     @staticmethod
-    def host_chunks(n: int) -> int:
-        """Slices a host batch of n images is streamed in: at most 4 (measured: with 8 the extra dependent launches of
-        the per-slice layers cost what the shorter exposed copy saves), at least 8 images per slice."""
-        for ch in (4, 2):
-            if n % ch == 0 and n // ch >= 8:
-                return ch
-        return 1
+    def host_slices(n: int, small_first: bool) -> List[Tuple[int, int]]:
+        """Batch slices [(n0, n1), ...] a host batch of n images is streamed in.  Up to four slices of >= 8 images keep
+        the per-slice layers efficient (measured: eight equal slices cost in extra dependent launches what the shorter
+        exposed copy saves); the slice whose PCIe copy cannot overlap anything -- the first one going in, the last one
+        coming out -- is split once more into a quarter and the rest, so only ~n/16 images' worth of copy stays exposed."""
+        ch = next((c for c in (4, 2) if n % c == 0 and n // c >= 8), 1)
+        nc = n // ch
+        bounds = [(c * nc, (c + 1) * nc) for c in range(ch)]
+        if ch > 1 and nc % 4 == 0:
+            if small_first:
+                bounds = [(0, nc // 4), (nc // 4, nc)] + bounds[1:]
+            else:
+                bounds = bounds[:-1] + [(n - nc, n - nc // 4), (n - nc // 4, n)]
+        return bounds
 
     def _device(self) -> torch.device:
         return self._encoder[0].weight.device
@@ -193,8 +200,7 @@ class BaseCompressor(nn.Module):
         """x: pinned host batch.  Chunk c is copied on the copy stream while chunk c-1 runs stem + first block."""
         dev = self._device()
         n, _, h, w = x.shape
-        ch = self.host_chunks(n)
-        nc = n // ch
+        bounds = self.host_slices(n, small_first=True)
         key = ("enc", tuple(x.shape), self.encode_passes, dev)
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
@@ -208,10 +214,9 @@ class BaseCompressor(nn.Module):
                 y1 = eng.alloc_act(n, hp // 2, wp // 2, self._encoder[0].out_channels, eng.needs_of(self._encoder[2]), dev)
                 sx.zero_()
                 heads, launches = [], 0
-                for c in range(ch):
+                for c, (n0, n1) in enumerate(bounds):
                     g, _, _, l = self._graph(key + ("head", c), list,
-                                             lambda c=c: self._encode_head(sx[c * nc:(c + 1) * nc],
-                                                                           y1.batch_slice(c * nc, (c + 1) * nc)))
+                                             lambda n0=n0, n1=n1: self._encode_head(sx[n0:n1], y1.batch_slice(n0, n1)))
                     heads.append(g)
                     launches += l
 
@@ -222,14 +227,14 @@ class BaseCompressor(nn.Module):
                 gt, _, codes, l = self._graph(key + ("tail",), list, tail)
                 pipe = self._pipes[key] = dict(sx=sx, sh=sh, y1=y1, heads=heads, tail=gt, codes=codes,
                                                launches=launches + l,
-                                               events=[torch.cuda.Event() for _ in range(ch)])
+                                               events=[torch.cuda.Event() for _ in bounds])
             main, copy = self._streams(dev)
             copy.wait_stream(main)          # the previous step's graphs may still read the staging buffer
             with torch.cuda.stream(copy):
-                for c in range(ch):
-                    pipe["sx"][c * nc:(c + 1) * nc].copy_(x[c * nc:(c + 1) * nc], non_blocking=True)
+                for c, (n0, n1) in enumerate(bounds):
+                    pipe["sx"][n0:n1].copy_(x[n0:n1], non_blocking=True)
                     pipe["events"][c].record(copy)
-            for c in range(ch):
+            for c in range(len(bounds)):
                 main.wait_event(pipe["events"][c])
                 pipe["heads"][c].replay()
             pipe["tail"].replay()
@@ -242,8 +247,7 @@ class BaseCompressor(nn.Module):
         """out: pinned host batch.  The pixels of chunk c travel to the host while chunk c+1 runs the last layers."""
         dev = codes[0].device
         n = codes[0].shape[0]
-        ch = self.host_chunks(n)
-        nc = n // ch
+        bounds = self.host_slices(n, small_first=False)
         key = ("dec", tuple(tuple(c.shape) for c in codes), tuple(out.shape), self.decode_passes, dev)
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
@@ -260,24 +264,23 @@ class BaseCompressor(nn.Module):
                 if (y4.n, 2 * y4.h, 2 * y4.w) != (out.shape[0], out.shape[2], out.shape[3]) or out.shape[1] != 3:
                     raise RuntimeError(f"`out` must be [n, 3, H_pad, W_pad] = [{y4.n}, 3, {2 * y4.h}, {2 * y4.w}]")
                 tails = []
-                for c in range(ch):
+                for c, (n0, n1) in enumerate(bounds):
                     g, _, _, l = self._graph(key + ("tail", c), list,
-                                             lambda c=c: self._decode_tail(y4.batch_slice(c * nc, (c + 1) * nc),
-                                                                           sout[c * nc:(c + 1) * nc]))
+                                             lambda n0=n0, n1=n1: self._decode_tail(y4.batch_slice(n0, n1), sout[n0:n1]))
                     tails.append(g)
                     launches += l
                 pipe = self._pipes[key] = dict(sc=sc, status=status, sout=sout, main=gm, tails=tails, y4=y4,
-                                               launches=launches, events=[torch.cuda.Event() for _ in range(ch)])
+                                               launches=launches, events=[torch.cuda.Event() for _ in bounds])
             main, copy = self._streams(dev)
             for dst, src in zip(pipe["sc"], codes):
                 dst.copy_(src)
             pipe["main"].replay()
-            for c in range(ch):
+            for c, (n0, n1) in enumerate(bounds):
                 pipe["tails"][c].replay()
                 pipe["events"][c].record(main)
                 with torch.cuda.stream(copy):
                     copy.wait_event(pipe["events"][c])
-                    out[c * nc:(c + 1) * nc].copy_(pipe["sout"][c * nc:(c + 1) * nc], non_blocking=True)
+                    out[n0:n1].copy_(pipe["sout"][n0:n1], non_blocking=True)
             main.wait_stream(copy)
             self.graph_launches += pipe["launches"]
             if int(pipe["status"].item()) != 0:      # also the synchronisation point: `out` is complete on return

@@ -144,7 +144,9 @@ def test_host_pipeline_matches_device_path(hw, n):
     cfg = dict(channel=128, m=1, k=[8192, 2048, 512])
     sd = synthetic_state_dict(cfg["channel"], cfg["m"], cfg["k"], seed=0)
     model = _model(cfg, sd)
-    assert [model.host_chunks(v) for v in (64, 32, 16, 6, 1)] == [4, 4, 2, 1, 1]
+    assert model.host_slices(64, True) == [(0, 4), (4, 16), (16, 32), (32, 48), (48, 64)]
+    assert model.host_slices(64, False) == [(0, 16), (16, 32), (32, 48), (48, 60), (60, 64)]
+    assert model.host_slices(16, True) == [(0, 2), (2, 8), (8, 16)] and model.host_slices(6, True) == [(0, 6)]
     total = sum(cfg["m"] * k for k in cfg["k"])
     for step in range(3):
         x = uniform((n, 3) + hw, f"pipe.image.{step}", 0)
