@@ -49,6 +49,7 @@ struct ConvArgs {
   unsigned long long* argmin_keys;  // EPI_ARGMIN: per-point packed (ordered distance << 32 | index) minima
   int argmin_stride;              // points are argmin_stride keys / aux entries apart (= number of codebooks)
   int debug_skip_store;           // MCQ_EPI_SKIP=1: drain TMEM but store nothing (profiling aid)
+  int direct_epilogue;            // 1 (default): transpose-free drain where it applies, see drain_tile (MCQ_DIRECT_EPI=0: off)
   // per-tap TMA coordinate offsets in the 5-D view of A (see conv_tc.cuh)
   int tap_c[9], tap_dx[9], tap_py[9], tap_dy[9];
 };
@@ -171,6 +172,21 @@ __device__ __forceinline__ void load_f32v(const float* p, size_t off, float (&r)
     float4 t = *reinterpret_cast<const float4*>(p + off + j);
     r[j] = t.x; r[j + 1] = t.y; r[j + 2] = t.z; r[j + 3] = t.w;
   }
+}
+
+// Output element offset of GEMM columns [c0, ..) of conv pixel (n, oy, ox) for the NHWC stores
+// (PixelShuffle convs: column (2i+j)*C/4 + c of pixel (oy, ox) is channel c of pixel (2oy+i, 2ox+j)).
+__device__ __forceinline__ size_t epilogue_offset(const ConvArgs& p, int n, int oy, int ox, int c0) {
+  int C = p.cout, H = p.hout, W = p.wout, py = oy, px = ox, c = c0;
+  if (p.store == MCQ_STORE_SHUFFLE_NHWC) {
+    const int cq = p.cout >> 2;
+    const int sub = c0 / cq;
+    c = c0 - sub * cq;
+    py = 2 * oy + (sub >> 1);
+    px = 2 * ox + (sub & 1);
+    H *= 2; W *= 2; C = cq;
+  }
+  return (((size_t)n * H + py) * W + px) * C + c;
 }
 
 // Fused epilogue for NV consecutive GEMM columns [c0, c0+NV) of output pixel (n, oy, ox).

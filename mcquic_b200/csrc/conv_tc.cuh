@@ -161,6 +161,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 256-bit global load / store (sm_100: LDG.E.256 / STG.E.256): one full 32 B sector per lane
+__device__ __forceinline__ void ld_global_256(const float* ptr, float* dst) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(dst[0]), "=f"(dst[1]), "=f"(dst[2]), "=f"(dst[3]), "=f"(dst[4]), "=f"(dst[5]), "=f"(dst[6]),
+                 "=f"(dst[7])
+               : "l"(ptr));
+}
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row atoms 1024 B apart.
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
@@ -223,6 +235,109 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
     if (ok && best_k != 0x7fffffff)
       atomicMin(p.argmin_keys + point * p.argmin_stride,
                 ((unsigned long long)ordered_f32(best) << 32) | (unsigned long long)(uint32_t)best_k);
+    return;
+  }
+  // ---- direct drain: no shared-memory transpose.  The lane keeps its GEMM row (= pixel) and moves 16 consecutive
+  // channels per step with 256-bit accesses: one full 32 B sector per lane and plane, two per fp32 tensor.  A quarter of
+  // the instructions of the transposed drain below (~800 per tile and warp), at the price of more L1TEX wavefronts per
+  // byte (32 lines per instruction).  Used where instructions / energy are the scarce resource: plane-only outputs (first
+  // conv of every ResidualBlock), 3-pass layers, 1x1 layers (64 B per lane in flight instead of 32 B for their HBM-bound
+  // operand reads) -- and, measured, everywhere else too.  At 64x64: 1-pass plane->plane 64 -> 60 us (mainloop alone
+  // 45), 3-pass 164 -> 157 us; whole step -2 %.
+  const bool plane_only = p.mode == MCQ_EPI_LINEAR && !p.res1 && !p.res2 && !p.out_f32 && p.o0_hi && !p.o1_hi;
+  // direct_epilogue (A/B knob MCQ_DIRECT_EPI): 1 = every NHWC / PixelShuffle-NHWC store (default; measured best also for
+  // the 1-pass layers with fp32 residual + output), 2 = plane-only outputs only, 0 = never
+  const bool direct_ok = p.direct_epilogue == 1 || (p.direct_epilogue == 2 && plane_only);
+  const bool shuffled = p.store == MCQ_STORE_SHUFFLE_NHWC;
+  if (direct_ok && ((p.store == MCQ_STORE_NHWC && p.cout % 16 == 0) || (shuffled && (p.cout >> 2) % 16 == 0))) {
+    int n, oy, ox;
+    const bool ok = pix(q * 32 + lane, n, oy, ox) && !p.debug_skip_store;
+    const size_t pixoff = (((size_t)n * p.hout + oy) * p.wout + ox) * (size_t)p.cout;
+    for (int cc = cg * 32; cc < bn; cc += 128) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int col0 = cc + half * 16;
+        if (col0 >= bn) break;
+        const int c0 = ct * bn + col0;
+        const bool live = ok && c0 < p.cout;
+        const size_t off = shuffled ? epilogue_offset(p, n, oy, ox, c0) : pixoff + c0;
+        uint32_t r[16];
+        float y[16];
+        tmem_ld16(t_acc + (uint32_t)col0, r);
+        // fp32 operands: requested before the accumulator wait
+        float o1[16], o2[16];
+        const float* src1 = (p.mode == MCQ_EPI_LINEAR || p.mode == MCQ_EPI_GATE) ? p.res1 : nullptr;
+        const float* src2 = (p.mode == MCQ_EPI_LINEAR) ? p.res2 : p.aux;
+        if (live && src1) { ld_global_256(src1 + off, o1); ld_global_256(src1 + off + 8, o1 + 8); }
+        if (live && src2) { ld_global_256(src2 + off, o2); ld_global_256(src2 + off + 8, o2 + 8); }
+        if (PASSES == 3) {
+          uint32_t l[16];
+          tmem_ld16(t_acc + (uint32_t)(bn + col0), l);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = fmaf(__uint_as_float(l[j]), kLoInv, __uint_as_float(r[j]));
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
+        }
+        if (!live) continue;
+        {
+          float b[16];
+          load_f32v<16>(bias_src, c0, b);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], p.w_scale, b[j]);
+        }
+        if (p.mode == MCQ_EPI_LINEAR) {
+          if (src1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = y[j] + p.res1_scale * o1[j];
+          }
+          if (src2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = y[j] + o2[j];
+          }
+        } else if (p.mode == MCQ_EPI_GATE) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = o2[j] * sigmoid_f<PASSES == 1>(y[j]) + o1[j];
+        } else if (p.mode == MCQ_EPI_GDN) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if constexpr (PASSES == 1) y[j] = o2[j] * rsqrtf(y[j]);
+            else y[j] = o2[j] * (1.0f / sqrtf(y[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if constexpr (PASSES == 1) y[j] = o2[j] * (y[j] * rsqrtf(y[j]));
+            else y[j] = o2[j] * sqrtf(y[j]);
+          }
+        }
+        if (p.out_f32) {
+          st_global_256(p.out_f32 + off, reinterpret_cast<const uint32_t(&)[8]>(y[0]));
+          st_global_256(p.out_f32 + off + 8, reinterpret_cast<const uint32_t(&)[8]>(y[8]));
+        }
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+          __half* hi_p = slot == 0 ? p.o0_hi : p.o1_hi;
+          __half* lo_p = slot == 0 ? p.o0_lo : p.o1_lo;
+          if (!hi_p) continue;
+          float t[16];
+          act_group<16, PASSES == 1>(y, t, slot == 0 ? p.o0_act : p.o1_act);
+          uint32_t h[8], lw[8];
+          if (lo_p) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_f32x2(t[2 * j], t[2 * j + 1], h[j], lw[j]);
+            st_global_256(hi_p + off, h);
+            st_global_256(lo_p + off, lw);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = f2h2_sat(t[2 * j], t[2 * j + 1]);
+            st_global_256(hi_p + off, h);
+          }
+        }
+      }
+    }
     return;
   }
   for (int cc = cg * 32; cc < bn; cc += 128) {

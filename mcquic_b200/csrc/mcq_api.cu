@@ -170,6 +170,8 @@ int fill_args(const mcq_conv_params* p, ConvArgs& a) {
   a.ktotal = p->ksize * p->ksize * p->cin;
   a.cin_total = p->cin; a.ch_off = 0;
   a.mode = p->mode; a.store = p->store; a.o0_act = p->out0_act; a.o1_act = p->out1_act; a.passes = p->passes;
+  static const int direct = env_int("MCQ_DIRECT_EPI", 1);
+  a.direct_epilogue = direct;
   return 0;
 }
 

@@ -21,7 +21,7 @@ g = torch.Generator().manual_seed(0)
 packs = [pack_conv(((torch.rand(c, c, 3, 3, generator=g) * 2 - 1) / (9 * c) ** 0.5).cuda(), torch.zeros(c).cuda(), 1, 0, "cuda")
          for _ in range(2 * L)]
 out = {}
-for hw in (4, 8, 16, 32, 64):
+for hw in ([int(v) for v in os.environ["PROF_HW"].split(",")] if os.environ.get("PROF_HW") else (4, 8, 16, 32, 64)):
     for passes in (1, 3):
         eng.passes = passes
         x = torch.randn(n, hw, hw, c, generator=g).cuda()
