@@ -49,6 +49,7 @@ struct ConvArgs {
   unsigned long long* argmin_keys;  // EPI_ARGMIN: per-point packed (ordered distance << 32 | index) minima
   int argmin_stride;              // points are argmin_stride keys / aux entries apart (= number of codebooks)
   int debug_skip_store;           // MCQ_EPI_SKIP=1: drain TMEM but store nothing (profiling aid)
+  int wait_sleep_ns;              // nanosleep between mbarrier polls of the producer / drain warps (MCQ_WAIT_SLEEP_NS)
   int direct_epilogue;            // 1 (default): transpose-free drain where it applies, see drain_tile (MCQ_DIRECT_EPI=0: off)
   // per-tap TMA coordinate offsets in the 5-D view of A (see conv_tc.cuh)
   int tap_c[9], tap_dx[9], tap_py[9], tap_dy[9];

@@ -177,7 +177,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int wi = cluster_id + (a_issue / kchunks) * num_clusters, kc = a_issue % kchunks;
         int ct, x0, y0, n;
         decode_tile(wi, ct, x0, y0, n);
-        mbar_wait(a_empty(ab), aph ^ 1u, 11);
+        mbar_wait(a_empty(ab), aph ^ 1u, 11, p.wait_sleep_ns);
         const uint32_t sa = a_base + a_buf_bytes * ab;
         if (elect_one()) {
           // the whole box is always transferred (out-of-image pixels are zero-filled): tx = box bytes
@@ -196,7 +196,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int row0 = ct * bn + (int)crank * (bn / CL);
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int sg = 0; sg < spc; ++sg) {
-            mbar_wait(b_empty(bs), bph ^ 1u, 12);
+            mbar_wait(b_empty(bs), bph ^ 1u, 12, p.wait_sleep_ns);
             if (elect_one()) {
               mbar_expect_tx(b_full(bs), b_stage_bytes);
               for (int tt = 0; tt < hp.tps; ++tt) {
@@ -306,7 +306,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
       prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
-      mbar_wait(tfull_bar(buf), use & 1u, 16);
+      mbar_wait(tfull_bar(buf), use & 1u, 16, p.wait_sleep_ns);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
       drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias);

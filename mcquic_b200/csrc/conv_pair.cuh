@@ -189,7 +189,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int wi = work_item(a_issue / kchunks), kc = a_issue % kchunks;
         int ct, x0, y0, n;
         decode_tile(wi, ct, x0, y0, n);
-        mbar_wait(a_empty(ab), aph ^ 1u, 21);
+        mbar_wait(a_empty(ab), aph ^ 1u, 21, p.wait_sleep_ns);
         const uint32_t sa = a_base + a_buf_bytes * ab;
         const uint32_t lbar = map_to_cta(a_full(ab), 0);
         if (elect_one()) {
@@ -210,7 +210,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int row_half = ct * bn + (int)crank * (bn / 2);
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int sg = 0; sg < spc; ++sg) {
-            if (!hp.resident) mbar_wait(b_empty(bs), bph ^ 1u, 22);
+            if (!hp.resident) mbar_wait(b_empty(bs), bph ^ 1u, 22, p.wait_sleep_ns);
             const uint32_t lbar = map_to_cta(b_full(bs), 0);
             if (load_b && elect_one()) {
               if (leader) mbar_expect_tx(b_full(bs), 2u * b_stage_bytes);
@@ -310,7 +310,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
       prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
-      mbar_wait(tfull_bar(buf), use & 1u, 26);
+      mbar_wait(tfull_bar(buf), use & 1u, 26, p.wait_sleep_ns);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
       drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias);

@@ -172,6 +172,8 @@ int fill_args(const mcq_conv_params* p, ConvArgs& a) {
   a.mode = p->mode; a.store = p->store; a.o0_act = p->out0_act; a.o1_act = p->out1_act; a.passes = p->passes;
   static const int direct = env_int("MCQ_DIRECT_EPI", 1);
   a.direct_epilogue = direct;
+  static const int wait_sleep = env_int("MCQ_WAIT_SLEEP_NS", 0);
+  a.wait_sleep_ns = wait_sleep;
   return 0;
 }
 
