@@ -150,6 +150,17 @@ int mcq_vq_dequant(const int64_t* codes, const float* codebook, int32_t n, int32
 int mcq_code_histogram(const int64_t* codes, int32_t n, int32_t m, int32_t hw, int32_t k, int32_t* hist,
                        mcq_stream_t stream);
 
+/* Replaces nn.GroupNorm(groups, c) as used between the two convolutions of ResidualBlock(denseNorm=True)
+ * (mcquic/nn/blocks.py:198; only the `Neon` tokenizer builds it, mcquic/modules/compressor.py:181-233):
+ * per image and group, mean / biased variance over (h, w, c/groups), y = (x - mean) * rsqrt(var + eps) * gamma + beta.
+ * x: fp32 NHWC [n,h,w,c] (the fp32 output of the producing convolution); gamma, beta: [c] (state_dict `weight`, `bias`).
+ * Outputs (at least one): out_f32 fp32 NHWC and/or the split-fp16 planes of act(y) that the next convolution reads as
+ * its A operand (out_lo may be NULL: 1-pass consumers).  One launch, one thread-block cluster per image; statistics
+ * are combined in double in a fixed order (bit-reproducible).  c % 4 == 0, c <= 512, else MCQ_ERR_UNSUPPORTED. */
+int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t groups, const float* gamma,
+                  const float* beta, float eps, float* out_f32, void* out_hi, void* out_lo, int32_t out_act,
+                  mcq_stream_t stream);
+
 /* fp32 [count] -> split-fp16 planes, act applied first (boundary helper; also NCHW->NHWC when c,h,w given). */
 int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, mcq_stream_t stream);
 int mcq_nchw_to_nhwc(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, float* out_f32, void* out0_hi,

@@ -14,6 +14,7 @@
 #include "conv_pair.cuh"
 #include "conv_tc.cuh"
 #include "conv_chain.cuh"
+#include "groupnorm.cuh"
 #include "misc.cuh"
 #include "vq.cuh"
 #include "vq_fused.cuh"
@@ -882,6 +883,36 @@ int mcq_code_histogram(const int64_t* codes, int32_t n, int32_t m, int32_t hw, i
                                                                                           m, hw, k, hist);
   g_launches++;
   return cuda_status();
+}
+
+int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t groups, const float* gamma,
+                  const float* beta, float eps, float* out_f32, void* out_hi, void* out_lo, int32_t out_act,
+                  mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && gamma && beta && (out_f32 || out_hi));
+  MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && groups > 0 && c % groups == 0 && eps >= 0.f);
+  MCQ_CHECK_ARG((long long)h * w <= 0x7fffffffLL / c);
+  if (c % 4 != 0 || c > GN_MAX_C) return MCQ_ERR_UNSUPPORTED;
+  GroupNormArgs a;
+  a.x = x; a.gamma = gamma; a.beta = beta; a.out_f32 = out_f32; a.o_hi = (__half*)out_hi; a.o_lo = (__half*)out_lo;
+  a.o_act = out_act; a.n = n; a.hw = h * w; a.c = c; a.groups = groups; a.eps = eps;
+  // one cluster per image; as many CTAs per cluster as leave every CTA >= 32 pixels (tiny maps: a single CTA)
+  int slices = GN_MAX_CLUSTER;
+  while (slices > 1 && a.hw < slices * 32) slices >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n * slices);
+  cfg.blockDim = dim3(GN_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)slices;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, groupnorm_kernel, a);
+  g_launches++;
+  return e == cudaSuccess ? cuda_status() : (int)e;
 }
 
 int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, mcq_stream_t stream) {

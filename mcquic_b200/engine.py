@@ -8,6 +8,9 @@ runs in libmcquic_b200.so (`_lib.py`).  Fusion map (reference op -> where it wen
   GDN / IGDN (gdn.py:67-91)          -> 1x1 tensor-core conv over x^2 planes, epilogue x * rsqrt/sqrt(.)
   PixelShuffle (convs.py:252-255)    -> store addressing of the producing conv (weights row-permuted at load)
   a * sigmoid(b) + x (blocks.py:281) -> epilogue of the AttentionBlock's trailing 1x1 conv
+  nn.GroupNorm (blocks.py:198)       -> one cluster-per-image launch: statistics + affine + split into the next
+                                        conv's operand planes (csrc/groupnorm.cuh)
+  conv1x1 skip (blocks.py:189-192)   -> its fp32 output is the residual operand of the block's second conv
   z - dequant(code) (quantizer.py:318), q + side (quantizer.py:354) -> residual operands
   AlignedPadding (transforms.py:86)  -> index arithmetic of the stem kernel
 """
@@ -357,6 +360,8 @@ class Engine:
     @staticmethod
     def needs_of(mod: nn.Module) -> Set[str]:
         """Representations of its input a module reads."""
+        if isinstance(mod, ResidualBlock) and mod._skip is not None:
+            return {"raw", "silu"}
         if isinstance(mod, (ResidualBlock, AttentionBlock)):
             return {"f32", "silu"}
         if isinstance(mod, (ResidualBlockWithStride, ResidualBlockShuffle)):
@@ -365,10 +370,45 @@ class Engine:
             return {"raw"}
         raise NotImplementedError(f"mcquic_b200: no accelerated path for {type(mod).__name__}")
 
+    def groupnorm(self, norm: nn.GroupNorm, x: Act, want: Set[str]) -> Act:
+        """nn.GroupNorm on the fp32 output of a conv -> the representations the next conv reads (one launch)."""
+        self.flush()
+        if x.f32 is None or norm.num_channels != x.c:
+            raise RuntimeError("mcquic_b200: GroupNorm expects the fp32 NHWC output of the producing convolution")
+        if not norm.affine:
+            raise NotImplementedError("mcquic_b200: GroupNorm without affine parameters is not on the accelerated path")
+        dev = x.f32.device
+        out = Act(x.n, x.h, x.w, x.c)
+        if "f32" in want:
+            out.f32 = torch.empty_like(x.f32)
+        pl, act = (None, None), _lib.ACT_NONE
+        planes = [name for name in ("raw", "silu", "sq") if name in want]
+        if len(planes) > 1:
+            raise NotImplementedError("mcquic_b200: GroupNorm writes one plane pair")
+        if planes:
+            pl = self._planes(x.n, x.h, x.w, x.c, dev)
+            setattr(out, planes[0], pl)
+            act = {"raw": _lib.ACT_NONE, "silu": _lib.ACT_SILU, "sq": _lib.ACT_SQUARE}[planes[0]]
+        gamma = norm.weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+        beta = norm.bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+        _lib.check(self.lib.mcq_groupnorm(_ptr(x.f32), x.n, x.h, x.w, x.c, norm.num_groups, _ptr(gamma), _ptr(beta),
+                                          float(norm.eps), _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act,
+                                          self._stream()), "mcq_groupnorm")
+        return out
+
     def residual_block(self, mod: ResidualBlock, x: Act, want: Set[str], res2: Optional[torch.Tensor] = None,
                        into: Optional[Act] = None) -> Act:
-        t = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"silu"})
-        return self.conv(self._packed_for(mod._branch[3]), t.silu, t, want, res1=x.f32, res2=res2, into=into)
+        identity = x.f32
+        if mod._skip is not None:       # channel-changing block: conv1x1 on the un-activated x (blocks.py:73-75)
+            identity = self.conv(self._packed_for(mod._skip), x.raw, x, {"f32"}).f32
+        if isinstance(mod._branch[2], nn.GroupNorm):
+            t = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"f32"})
+            t = self.groupnorm(mod._branch[2], t, {"raw"})
+            a = t.raw
+        else:
+            t = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"silu"})
+            a = t.silu
+        return self.conv(self._packed_for(mod._branch[3]), a, t, want, res1=identity, res2=res2, into=into)
 
     def residual_block_stride(self, mod: ResidualBlockWithStride, x: Act, want: Set[str]) -> Act:
         u = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"f32", "sq"})
@@ -396,7 +436,8 @@ class Engine:
                 b = self.residual_block(mod._sideBranch[i], b, {"f32", "silu"} if i < 2 else {"raw"})
             return b
 
-        a, b = self.parallel(main_branch, side_branch, chain=self.can_chain(x))
+        dense = isinstance(mod._mainBranch[0]._branch[2], nn.GroupNorm)   # its GroupNorm launches cannot join a chain
+        a, b = self.parallel(main_branch, side_branch, chain=self.can_chain(x) and not dense)
         return self.conv(self._packed_for(mod._sideBranch[3]), b.raw, b, want, mode=_lib.EPI_GATE, res1=x.f32,
                          aux=a.f32)
 

@@ -33,12 +33,15 @@ class _ResidualBase(_EngineModule):
 
 
 class ResidualBlock(_ResidualBase):
-    """y = x + conv3(SiLU(conv3(SiLU(x))))"""
+    """y = skip(x) + conv3(act2(conv3(SiLU(x)))),  act2 = SiLU, or nn.GroupNorm(groups, outChannels) when denseNorm
+    (then NO activation before the second conv, blocks.py:198); skip = conv1x1 iff the channel count changes
+    (blocks.py:189-192), else the identity.  `groups` is the GroupNorm group count, not a grouped convolution."""
 
     def __init__(self, inChannels: int, outChannels: int, groups: int = 1, denseNorm: bool = False):
-        if denseNorm or inChannels != outChannels:
-            raise NotImplementedError("mcquic_b200: GroupNorm / channel-changing ResidualBlock (Neon only) is out of scope")
-        super().__init__(nn.SiLU(), conv3x3(inChannels, outChannels), nn.SiLU(), conv3x3(outChannels, outChannels), None)
+        skip = conv1x1(inChannels, outChannels) if inChannels != outChannels else None
+        super().__init__(nn.SiLU(), conv3x3(inChannels, outChannels),
+                         nn.GroupNorm(groups, outChannels) if denseNorm else nn.SiLU(),
+                         conv3x3(outChannels, outChannels), skip)
 
 
 class ResidualBlockWithStride(_ResidualBase):

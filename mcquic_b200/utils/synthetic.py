@@ -65,3 +65,24 @@ def synthetic_state_dict(channel: int, m: int, k: List[int], seed: int = 0) -> D
         else:  # reparam constants, temperatures, freqEMA, bounds: keep the reference's init values
             out[key] = ref.clone()
     return out
+
+
+def synthetic_block_state(template: Dict[str, torch.Tensor], tag: str, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Deterministic weights for ONE block (`template` = its state_dict): convolutions as above, nn.GroupNorm
+    affine parameters (1-D `weight` / `bias` without a 4-D sibling) as 1 + 0.2 u and 0.1 u."""
+    out: Dict[str, torch.Tensor] = {}
+    for key, ref in template.items():
+        shape = tuple(ref.shape)
+        name = f"{tag}.{key}"
+        if key.endswith(".weight") and len(shape) == 4:
+            out[key] = uniform(shape, name, seed) / (shape[1] * shape[2] * shape[3]) ** 0.5
+        elif key.endswith(".bias") and template[key[:-4] + "weight"].dim() == 4:
+            w = template[key[:-4] + "weight"]
+            out[key] = uniform(shape, name, seed) / (w.shape[1] * w.shape[2] * w.shape[3]) ** 0.5
+        elif key.endswith(".weight") and len(shape) == 1:
+            out[key] = 1.0 + 0.2 * uniform(shape, name, seed)
+        elif key.endswith(".bias"):
+            out[key] = 0.1 * uniform(shape, name, seed)
+        else:
+            out[key] = ref.clone()
+    return out

@@ -85,5 +85,29 @@ def main():
     print("vq", tuple(code.shape), "min margin", float(O.vq_margin(x, cb).min()))
 
 
+def blocks():
+    """tests/golden/blocks_dense.npz: the reference's own ResidualBlock / AttentionBlock classes (GroupNorm via
+    denseNorm=True, conv1x1 skips) on the deterministic weights / inputs of tests/common.py:DENSE_BLOCKS."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import DENSE_BLOCKS, dense_block_inputs, dense_stride
+    ref_import.load()
+    import mcquic.nn.blocks as RB
+    torch.set_num_threads(8)
+    rec = {}
+    for name, (kind, args, shape) in DENSE_BLOCKS.items():
+        block, x = dense_block_inputs(name, getattr(RB, kind))
+        with torch.inference_mode():
+            y = block(x)
+        rec[name] = y[..., ::dense_stride(shape), ::dense_stride(shape)].numpy().astype(np.float32)
+        rec[name + "_sha256"] = np.array(sha(y))
+        print(name, tuple(y.shape), "absmax", float(y.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "blocks_dense.npz"), **rec)
+
+
 if __name__ == "__main__":
-    main()
+    os.makedirs(OUT, exist_ok=True)
+    if "--blocks" in sys.argv:
+        blocks()
+    else:
+        main()
+        blocks()

@@ -66,10 +66,18 @@ def _gdn(sd: StateDict, p: str, x: torch.Tensor, inverse: bool) -> torch.Tensor:
 
 
 # mcquic/nn/blocks.py:62-78 (_residulBlock.forward) + :163-200 (ResidualBlock)
-def residual_block(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
+# groups: nn.GroupNorm(groups, C) replaces the second SiLU when the block was built with denseNorm=True (:198; then
+# there is NO activation before the second conv) -- recognised by the norm's `_branch.2.weight` in the state_dict;
+# a `_skip` conv1x1 exists iff the channel count changes (:189-192) and takes the un-activated x.
+def residual_block(sd: StateDict, p: str, x: torch.Tensor, groups: int = 1, eps: float = 1e-5) -> torch.Tensor:
     out = _conv(sd, p + "._branch.1", F.silu(x))
-    out = _conv(sd, p + "._branch.3", F.silu(out))
-    return out + x
+    if p + "._branch.2.weight" in sd:
+        out = F.group_norm(out, groups, sd[p + "._branch.2.weight"], sd[p + "._branch.2.bias"], eps)
+    else:
+        out = F.silu(out)
+    out = _conv(sd, p + "._branch.3", out)
+    identity = _conv(sd, p + "._skip", x) if p + "._skip.weight" in sd else x
+    return out + identity
 
 
 # mcquic/nn/blocks.py:82-122 (ResidualBlockWithStride): SiLU, conv3 s2, GDN, conv3; skip = conv3 s2 on raw x
@@ -88,14 +96,14 @@ def residual_block_shuffle(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tens
     return out + _pixel_shuffle_conv(sd, p + "._skip", x)
 
 
-# mcquic/nn/blocks.py:246-288 (AttentionBlock)
-def attention_block(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
+# mcquic/nn/blocks.py:246-288 (AttentionBlock); groups / denseNorm are handed to its six ResidualBlocks (:264-273)
+def attention_block(sd: StateDict, p: str, x: torch.Tensor, groups: int = 1) -> torch.Tensor:
     a = x
     for i in range(3):
-        a = residual_block(sd, f"{p}._mainBranch.{i}", a)
+        a = residual_block(sd, f"{p}._mainBranch.{i}", a, groups)
     b = x
     for i in range(3):
-        b = residual_block(sd, f"{p}._sideBranch.{i}", b)
+        b = residual_block(sd, f"{p}._sideBranch.{i}", b, groups)
     b = _conv(sd, p + "._sideBranch.3", b)
     return a * torch.sigmoid(b) + x
 

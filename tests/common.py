@@ -37,3 +37,41 @@ def code_report(got, ref, margins=None):
         if margins is not None:
             at += torch.as_tensor(margins[lv])[mism].tolist()
     return flips, total, at
+
+
+# ResidualBlock / AttentionBlock variants only the `Neon` tokenizer builds (GroupNorm via denseNorm=True, channel-
+# changing blocks with a conv1x1 skip): name -> (kind, constructor args, input shape [n, c, h, w])
+DENSE_BLOCKS = {
+    "rb64_gn8": ("ResidualBlock", (64, 64, 8, True), (2, 64, 24, 20)),
+    "rb64to128_gn32": ("ResidualBlock", (64, 128, 32, True), (2, 64, 16, 16)),
+    "rb128to64_plain": ("ResidualBlock", (128, 64, 1, False), (3, 128, 8, 8)),
+    "rb128_gn1_64x64": ("ResidualBlock", (128, 128, 1, True), (2, 128, 64, 64)),
+    "ab64_gn4": ("AttentionBlock", (64, 4, True), (2, 64, 12, 16)),
+    "rb32_gn32_simt": ("ResidualBlock", (32, 32, 32, True), (1, 32, 10, 6)),
+}
+
+
+def dense_stride(shape):
+    """spatial sampling stride of the stored golden output (full for the small cases)"""
+    return 4 if shape[2] * shape[3] > 1024 else 1
+
+
+def dense_block_inputs(name, cls):
+    """(block with deterministic weights, input) for one DENSE_BLOCKS case; cls = the class to instantiate."""
+    from mcquic_b200.utils.synthetic import synthetic_block_state
+    kind, args, shape = DENSE_BLOCKS[name]
+    block = cls(*args).eval()
+    block.load_state_dict(synthetic_block_state(block.state_dict(), name, seed=0))
+    return block, uniform(shape, name + ".x", 2)
+
+
+def dense_block_oracle(name, sd, x):
+    from oracle import mcquic_oracle as O
+    kind, args, _ = DENSE_BLOCKS[name]
+    if kind == "AttentionBlock":
+        return O.attention_block(_prefixed(sd), "b", x, groups=args[1])
+    return O.residual_block(_prefixed(sd), "b", x, groups=args[2])
+
+
+def _prefixed(sd):
+    return {"b." + k: v for k, v in sd.items()}

@@ -179,6 +179,19 @@ class EmulatedLib:
         self.launches += 1
         return 0
 
+    def mcq_groupnorm(self, x, n, h, w, c, groups, gamma, beta, eps, out_f32, out_hi, out_lo, act, stream):
+        """header contract: nn.GroupNorm(groups, c) on fp32 NHWC, outputs fp32 and/or planes of act(y)"""
+        xi = torch.from_numpy(_arr(x.value, (n, h, w, c), np.float32).copy())
+        g = torch.from_numpy(_arr(gamma.value, (c,), np.float32).copy())
+        b = torch.from_numpy(_arr(beta.value, (c,), np.float32).copy())
+        y = F.group_norm(xi.permute(0, 3, 1, 2), groups, g, b, eps).permute(0, 2, 3, 1).contiguous()
+        v = lambda q: q.value if q is not None and q.value else 0
+        if v(out_f32):
+            _arr(v(out_f32), (n, h, w, c), np.float32)[...] = y.numpy()
+        _store_planes(v(out_hi), v(out_lo), (n, h, w, c), y, act)
+        self.launches += 1
+        return 0
+
     def mcq_split_planes(self, x, count, act, out_hi, out_lo, stream):
         y = torch.from_numpy(_arr(x.value, (count,), np.float32).copy())
         _store_planes(out_hi.value, out_lo.value if out_lo is not None and out_lo.value else 0, (count,), y, act)
