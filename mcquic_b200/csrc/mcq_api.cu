@@ -895,13 +895,19 @@ int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, in
   GroupNormArgs a;
   a.x = x; a.gamma = gamma; a.beta = beta; a.out_f32 = out_f32; a.o_hi = (__half*)out_hi; a.o_lo = (__half*)out_lo;
   a.o_act = out_act; a.n = n; a.hw = h * w; a.c = c; a.groups = groups; a.eps = eps;
-  // one cluster per image; as many CTAs per cluster as leave every CTA >= 32 pixels (tiny maps: a single CTA)
+  // a cluster per image in flight; as many CTAs per cluster as leave every CTA >= 32 pixels (tiny maps: a single CTA)
   int slices = GN_MAX_CLUSTER;
   while (slices > 1 && a.hw < slices * 32) slices >>= 1;
+  static const int threads = env_int("MCQ_GN_THREADS", 256);
+  static const int ctas_per_sm = env_int("MCQ_GN_CTAS_PER_SM", 4);
+  // persistent clusters, ctas_per_sm CTAs per SM's worth of them (never more than images)
+  long long clusters = ((long long)ctas_per_sm * num_sms()) / slices;
+  if (clusters < 1) clusters = 1;
+  if (clusters > n) clusters = n;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)n * slices);
-  cfg.blockDim = dim3(GN_THREADS);
-  cfg.dynamicSmemBytes = 0;
+  cfg.gridDim = dim3((unsigned)(clusters * slices));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = (size_t)gn_smem_bytes(threads);
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -910,7 +916,17 @@ int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, in
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, groupnorm_kernel, a);
+  cudaError_t e;
+  if (threads == 1024) {
+    static const cudaError_t attr = cudaFuncSetAttribute(groupnorm_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, gn_smem_bytes(1024));
+    e = attr != cudaSuccess ? attr : cudaLaunchKernelEx(&cfg, groupnorm_kernel<1024>, a);
+  } else if (threads == 512) {
+    e = cudaLaunchKernelEx(&cfg, groupnorm_kernel<512>, a);
+  } else if (threads == 256) {
+    e = cudaLaunchKernelEx(&cfg, groupnorm_kernel<256>, a);
+  } else {
+    return MCQ_ERR_BAD_ARG;
+  }
   g_launches++;
   return e == cudaSuccess ? cuda_status() : (int)e;
 }
