@@ -161,6 +161,13 @@ int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, in
                   const float* beta, float eps, float* out_f32, void* out_hi, void* out_lo, int32_t out_act,
                   mcq_stream_t stream);
 
+/* out = x + alpha * y over `count` fp32 values (count % 4 == 0), written as fp32 and/or as the split-fp16 planes of
+ * act(out).  Replaces the two element-wise steps of ResidualBackwardQuantizer that no convolution epilogue can absorb:
+ * `residual = latent - currentLatent` (mcquic/modules/quantizer.py:686; the latent exists before currentLatent does)
+ * and `quantized + formerLevel` (:701).  alpha = +-1 reproduces the reference's fp32 result bit for bit. */
+int mcq_add_scaled(const float* x, const float* y, float alpha, int64_t count, float* out_f32, void* out_hi,
+                   void* out_lo, int32_t out_act, mcq_stream_t stream);
+
 /* fp32 [count] -> split-fp16 planes, act applied first (boundary helper; also NCHW->NHWC when c,h,w given). */
 int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, mcq_stream_t stream);
 int mcq_nchw_to_nhwc(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, float* out_f32, void* out0_hi,

@@ -51,6 +51,7 @@ SYMBOLS = {
     "mcq_vq_dequant": (_c.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _i32, _p, _p]),
     "mcq_code_histogram": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "mcq_groupnorm": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _p, _p, _i32, _p]),
+    "mcq_add_scaled": (_c.c_int, [_p, _p, _f, _i64, _p, _p, _p, _i32, _p]),
     "mcq_split_planes": (_c.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "mcq_nchw_to_nhwc": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _i32, _p]),
     "mcq_nhwc_to_nchw": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),

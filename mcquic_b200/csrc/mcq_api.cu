@@ -931,6 +931,16 @@ int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, in
   return e == cudaSuccess ? cuda_status() : (int)e;
 }
 
+int mcq_add_scaled(const float* x, const float* y, float alpha, int64_t count, float* out_f32, void* out_hi,
+                   void* out_lo, int32_t out_act, mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && y && (out_f32 || out_hi) && count > 0 && count % 4 == 0);
+  const long long c4 = count / 4;
+  add_scaled_kernel<<<(unsigned)((c4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, alpha, c4, out_f32, out_act,
+                                                                                    (__half*)out_hi, (__half*)out_lo);
+  g_launches++;
+  return cuda_status();
+}
+
 int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, mcq_stream_t stream) {
   MCQ_CHECK_ARG(x && out_hi && count > 0 && count % 4 == 0);
   const long long c4 = count / 4;

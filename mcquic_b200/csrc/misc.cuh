@@ -90,6 +90,21 @@ __global__ void split_planes_kernel(const float* x, long long count4, int act, _
   store_planes<4>(hi, lo, (size_t)i * 4, y, act);
 }
 
+// out = x + alpha * y (one rounding: alpha = +-1 gives exactly the reference's `latent - currentLatent` /
+// `quantized + formerLevel`, mcquic/modules/quantizer.py:686,701), as fp32 and/or split planes of act(out)
+__global__ void add_scaled_kernel(const float* x, const float* y, float alpha, long long count4, float* out_f32,
+                                  int act, __half* hi, __half* lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count4) return;
+  float a[4], b[4], v[4];
+  load_f32v<4>(x, (size_t)i * 4, a);
+  load_f32v<4>(y, (size_t)i * 4, b);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = fmaf(alpha, b[j], a[j]);
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  if (hi) store_planes<4>(hi, lo, (size_t)i * 4, v, act);
+}
+
 struct LayoutArgs {
   const float* x;
   float* out_f32;

@@ -89,11 +89,24 @@ def pack_codebook(codebook: torch.Tensor):
     return hi, lo, scale, torch.cat([lo, hi], dim=1).contiguous()
 
 
-def pack_conv(weight: torch.Tensor, bias: torch.Tensor, stride: int, store: int, device) -> PackedConv:
-    """nn.Conv2d weight [cout, cin, k, k] -> K-major GEMM matrix [cout_pad, (r, s, cin)] (split fp16)."""
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, store: int, device) -> PackedConv:
+    """nn.Conv2d weight [cout, cin, k, k] -> K-major GEMM matrix [cout_pad, (r, s, cin)] (split fp16).
+    bias=None (conv1x1(..., bias=False) of the Neon quantizer) packs a zero bias.  Channel counts the kernels' vector
+    accesses cannot address are zero-padded: cin to a multiple of 4 (RGB input of Neon's first conv: the caller pads
+    the activation likewise) and, for plain NHWC stores, cout to a multiple of 8 (Neon's final C -> 3 conv: the
+    caller drops the extra channels); `PackedConv.cin / .cout` are the padded counts."""
     cout, cin, k, _ = weight.shape
-    w = weight.detach().to(device=device, dtype=torch.float32).permute(0, 2, 3, 1).reshape(cout, k * k * cin)
-    b = bias.detach().to(device=device, dtype=torch.float32)
+    w4 = weight.detach().to(device=device, dtype=torch.float32)
+    b = torch.zeros(cout, device=device) if bias is None else bias.detach().to(device=device, dtype=torch.float32)
+    if cin % 4 != 0:
+        w4 = torch.cat([w4, torch.zeros(cout, 4 - cin % 4, k, k, device=device)], 1)
+        cin = w4.shape[1]
+    if store == _lib.STORE_NHWC and cout % 8 != 0:
+        extra = 8 - cout % 8
+        w4 = torch.cat([w4, torch.zeros(extra, cin, k, k, device=device)], 0)
+        b = torch.cat([b, torch.zeros(extra, device=device)])
+        cout += extra
+    w = w4.permute(0, 2, 3, 1).reshape(cout, k * k * cin)
     if store == _lib.STORE_SHUFFLE_NHWC:
         # PixelShuffle(2): conv channel 4c + 2i + j -> GEMM column (2i + j) * C + c, so an N tile is one sub-pixel
         cq = cout // 4
@@ -258,6 +271,8 @@ class Engine:
 
         if isinstance(mod, GenDivNorm):
             ver = (version(mod.beta), version(mod.gamma), mod.beta.data_ptr(), mod.gamma.data_ptr())
+        elif mod.bias is None:
+            ver = (version(mod.weight), mod.weight.data_ptr())
         else:
             ver = (version(mod.weight), version(mod.bias), mod.weight.data_ptr(), mod.bias.data_ptr())
         hit = self._packed.get(key)
@@ -502,8 +517,34 @@ class Engine:
                    "mcq_stem_conv")
         return out
 
-    def from_nchw(self, x: torch.Tensor, want: Set[str]) -> Act:
+    def add_scaled(self, x: torch.Tensor, y: torch.Tensor, alpha: float, shape: Tuple[int, int, int, int],
+                   want: Set[str]) -> Act:
+        """x + alpha * y on fp32 NHWC tensors of `shape` = (n, h, w, c) -> the representations in `want`."""
         self.flush()
+        n, h, w, c = shape
+        if tuple(x.shape) != tuple(shape) or tuple(y.shape) != tuple(shape):
+            raise RuntimeError(f"mcquic_b200: add_scaled operands must both be {tuple(shape)}")
+        out = Act(n, h, w, c)
+        if "f32" in want:
+            out.f32 = torch.empty_like(x)
+        planes = [name for name in ("raw", "silu", "sq") if name in want]
+        if len(planes) > 1:
+            raise NotImplementedError("mcquic_b200: add_scaled writes one plane pair")
+        pl, act = (None, None), _lib.ACT_NONE
+        if planes:
+            pl = self._planes(n, h, w, c, x.device)
+            setattr(out, planes[0], pl)
+            act = {"raw": _lib.ACT_NONE, "silu": _lib.ACT_SILU, "sq": _lib.ACT_SQUARE}[planes[0]]
+        _lib.check(self.lib.mcq_add_scaled(_ptr(x), _ptr(y), float(alpha), x.numel(), _ptr(out.f32), _ptr(pl[0]),
+                                           _ptr(pl[1]), act, self._stream()), "mcq_add_scaled")
+        return out
+
+    def from_nchw(self, x: torch.Tensor, want: Set[str], pad_channels_to: int = 1) -> Act:
+        """pad_channels_to: zero channels are appended up to a multiple of it (RGB -> 4 for Neon's first conv)."""
+        self.flush()
+        if x.shape[1] % pad_channels_to != 0:
+            extra = pad_channels_to - x.shape[1] % pad_channels_to
+            x = torch.cat([x, x.new_zeros(x.shape[0], extra, x.shape[2], x.shape[3])], 1)
         n, c, h, w = x.shape
         out = Act(n, h, w, c)
         xc = x.contiguous().float()

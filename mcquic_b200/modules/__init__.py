@@ -1,2 +1,2 @@
-from .compressor import BaseCompressor, Compressor  # noqa: F401
-from .quantizer import UMGMQuantizer  # noqa: F401
+from .compressor import BaseCompressor, Compressor, Neon  # noqa: F401
+from .quantizer import ResidualBackwardQuantizer, UMGMQuantizer  # noqa: F401

@@ -12,7 +12,7 @@ from torch import nn
 
 from ..engine import Act, Engine
 from ..nn import AttentionBlock, ResidualBlock, ResidualBlockShuffle, ResidualBlockWithStride, conv3x3, pixelShuffle3x3
-from .quantizer import UMGMQuantizer
+from .quantizer import ResidualBackwardQuantizer, UMGMQuantizer
 
 ALIGN_BASE = 128  # mcquic/data/transforms.py:82
 
@@ -58,6 +58,23 @@ class BaseCompressor(nn.Module):
     @property
     def NormalizedFreq(self):
         return self._quantizer.NormalizedFreq
+
+    @property
+    def CodeUsage(self):
+        """compressor.py:62-64: fraction of codewords with a non-negligible frequency"""
+        return torch.cat([(freq > 1e-6).flatten() for freq in self._quantizer.NormalizedFreq]).float().mean()
+
+    def reAssignCodebook(self) -> torch.Tensor:
+        """compressor.py:45-46 (codebook maintenance between epochs); drops the captured graphs' packed codebooks"""
+        out = self._quantizer.reAssignCodebook()
+        self.invalidate()
+        return out
+
+    def syncCodebook(self):
+        """compressor.py:48-49"""
+        out = self._quantizer.syncCodebook()
+        self.invalidate()
+        return out
 
     @property
     def engine(self) -> Engine:
@@ -207,7 +224,7 @@ class BaseCompressor(nn.Module):
             if pipe is None:
                 eng = self.engine
                 eng.passes = self.encode_passes
-                total = sum(self._quantizer._m * k for k in self._quantizer._k)
+                total = self._quantizer.hist_size()
                 sx = torch.empty(tuple(x.shape), dtype=torch.float32, device=dev)
                 sh = torch.zeros(total, dtype=torch.int32, device=dev)
                 _, _, hp, wp = aligned_pad_amounts(h, w)
@@ -299,7 +316,7 @@ class BaseCompressor(nn.Module):
         if not (self.use_graphs and x.is_cuda):
             return self._encode_eager(x, hist)
         x = x.contiguous().float()
-        total = sum(self._quantizer._m * k for k in self._quantizer._k)
+        total = self._quantizer.hist_size()
 
         def make_static():
             return [torch.empty_like(x), torch.zeros(total, dtype=torch.int32, device=x.device)]
@@ -407,3 +424,64 @@ class Compressor(BaseCompressor):
             "sideHead": lambda: nn.Sequential(AB(C), conv3x3(C, C), RB(C, C)),
         })
         super().__init__(encoder, quantizer, decoder)
+
+
+class Neon(BaseCompressor):
+    """The tokenizer of BASELINE configs[4] (mcquic/modules/compressor.py:181-233): a full-resolution stem (no stride),
+    three strided stages, a bottleneck to the quantizer's 8 channels, and `ResidualBackwardQuantizer` (len(size) levels
+    sharing one [1, k, 8] codebook).  With denseNorm=True every ResidualBlock normalises with nn.GroupNorm (32 groups in
+    the trunk, 1 around the quantizer).  encode/decode (inference) run on the CUDA engine; `codes` are ordered smallest
+    level first, as upstream."""
+
+    def __init__(self, channel: int, k: int, size: List[int], denseNorm: bool = False, *_, **__):
+        quantizer = ResidualBackwardQuantizer(k, list(size), denseNorm)
+        RB, RBS, RBU, AB = ResidualBlock, ResidualBlockWithStride, ResidualBlockShuffle, AttentionBlock
+        C, Q, d = channel, quantizer.channel, denseNorm
+        encoder = nn.Sequential(
+            conv3x3(3, C), AB(C, 32, d), RB(C, C, 32, d), RB(C, C, 32, d), RBS(C, C, 2, 32, d), RB(C, C, 32, d),
+            RBS(C, C, 2, 32, d), RB(C, C, 32, d), RBS(C, C, 2, 32, d), AB(C, 32, d), RB(C, 2 * C, 32, d),
+            RB(2 * C, 2 * C, 32, d), RB(2 * C, 2 * C, 32, d), RB(2 * C, 2 * C, 32, d), RB(2 * C, Q, 1, d), AB(Q, 1, d))
+        decoder = nn.Sequential(
+            AB(Q, 1, d), RB(Q, 2 * C, 1, d), RB(2 * C, 2 * C, 32, d), RB(2 * C, 2 * C, 32, d), RB(2 * C, 2 * C, 32, d),
+            RB(2 * C, C, 32, d), AB(C, 32, d), RB(C, C, 32, d), RBU(C, C, 2, 32, d), RB(C, C, 32, d), RBU(C, C, 2, 32, d),
+            RB(C, C, 32, d), RBU(C, C, 2, 32, d), RB(C, C, 32, d), RB(C, C, 32, d), AB(C, 32, d), conv3x3(C, 3))
+        super().__init__(encoder, quantizer, decoder)
+        # 57 convolutions and 50 GroupNorms deep: the single-pass (TF32-grade) decode drifts to ~2.5e-3 of the output
+        # range, so the tokenizer decodes with the fp32-grade 3-pass path unless told otherwise
+        self.decode_passes = 3
+
+    def _host_batch_ok(self, t: torch.Tensor) -> bool:
+        return False        # the host I/O pipeline is built around Compressor's strided stem / pixel-shuffle tail
+
+    def _encode_eager(self, x: torch.Tensor, hist: Optional[torch.Tensor]) -> List[torch.Tensor]:
+        eng = self.engine
+        eng.passes = self.encode_passes
+        n, _, h, w = x.shape
+        top, left, hp, wp = aligned_pad_amounts(h, w)
+        if (hp, wp) != (h, w):       # AlignedPadding (transforms.py:86-99): a copy with reflected borders, no arithmetic
+            x = torch.nn.functional.pad(x, (left, wp - w - left, top, hp - h - top), "reflect")
+        a0 = eng.from_nchw(x, eng.needs_of(self._encoder[0]), pad_channels_to=4)
+        y = eng.run_seq(list(self._encoder), a0, self._quantizer.first_needs(eng))
+        codes = self._quantizer.encode_act(eng, y, hist)
+        eng.flush()
+        return codes
+
+    def _decode_eager(self, codes: List[torch.Tensor], status: torch.Tensor) -> torch.Tensor:
+        eng = self.engine
+        eng.passes = self.decode_passes
+        yHat = self._quantizer.decode_act(eng, codes, eng.needs_of(self._decoder[0]), status)
+        out = eng.run_seq(list(self._decoder), yHat, {"f32"})      # final conv C -> 3 runs with 8 stored channels
+        eng.flush()
+        return eng.to_nchw(out)[:, :3].contiguous()
+
+    def residual_backward(self, code: torch.Tensor, level: int) -> torch.Tensor:
+        return self._quantizer.residual_backward(code, level)       # compressor.py:235-237
+
+    def residual_forward(self, code: torch.Tensor, formerLevel: Optional[torch.Tensor], level: int) -> torch.Tensor:
+        return self._quantizer.residual_forward(code, formerLevel, level)   # compressor.py:239-241
+
+    def compress(self, x: torch.Tensor):
+        raise NotImplementedError("VariousMCoder.compress raises upstream as well (entropyCoder.py:250)")
+
+    def decompress(self, binaries, headers):
+        raise NotImplementedError("VariousMCoder.decompress raises upstream as well (entropyCoder.py:281)")

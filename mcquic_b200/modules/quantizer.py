@@ -25,13 +25,23 @@ class CodeFrequency(nn.Module):
     uniform; checkpoint keys `_entropyCoder._freqEMA.{l}`), quantized CDF tables and per-image rANS streams.  The
     coder itself is the host C++ library behind `mcquic_b200.entropy` (bit-identical streams to `mcquic.rans`)."""
 
-    def __init__(self, m: int, k: List[int], ema: float = 0.9):
+    def __init__(self, m: Union[int, List[int]], k: List[int], ema: float = 0.9):
+        """m: one codebook count for every level (EntropyCoder, entropyCoder.py:15-26, ema 0.9) or one per level
+        (VariousMCoder, entropyCoder.py:293-303, ema 0.998)."""
         super().__init__()
-        self._freqEMA = nn.ParameterList(nn.Parameter(torch.ones(m, ki) / ki, requires_grad=False) for ki in k)
         self._k = list(k)
         self._m = m
+        self._freqEMA = nn.ParameterList(nn.Parameter(torch.ones(mi, ki) / ki, requires_grad=False)
+                                         for mi, ki in zip(self.level_m(), self._k))
         self._ema = ema
         self._cdfs = None
+
+    def level_m(self) -> List[int]:
+        return list(self._m) if isinstance(self._m, (list, tuple)) else [self._m] * len(self._k)
+
+    def hist_size(self) -> int:
+        """length of the flat int32 code histogram: sum over levels of m_l * k_l (level-major, the order of _freqEMA)"""
+        return sum(mi * ki for mi, ki in zip(self.level_m(), self._k))
 
     @property
     def NormalizedFreq(self) -> List[torch.Tensor]:
@@ -58,9 +68,9 @@ class CodeFrequency(nn.Module):
         """EMA update from a flat int32 histogram [sum_l m*k_l] (already summed over ranks);
         same arithmetic as entropyCoder.py:38-43."""
         off = 0
-        for lv, ki in enumerate(self._k):
-            total = flat_hist[off:off + self._m * ki].reshape(self._m, ki).to(self._freqEMA[lv].dtype)
-            off += self._m * ki
+        for lv, (mi, ki) in enumerate(zip(self.level_m(), self._k)):
+            total = flat_hist[off:off + mi * ki].reshape(mi, ki).to(self._freqEMA[lv].dtype)
+            off += mi * ki
             normalized = total / total.sum(-1, keepdim=True)
             self._freqEMA[lv].copy_((1 - self._ema) * normalized + self._ema * self._freqEMA[lv])
 
@@ -111,7 +121,45 @@ class _multiCodebookQuantization(nn.Module):
         self._scale = math.sqrt(self._k)
         self._temperature = nn.Parameter(torch.ones((self._m, 1, 1, 1)))
         self._bound = LowerBound(_EPS)  # checkpoint key `_bound.bound` (quantizer.py:107)
+        # quantizer.py:109: whatever the owner hands over is stored; only a Parameter (ResidualBackwardQuantizer passes
+        # the entropy coder's, :618) shows up in the state_dict -- UMGMQuantizer passes a float (:399)
+        if isinstance(freqEMA, nn.Parameter):
+            self._freqEMA = freqEMA
         self._c2_cache = None
+
+    @torch.no_grad()
+    def reAssignCodebook(self, freq: torch.Tensor) -> torch.Tensor:
+        """quantizer.py:111-136 (codebook maintenance, SURVEY.md 8f NEXT-4): per codebook, codewords whose normalised
+        frequency is below Eps are overwritten by the most frequently used ones; when more than half were never
+        used, a random half of the never-used ones (torch.randperm, like upstream) is kept untouched.  Returns the
+        flat [m*k] bool mask of codewords that moved by more than 1e-4 (squared L2).  Control plane: plain torch ops
+        on the codebook's device."""
+        new = self._codebook.detach().clone()
+        freq = freq.to(self._codebook.device).detach().clone()
+        half = self._k // 2
+        for j in range(self._m):
+            row = freq[j]
+            never = row < _EPS
+            count = int(never.sum())
+            if count > half:
+                marks = torch.zeros((count,), device=self._codebook.device)
+                marks[torch.randperm(count)[half:]] = -1.0     # these never-used slots are left alone this time
+                row[never] = marks
+                never = (row < _EPS) * (row > -_EPS)
+                count = int(never.sum())
+            order = torch.argsort(row, descending=True)
+            new[j, never] = self._codebook.detach()[j][order][:count]
+        moved = ((new - self._codebook.detach()) ** 2).sum(-1) > 1e-4
+        self._codebook.data.copy_(new)
+        return moved.flatten()
+
+    @torch.no_grad()
+    def syncCodebook(self):
+        """quantizer.py:138-142: rank 0's codebook wins (broadcast of [m, k, d] over NCCL / gloo)."""
+        import torch.distributed as dist
+        codebook = self._codebook.detach().clone()
+        dist.broadcast(codebook, 0)
+        self._codebook.data.copy_(codebook)
 
     def _tables(self):
         """Per codebook version: fp32 codebook, |c_k|^2 [m, k] (quantizer.py:165) and the split-fp16 packing the
@@ -222,6 +270,12 @@ class _quantizerEncoder(nn.Module):
     def Codebook(self):
         return self._quantizer._codebook
 
+    def reAssignCodebook(self, freq: torch.Tensor) -> torch.Tensor:     # quantizer.py:291-292
+        return self._quantizer.reAssignCodebook(freq)
+
+    def syncCodebook(self):                                             # quantizer.py:294-295
+        return self._quantizer.syncCodebook()
+
     def encode_act(self, eng: Engine, x: Act, next_needs, hist: Optional[torch.Tensor]):
         """quantizer.py:310-318 on engine activations: returns (residual Act or None, codes)."""
         z = eng.run_seq(self._latentStageEncoder, x, {"f32", "silu"})
@@ -315,6 +369,21 @@ class UMGMQuantizer(nn.Module):
     def CDFs(self):
         return self._entropyCoder.CDFs
 
+    def hist_size(self) -> int:
+        return self._entropyCoder.hist_size()
+
+    def reAssignCodebook(self) -> torch.Tensor:
+        """quantizer.py:430-436: fraction of codewords re-assigned over all levels"""
+        moved = [enc.reAssignCodebook(freq) for enc, freq in zip(self._encoders, self.NormalizedFreq)]
+        return torch.cat(moved).float().mean()
+
+    def syncCodebook(self):
+        """quantizer.py:438-441"""
+        import torch.distributed as dist
+        dist.barrier()
+        for enc in self._encoders:
+            enc.syncCodebook()
+
     def first_needs(self, eng: Engine):
         return eng.needs_of(self._encoders[0]._latentStageEncoder[0])
 
@@ -351,3 +420,178 @@ class UMGMQuantizer(nn.Module):
     def decode(self, codes: List[torch.Tensor]) -> torch.Tensor:
         eng = default_engine()
         return eng.to_nchw(self.decode_act(eng, codes, {"f32"}))
+
+
+class ResidualBackwardQuantizer(nn.Module):
+    """The `Neon` tokenizer's quantizer (mcquic/modules/quantizer.py:577-765, on VariousMQuantizer :88-93): every level
+    has m = 1 and shares ONE codebook [1, k, 8]; `size` lists the latent grid per level and must halve or stay equal
+    from left to right (:600-657).  Encoding first produces all latents (large to small), then codes the residual of
+    each latent against the up-projection (`_backwards`) of what the smaller levels already explain, from the smallest
+    level back to the largest -- codes are therefore returned SMALLEST level first (:675-693); decoding sums the
+    de-quantised codes into the running reconstruction level by level (:695-703).
+
+    State-dict keys as upstream: `_entropyCoder._freqEMA.{j}`, `_encoders.{l}.{0..3}`, `_backwards.{l}.{0..3}`,
+    `_decoders.{l}.{0..3}`, `_quantizers.{l}.{_codebook,_temperature,_freqEMA,_bound.bound}`,
+    `_dequantizers.{l}._codebook` (all codebook keys alias one Parameter; `_quantizers.{l}._freqEMA` aliases
+    `_entropyCoder._freqEMA.{L-1-l}`)."""
+
+    channel = 8
+
+    def __init__(self, k: int, size: List[int], denseNorm: bool):
+        super().__init__()
+        from ..nn import AttentionBlock, ResidualBlock, ResidualBlockShuffle, ResidualBlockWithStride, conv1x1
+        c = self.channel
+        self._m, self._k = [1] * len(size), [k] * len(size)
+        self._entropyCoder = CodeFrequency(self._m, self._k, ema=0.998)
+        codebook = nn.Parameter(nn.init.trunc_normal_(torch.empty(1, k, c), std=math.sqrt(2 / (5 * c))))
+        encoders, backwards, decoders, quantizers, dequantizers = [], [], [], [], []
+        self._strided: List[bool] = []
+        last = size[0] * 2
+        for i, this in enumerate(size):
+            if this == last // 2:
+                strided = True
+            elif this == last:
+                strided = False
+            else:
+                raise ValueError("The given size sequence does not half or equal to from left to right.")
+            self._strided.append(strided)
+
+            def up():
+                return nn.Sequential(conv1x1(c, c * 4, bias=False),
+                                     ResidualBlockShuffle(c * 4, c * 4, 2, 1, denseNorm) if strided
+                                     else ResidualBlock(c * 4, c * 4, 1, denseNorm),
+                                     AttentionBlock(c * 4, 1, denseNorm), ResidualBlock(c * 4, c, 1, denseNorm))
+
+            encoders.append(nn.Sequential(ResidualBlock(c, c * 4, 1, denseNorm), AttentionBlock(c * 4, 1, denseNorm),
+                                          ResidualBlockWithStride(c * 4, c * 4, 2, 1, denseNorm) if strided
+                                          else ResidualBlock(c * 4, c * 4, 1, denseNorm),
+                                          conv1x1(c * 4, c, bias=False)))
+            quantizers.append(_multiCodebookQuantization(codebook, self._entropyCoder._freqEMA[-(i + 1)]))
+            dequantizers.append(_multiCodebookDeQuantization(codebook))
+            backwards.append(up() if i < len(size) - 1 else nn.Identity())
+            decoders.append(up())
+            last = this
+        self._encoders = nn.ModuleList(encoders)
+        self._decoders = nn.ModuleList(decoders)
+        self._backwards = nn.ModuleList(backwards)
+        self._quantizers = nn.ModuleList(quantizers)
+        self._dequantizers = nn.ModuleList(dequantizers)
+
+    @property
+    def Codebooks(self):
+        return [q._codebook for q in self._quantizers]
+
+    @property
+    def NormalizedFreq(self):
+        return self._entropyCoder.NormalizedFreq
+
+    @property
+    def CDFs(self):
+        return self._entropyCoder.CDFs
+
+    def hist_size(self) -> int:
+        return self._entropyCoder.hist_size()
+
+    def reAssignCodebook(self) -> torch.Tensor:                        # quantizer.py:714-720
+        moved = [q.reAssignCodebook(freq) for q, freq in zip(self._quantizers, self.NormalizedFreq)]
+        return torch.cat(moved).float().mean()
+
+    def syncCodebook(self):                                            # quantizer.py:722-725
+        import torch.distributed as dist
+        dist.barrier()
+        for q in self._quantizers:
+            q.syncCodebook()
+
+    def first_needs(self, eng: Engine):
+        return eng.needs_of(self._encoders[0][0])
+
+    def _up_act(self, eng: Engine, net: nn.Sequential, q: Act, want) -> Act:
+        return eng.run_seq(net, q, want)
+
+    def encode_act(self, eng: Engine, y: Act, hist: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        """quantizer.py:675-693.  hist: flat int32 [L*k]; segment j counts codes[j] (the order of `_freqEMA`, :616)."""
+        levels = len(self._encoders)
+        latents, x = [], y
+        for lv, enc in enumerate(self._encoders):
+            want = {"f32"} | (eng.needs_of(self._encoders[lv + 1][0]) if lv + 1 < levels else set())
+            x = eng.run_seq(enc, x, want)
+            latents.append(x)
+        codes: List[torch.Tensor] = []
+        current: Optional[Act] = None
+        k = self._k[0]
+        for j, lv in enumerate(reversed(range(levels))):
+            lat = latents[lv]
+            residual = lat.f32 if current is None else eng.add_scaled(lat.f32, current.f32, -1.0,
+                                                                      (lat.n, lat.h, lat.w, lat.c), {"f32"}).f32
+            view = None if hist is None else hist[j * k:(j + 1) * k]
+            code = self._quantizers[lv].encode_nhwc(residual, lat.n, lat.h, lat.w, view, eng)
+            codes.append(code)
+            if lv == 0:
+                break                                    # upstream still up-projects the last level; nothing reads it
+            back = self._backwards[lv]
+            if isinstance(back, nn.Identity):
+                current = self._dequantizers[lv].decode_act(code, {"f32"}, eng)
+            else:
+                q = self._dequantizers[lv].decode_act(code, eng.needs_of(back[0]), eng)
+                current = eng.run_seq(back, q, {"f32"})
+        return codes
+
+    def decode_act(self, eng: Engine, codes: List[torch.Tensor], final_needs, status=None) -> Act:
+        """quantizer.py:695-703 (codes smallest level first)."""
+        levels = len(self._decoders)
+        if len(codes) != levels:
+            raise RuntimeError(f"expected {levels} code levels, got {len(codes)}")
+        former: Optional[Act] = None
+        for lv, code in zip(reversed(range(levels)), codes):
+            dec = self._decoders[lv]
+            needs = eng.needs_of(dec[0])
+            if former is None:
+                q = self._dequantizers[lv].decode_act(code, needs, eng, status)
+            else:
+                q0 = self._dequantizers[lv].decode_act(code, {"f32"}, eng, status)
+                if (q0.n, q0.h, q0.w, q0.c) != (former.n, former.h, former.w, former.c):
+                    raise RuntimeError(f"code level of grid {q0.h}x{q0.w} does not continue a {former.h}x{former.w} "
+                                       "reconstruction")
+                q = eng.add_scaled(q0.f32, former.f32, 1.0, (q0.n, q0.h, q0.w, q0.c), needs)
+            former = eng.run_seq(dec, q, final_needs if lv == 0 else {"f32"})
+        return former
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor) -> List[torch.Tensor]:
+        eng = default_engine()
+        codes = self.encode_act(eng, eng.from_nchw(x, self.first_needs(eng)))
+        eng.flush()
+        return codes
+
+    @torch.no_grad()
+    def decode(self, codes: List[torch.Tensor]) -> torch.Tensor:
+        eng = default_engine()
+        return eng.to_nchw(self.decode_act(eng, codes, {"f32"}))
+
+    @torch.no_grad()
+    def residual_backward(self, code: torch.Tensor, level: int) -> torch.Tensor:
+        """quantizer.py:670-673: up-projection of one level's codes, indexed from the END like upstream
+        (`self._dequantizers[-level]`)."""
+        eng = default_engine()
+        dq, back = self._dequantizers[-level], self._backwards[-level]
+        if isinstance(back, nn.Identity):
+            return dq.decode(code)
+        return eng.to_nchw(eng.run_seq(back, dq.decode_act(code, eng.needs_of(back[0]), eng), {"f32"}))
+
+    @torch.no_grad()
+    def residual_forward(self, code: torch.Tensor, formerLevel: Optional[torch.Tensor], level: int) -> torch.Tensor:
+        """quantizer.py:705-712"""
+        if formerLevel is None and level > 0:
+            raise RuntimeError("For reconstruction after level-0, you should provide not None formerLevel as input.")
+        if formerLevel is not None and level == 0:
+            raise RuntimeError("For reconstruction at level-0, you should provide None formerLevel as input.")
+        eng = default_engine()
+        dec, dq = self._decoders[-(level + 1)], self._dequantizers[-(level + 1)]
+        needs = eng.needs_of(dec[0])
+        if formerLevel is None:
+            q = dq.decode_act(code, needs, eng)
+        else:
+            q0 = dq.decode_act(code, {"f32"}, eng)
+            former = eng.from_nchw(formerLevel, {"f32"})
+            q = eng.add_scaled(q0.f32, former.f32, 1.0, (q0.n, q0.h, q0.w, q0.c), needs)
+        return eng.to_nchw(eng.run_seq(dec, q, {"f32"}))

@@ -16,9 +16,9 @@ def conv3x3(inChannels: int, outChannels: int, stride: int = 1, bias: bool = Tru
 
 
 def conv1x1(inChannels: int, outChannels: int, stride: int = 1, bias: bool = True, groups: int = 1) -> nn.Conv2d:
-    if groups != 1 or not bias or stride != 1:
-        raise NotImplementedError("mcquic_b200: only groups=1, bias=True, stride=1 1x1 convolutions are accelerated")
-    return nn.Conv2d(inChannels, outChannels, kernel_size=1)
+    if groups != 1 or stride != 1:
+        raise NotImplementedError("mcquic_b200: only groups=1, stride=1 1x1 convolutions are accelerated")
+    return nn.Conv2d(inChannels, outChannels, kernel_size=1, bias=bias)
 
 
 def pixelShuffle3x3(inChannels: int, outChannels: int, r: float = 1, groups: int = 1) -> nn.Sequential:

@@ -74,8 +74,16 @@ def synthetic_block_state(template: Dict[str, torch.Tensor], tag: str, seed: int
     for key, ref in template.items():
         shape = tuple(ref.shape)
         name = f"{tag}.{key}"
-        if key.endswith(".weight") and len(shape) == 4:
+        if key.endswith("._codebook"):
+            # every codebook key of a ResidualBackwardQuantizer aliases ONE [1, k, d] tensor (quantizer.py:596)
+            std = (2.0 / (5.0 * shape[-1])) ** 0.5
+            out[key] = uniform(shape, f"{tag}.codebook", seed) * (std * 3.0 ** 0.5)
+        elif key.endswith(".weight") and len(shape) == 4:
             out[key] = uniform(shape, name, seed) / (shape[1] * shape[2] * shape[3]) ** 0.5
+        elif key.endswith(".gamma"):
+            out[key] = ref.clone() + uniform(shape, name, seed).abs() * 0.02
+        elif key.endswith(".beta"):
+            out[key] = ref.clone() + uniform(shape, name, seed).abs() * 0.1
         elif key.endswith(".bias") and template[key[:-4] + "weight"].dim() == 4:
             w = template[key[:-4] + "weight"]
             out[key] = uniform(shape, name, seed) / (w.shape[1] * w.shape[2] * w.shape[3]) ** 0.5

@@ -104,10 +104,36 @@ def blocks():
     np.savez_compressed(os.path.join(OUT, "blocks_dense.npz"), **rec)
 
 
+def neon():
+    """tests/golden/neon_*.npz: the reference's own `Neon` (compressor.py:181-233) on tests/common.py:NEON_CASES."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import NEON_CASES, neon_inputs
+    ref_import.load()
+    from mcquic.modules.compressor import Neon
+    torch.set_num_threads(8)
+    for name, (c, k, size, dense, n, h, w) in NEON_CASES.items():
+        model, x = neon_inputs(name, Neon)
+        with torch.inference_mode():
+            codes = model.encode(x)
+            xhat = model.decode(codes)
+        _, margins = O.neon_encode(model.state_dict(), x, size, with_margin=True)
+        rec = {"xhat": xhat.numpy().astype(np.float32), "xhat_sha256": np.array(sha(xhat)),
+               "codes_sha256": np.array(sha(torch.cat([q.flatten() for q in codes])))}
+        for j, (q, mg) in enumerate(zip(codes, margins)):
+            rec[f"codes_{j}"] = q.numpy().astype(np.int32)
+            rec[f"margin_{j}"] = mg.numpy().astype(np.float32)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, [tuple(q.shape) for q in codes], tuple(xhat.shape), "min margin", min(float(mg.min()) for mg in margins),
+              "xhat absmax", float(xhat.abs().max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if "--blocks" in sys.argv:
         blocks()
+    elif "--neon" in sys.argv:
+        neon()
     else:
         main()
         blocks()
+        neon()

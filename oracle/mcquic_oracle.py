@@ -226,6 +226,104 @@ def decode(sd: StateDict, codes: List[torch.Tensor]) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
+# `Neon` tokenizer: mcquic/modules/compressor.py:181-233 + ResidualBackwardQuantizer,
+# mcquic/modules/quantizer.py:577-700.  Every ResidualBlock / AttentionBlock carries (groups, denseNorm); GroupNorm
+# groups are 32 in the trunk and 1 inside the quantizer and for the blocks that touch its 8 channels.
+NEON_LATENT = 8  # ResidualBackwardQuantizer.channel, quantizer.py:583
+
+
+def _rb(groups):
+    return lambda sd, p, x: residual_block(sd, p, x, groups)
+
+
+def _ab(groups):
+    return lambda sd, p, x: attention_block(sd, p, x, groups)
+
+
+def _conv_nobias(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:   # conv1x1(..., bias=False), convs.py:257-276
+    return F.conv2d(x, sd[p + ".weight"], None)
+
+
+# compressor.py:186-206
+def neon_analysis(sd: StateDict, x: torch.Tensor) -> torch.Tensor:
+    x = _conv(sd, "_encoder.0", x)
+    blocks = [_ab(32), _rb(32), _rb(32), _RBS, _rb(32), _RBS, _rb(32), _RBS, _ab(32), _rb(32), _rb(32), _rb(32), _rb(32),
+              _rb(1), _ab(1)]
+    return _run_from(sd, "_encoder", 1, blocks, x)
+
+
+# compressor.py:207-227
+def neon_synthesis(sd: StateDict, y: torch.Tensor) -> torch.Tensor:
+    blocks = [_ab(1), _rb(1), _rb(32), _rb(32), _rb(32), _rb(32), _ab(32), _rb(32), _RBU, _rb(32), _RBU, _rb(32), _RBU,
+              _rb(32), _rb(32), _ab(32)]
+    y = _run_from(sd, "_decoder", 0, blocks, y)
+    return _conv(sd, "_decoder.16", y)
+
+
+def _neon_strided(size: Sequence[int]) -> List[bool]:
+    """per level: does its stage halve the resolution (quantizer.py:600-657: thisSize == lastSize // 2)"""
+    out, last = [], size[0] * 2
+    for this in size:
+        if this not in (last, last // 2):
+            raise ValueError("The given size sequence does not half or equal to from left to right.")
+        out.append(this == last // 2)
+        last = this
+    return out
+
+
+# quantizer.py:600-657 -- the three per-level nets; the middle block is strided / shuffling or a plain ResidualBlock
+def _neon_stage(sd, p, x, strided):
+    return _conv_nobias(sd, p + ".3", _run_from(sd, p, 0, [_rb(1), _ab(1), _RBS if strided else _rb(1)], x))
+
+
+def _neon_up(sd, p, x, strided):
+    x = _conv_nobias(sd, p + ".0", x)
+    return _run_from(sd, p, 1, [_RBU if strided else _rb(1), _ab(1), _rb(1)], x)
+
+
+# quantizer.py:675-693 (ResidualBackwardQuantizer.encode): all latents first, then residual codes from the smallest
+# level back to the largest; codes are returned smallest level first
+def neon_quantizer_encode(sd: StateDict, y: torch.Tensor, size: Sequence[int], with_margin: bool = False):
+    strided = _neon_strided(size)
+    latents, x = [], y
+    for lv in range(len(size)):
+        x = _neon_stage(sd, f"_quantizer._encoders.{lv}", x, strided[lv])
+        latents.append(x)
+    codes, margins = [], []
+    current = torch.zeros_like(latents[-1])
+    for lv in reversed(range(len(size))):
+        cb = sd[f"_quantizer._quantizers.{lv}._codebook"]
+        residual = latents[lv] - current
+        code = vq_assign(residual, cb)
+        codes.append(code)
+        if with_margin:
+            margins.append(vq_margin(residual, cb))
+        quantized = vq_dequantize(code, cb)
+        current = quantized if lv == len(size) - 1 else _neon_up(sd, f"_quantizer._backwards.{lv}", quantized, strided[lv])
+    return (codes, margins) if with_margin else codes
+
+
+# quantizer.py:695-703 (ResidualBackwardQuantizer.decode); codes smallest level first
+def neon_quantizer_decode(sd: StateDict, codes: List[torch.Tensor], size: Sequence[int]) -> torch.Tensor:
+    strided = _neon_strided(size)
+    former: Optional[torch.Tensor] = None
+    for lv, code in zip(reversed(range(len(size))), codes):
+        q = vq_dequantize(code, sd[f"_quantizer._dequantizers.{lv}._codebook"])
+        former = _neon_up(sd, f"_quantizer._decoders.{lv}", q if former is None else q + former, strided[lv])
+    return former
+
+
+@torch.inference_mode()
+def neon_encode(sd: StateDict, x: torch.Tensor, size: Sequence[int], with_margin: bool = False):
+    return neon_quantizer_encode(sd, neon_analysis(sd, aligned_padding(x)), size, with_margin)
+
+
+@torch.inference_mode()
+def neon_decode(sd: StateDict, codes: List[torch.Tensor], size: Sequence[int]) -> torch.Tensor:
+    return neon_synthesis(sd, neon_quantizer_decode(sd, codes, size))
+
+
+# ----------------------------------------------------------------------------------------------
 # mcquic/validate/handlers.py:138-172 (IdealBPP: torch.bincount per level/codebook) and the counting half of
 # mcquic/modules/entropyCoder.py:28-36 (one-hot .sum((0,2,3)) == per-(m, k) occurrence count).
 def code_histogram(codes: List[torch.Tensor], ks: Sequence[int]) -> List[torch.Tensor]:

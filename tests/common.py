@@ -75,3 +75,19 @@ def dense_block_oracle(name, sd, x):
 
 def _prefixed(sd):
     return {"b." + k: v for k, v in sd.items()}
+
+
+# `Neon` tokenizer cases (BASELINE configs[4] family at test size): name -> (channel, k, size, denseNorm, n, h, w)
+NEON_CASES = {
+    "neon_c32_gn": (32, 64, [16, 16, 8, 8], True, 2, 100, 128),     # GroupNorm everywhere, reflect padding, SIMT convs
+    "neon_c64_plain": (64, 128, [8, 8], False, 1, 128, 128),        # SiLU blocks, tensor-core trunk (C = 64 / 128)
+}
+
+
+def neon_inputs(name, cls):
+    """(model with deterministic weights, image batch) for one NEON_CASES entry; cls = the Neon class to build."""
+    from mcquic_b200.utils.synthetic import synthetic_block_state
+    c, k, size, dense, n, h, w = NEON_CASES[name]
+    model = cls(c, k, list(size), dense).eval()
+    model.load_state_dict(synthetic_block_state(model.state_dict(), name, seed=0))
+    return model, uniform((n, 3, h, w), name + ".image", 1)

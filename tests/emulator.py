@@ -192,6 +192,17 @@ class EmulatedLib:
         self.launches += 1
         return 0
 
+    def mcq_add_scaled(self, x, y, alpha, count, out_f32, out_hi, out_lo, act, stream):
+        a = torch.from_numpy(_arr(x.value, (count,), np.float32).copy())
+        b = torch.from_numpy(_arr(y.value, (count,), np.float32).copy())
+        v = (a.double() + float(alpha) * b.double()).float()      # one rounding, like the kernel's FFMA
+        q = lambda t: t.value if t is not None and t.value else 0
+        if q(out_f32):
+            _arr(q(out_f32), (count,), np.float32)[...] = v.numpy()
+        _store_planes(q(out_hi), q(out_lo), (count,), v, act)
+        self.launches += 1
+        return 0
+
     def mcq_split_planes(self, x, count, act, out_hi, out_lo, stream):
         y = torch.from_numpy(_arr(x.value, (count,), np.float32).copy())
         _store_planes(out_hi.value, out_lo.value if out_lo is not None and out_lo.value else 0, (count,), y, act)

@@ -1,0 +1,237 @@
+"""`Neon` tokenizer + `ResidualBackwardQuantizer` (mcquic/modules/compressor.py:181-233,
+mcquic/modules/quantizer.py:577-765) and the codebook maintenance of SURVEY 8f NEXT-4 (quantizer.py:111-142).
+
+CPU: state_dict layout == the reference's; the oracle restatement == the reference (bit for bit, where /root/reference
+exists) == the committed reference outputs tests/golden/neon_*.npz (oracle/gen_golden.py --neon); the product's host
+logic against the CPU model of the C ABI; reAssignCodebook against the reference method under the same RNG seed;
+syncCodebook over a 2-rank gloo group.  GPU: encode/decode through the C ABI against the golden vectors.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import GOLDEN, NEON_CASES, neon_inputs
+from emulator import EmulatedLib
+from mcquic_b200 import Neon, _lib
+from mcquic_b200.engine import Engine
+from mcquic_b200.modules.quantizer import _multiCodebookQuantization
+from oracle import mcquic_oracle as O
+from oracle import ref_import
+
+PIXEL_TOL = 2e-5        # relative to the output range: Neon decodes with the fp32-grade 3-pass path by default
+ONE_PASS_TOL = 5e-3     # opt-in 1-pass (fp16 operands, TF32-grade) decode: 57 conv layers and 50 GroupNorms deep, the
+                        # operand rounding accumulates to ~2.5e-3 of the output range (measured on the CPU model)
+MARGIN_TIE = 2e-6       # a code flip at a relative top-2 distance gap below this is fp32 rounding, not a bug
+
+
+def _golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    levels = len(NEON_CASES[name][2])
+    codes = [torch.from_numpy(g[f"codes_{j}"].astype(np.int64)) for j in range(levels)]
+    margins = [torch.from_numpy(g[f"margin_{j}"]) for j in range(levels)]
+    return g, codes, margins
+
+
+def _flips(codes, ref, margins):
+    at = []
+    for a, b, mg in zip(codes, ref, margins):
+        assert a.dtype == torch.int64 and tuple(a.shape) == tuple(b.shape)
+        at += mg[a.cpu() != b].tolist()
+    return at
+
+
+@pytest.mark.parametrize("name", list(NEON_CASES))
+def test_oracle_reproduces_reference_golden(name):
+    size = NEON_CASES[name][2]
+    model, x = neon_inputs(name, Neon)
+    sd = model.state_dict()
+    g, ref, margins = _golden(name)
+    codes = O.neon_encode(sd, x, size)
+    assert _flips(codes, ref, margins) == []
+    xhat = O.neon_decode(sd, ref, size)
+    assert float((xhat - torch.from_numpy(g["xhat"])).abs().max()) <= 2e-6
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+@pytest.mark.parametrize("name", list(NEON_CASES))
+def test_oracle_and_state_dict_against_the_reference_itself(name):
+    ref_import.load()
+    from mcquic.modules.compressor import Neon as RefNeon
+    size = NEON_CASES[name][2]
+    ref_model, x = neon_inputs(name, RefNeon)
+    mine, _ = neon_inputs(name, Neon)
+    rsd, msd = ref_model.state_dict(), mine.state_dict()
+    assert list(rsd) == list(msd)                                          # same keys, same order
+    assert all(rsd[k].shape == msd[k].shape and rsd[k].dtype == msd[k].dtype for k in rsd)
+    assert all(torch.equal(rsd[k], msd[k]) for k in rsd)                   # same deterministic weights
+    with torch.inference_mode():
+        codes = ref_model.encode(x)
+        xhat = ref_model.decode(codes)
+    assert all(torch.equal(a, b) for a, b in zip(codes, O.neon_encode(rsd, x, size)))
+    assert torch.equal(xhat, O.neon_decode(rsd, codes, size))
+    g, gcodes, _ = _golden(name)
+    assert all(torch.equal(a, b) for a, b in zip(codes, gcodes))
+    assert torch.equal(xhat, torch.from_numpy(g["xhat"]))
+
+
+@pytest.mark.parametrize("name", list(NEON_CASES))
+def test_host_logic_through_emulated_abi(name):
+    c, k, size, dense, n, h, w = NEON_CASES[name]
+    model, x = neon_inputs(name, Neon)
+    model._engine = Engine(lib=EmulatedLib())
+    g, ref, margins = _golden(name)
+    hist = torch.zeros(len(size) * k, dtype=torch.int32)
+    codes = model.encode(x, hist=hist)
+    at = _flips(codes, ref, margins)
+    assert at == [] or max(at) < MARGIN_TIE, at
+    assert all(cd.is_contiguous() for cd in codes)
+    # histogram segment j counts codes[j] (the order of the entropy coder's _freqEMA, quantizer.py:616)
+    exp = torch.cat([torch.bincount(cd.flatten(), minlength=k) for cd in codes]).int()
+    assert torch.equal(hist, exp)
+    xref = torch.from_numpy(g["xhat"])
+    scale = max(1.0, float(xref.abs().max()))
+    assert model.decode_passes == 3
+    assert float((model.decode(ref) - xref).abs().max()) <= PIXEL_TOL * scale
+    model.decode_passes = 1
+    assert float((model.decode(ref) - xref).abs().max()) <= ONE_PASS_TOL * scale
+    with pytest.raises(RuntimeError):
+        model.decode(ref[:-1])
+    with pytest.raises(NotImplementedError):
+        model.compress(x)                                # VariousMCoder.compress raises upstream too
+    # the stage-2 generators' entry points (compressor.py:235-241), smallest level = level 0 of residual_forward
+    from mcquic_b200 import engine as E
+    old, E._DEFAULT = E._DEFAULT, model.engine
+    try:
+        model.engine.passes = 3
+        sd = model.state_dict()
+        lv = len(size) - 1
+        first = model.residual_forward(ref[0], None, 0)
+        want = O._neon_up(sd, f"_quantizer._decoders.{lv}", O.vq_dequantize(ref[0], sd["_quantizer._dequantizers.0._codebook"]),
+                          O._neon_strided(size)[lv])
+        assert float((first - want).abs().max()) <= 2e-5
+        second = model.residual_forward(ref[1], first, 1)
+        assert tuple(second.shape[:2]) == (n, 8)
+        with pytest.raises(RuntimeError):
+            model.residual_forward(ref[1], None, 1)
+        with pytest.raises(RuntimeError):
+            model.residual_forward(ref[0], first, 0)
+    finally:
+        E._DEFAULT = old
+
+
+def test_size_sequence_is_validated_like_upstream():
+    with pytest.raises(ValueError, match="does not half or equal"):
+        Neon(32, 16, [16, 4], True)
+
+
+# ------------------------------------------------------------------------------------------------ NEXT-4
+def test_reassign_codebook_few_unused():
+    torch.manual_seed(3)
+    cb = torch.nn.Parameter(torch.randn(2, 8, 4))
+    q = _multiCodebookQuantization(cb)
+    before = cb.detach().clone()
+    freq = torch.tensor([[.3, .0, .2, .1, .05, .0, .25, .1], [.125] * 8])
+    moved = q.reAssignCodebook(freq)
+    # codebook 0: slots 1 and 5 were never used -> overwritten by the two most used codewords (0, then 6)
+    assert torch.equal(cb[0, 1], before[0, 0]) and torch.equal(cb[0, 5], before[0, 6])
+    keep = [0, 2, 3, 4, 6, 7]
+    assert torch.equal(cb[0, keep], before[0, keep]) and torch.equal(cb[1], before[1])
+    assert moved.dtype == torch.bool and moved.shape == (16,) and moved.nonzero().flatten().tolist() == [1, 5]
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+@pytest.mark.parametrize("unused", [2, 11])
+def test_reassign_codebook_matches_reference_method(unused):
+    """same codebook, same frequencies, same torch RNG seed -> identical codebook and mask, including the branch that
+    spares a random half when more than k/2 codewords were never used (quantizer.py:118-125)"""
+    ref_import.load()
+    from mcquic.modules.quantizer import _multiCodebookQuantization as RefQ
+    torch.manual_seed(11)
+    init = torch.randn(3, 16, 8)
+    freq = torch.rand(3, 16)
+    freq[:, :unused] = 0
+    freq[1] = freq[1][torch.randperm(16)]
+    freq = freq / freq.sum(-1, keepdim=True)
+    mine = _multiCodebookQuantization(torch.nn.Parameter(init.clone()))
+    ref = RefQ(torch.nn.Parameter(init.clone()), None)
+    torch.manual_seed(5)
+    a = mine.reAssignCodebook(freq.clone())
+    torch.manual_seed(5)
+    b = ref.reAssignCodebook(freq.clone())
+    assert torch.equal(a, b) and torch.equal(mine._codebook.data, ref._codebook.data)
+    assert bool(a.any())
+
+
+def _sync_worker(rank, world, port, out):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                       # ranks start from different codebooks
+        model = Neon(32, 16, [8, 8], False)
+        model.syncCodebook()
+        out[rank] = [cb.detach().clone() for cb in model.Codebooks]
+        freq = [f.clone() for f in model.NormalizedFreq]
+        assert float(model.CodeUsage) == 1.0 and all(abs(float(f.sum()) - 1.0) < 1e-5 for f in freq)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sync_codebook_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 1000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_sync_worker, args=(2, port, out), nprocs=2, join=True)
+        a, b = out[0], out[1]
+    assert len(a) == 2 and all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(NEON_CASES))
+@pytest.mark.parametrize("graphs", [False, True])
+def test_gpu_neon_against_reference_golden(name, graphs):
+    c, k, size, dense, n, h, w = NEON_CASES[name]
+    model, x = neon_inputs(name, Neon)
+    model = model.cuda()
+    model.use_graphs = graphs
+    g, ref, margins = _golden(name)
+    before = _lib.launch_count() + model.graph_launches
+    hist = torch.zeros(len(size) * k, dtype=torch.int32, device="cuda")
+    codes = model.encode(x.cuda(), hist=hist)
+    if graphs:
+        codes2 = model.encode(x.cuda())                      # pure replay
+        assert all(torch.equal(a, b) for a, b in zip(codes, codes2))
+    at = _flips(codes, ref, margins)
+    assert at == [] or max(at) < MARGIN_TIE, f"code indices differ from the reference's at margins {at}"
+    assert all(cd.is_cuda and cd.is_contiguous() for cd in codes)
+    exp = torch.cat([torch.bincount(cd.flatten().cpu(), minlength=k) for cd in codes]).int()
+    assert torch.equal(hist.cpu(), exp)
+    xref = torch.from_numpy(g["xhat"])
+    scale = max(1.0, float(xref.abs().max()))
+    xhat = model.decode([cd.cuda() for cd in ref])
+    assert tuple(xhat.shape) == tuple(xref.shape)
+    assert float((xhat.cpu() - xref).abs().max()) <= PIXEL_TOL * scale
+    model.decode_passes = 1
+    assert float((model.decode([cd.cuda() for cd in ref]).cpu() - xref).abs().max()) <= ONE_PASS_TOL * scale
+    assert _lib.launch_count() + model.graph_launches - before >= 100         # the CUDA path really ran
+    assert model.engine.lib.mcq_device_error_flag() == 0
+    with pytest.raises(RuntimeError):
+        model.encode(x)                                      # CPU tensor: no fallback
+
+
+@pytest.mark.gpu
+def test_gpu_add_scaled():
+    eng = Engine("tcgen05")
+    eng.passes = 3
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.randn(3, 5, 7, 8, generator=g).cuda(), torch.randn(3, 5, 7, 8, generator=g).cuda()
+    out = eng.add_scaled(x, y, -1.0, (3, 5, 7, 8), {"f32", "raw"})
+    assert torch.equal(out.f32, x - y)                       # one rounding: exactly the reference's subtraction
+    rec = out.raw[0].double() + out.raw[1].double() / 2048.0
+    assert float((rec - (x - y).double()).abs().max()) <= 2.0 ** -19 * float((x - y).abs().max())
+    assert torch.equal(eng.add_scaled(x, y, 1.0, (3, 5, 7, 8), {"f32"}).f32, x + y)
+    with pytest.raises(RuntimeError):
+        eng.add_scaled(x, y[:2], 1.0, (3, 5, 7, 8), {"f32"})
