@@ -77,6 +77,13 @@ typedef struct mcq_conv_params {
   int32_t impl;     /* MCQ_IMPL_* */
   void* ev_start;   /* optional cudaEvent_t recorded on the stream immediately before / after the kernel launch */
   void* ev_stop;    /* (tight per-launch timing for bench.py's roofline leg); NULL = none */
+  /* optional: GroupNorm statistics fused into this convolution's epilogue (the conv3x3 in front of the nn.GroupNorm
+   * of ResidualBlock(denseNorm=True), mcquic/nn/blocks.py:196-199).  When gn_partials != NULL the kernel also writes
+   * (sum y, sum y^2) of its fp32 output y per (row block of 32 output pixels, `unit` consecutive channels) as
+   * float2 [n][rowblocks_per_image][cout / unit]; layout from mcq_conv_gn_layout(), consumer mcq_groupnorm_apply().
+   * Every entry is written exactly once (no atomics, no clearing needed). */
+  void* gn_partials;
+  int32_t gn_groups; /* group count of the GroupNorm that follows */
 } mcq_conv_params;
 
 /* Replaces nn.Conv2d 3x3 / 1x1 (+ the elementwise ops around it) as used by mcquic/nn/blocks.py:62-288,
@@ -160,6 +167,20 @@ int mcq_code_histogram(const int64_t* codes, int32_t n, int32_t m, int32_t hw, i
 int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t groups, const float* gamma,
                   const float* beta, float eps, float* out_f32, void* out_hi, void* out_lo, int32_t out_act,
                   mcq_stream_t stream);
+
+/* GroupNorm with the statistics pass fused into the producing convolution (north_star: "GroupNorm ... fused into the
+ * epilogue").  mcq_conv_gn_layout: can the convolution described by p (shape, kernel, stride, store, mode, impl,
+ * gn_groups; pointers other than out_f32 are not inspected) emit the partials?  0 = yes (sizes returned),
+ * MCQ_ERR_UNSUPPORTED = no -> run the convolution without gn_partials and use mcq_groupnorm.
+ * mcq_groupnorm_apply: reduces the partials in a fixed order in double (bit-reproducible) into stats
+ * (float2 [n][groups] = mean, rstd; caller-allocated) and normalises x in ONE streaming pass:
+ * y = x * (rstd * gamma) + (beta - mean * rstd * gamma) -> fp32 and/or split-fp16 planes of act(y).
+ * HBM traffic: x once in, outputs once out (mcq_groupnorm reads x twice). */
+int mcq_conv_gn_layout(const mcq_conv_params* p, int32_t* rowblocks_per_image, int32_t* unit);
+int mcq_groupnorm_apply(const float* x, const void* partials, int32_t rowblocks_per_image, int32_t unit, int32_t n,
+                        int32_t h, int32_t w, int32_t c, int32_t groups, const float* gamma, const float* beta,
+                        float eps, void* stats, float* out_f32, void* out_hi, void* out_lo, int32_t out_act,
+                        mcq_stream_t stream);
 
 /* out = x + alpha * y over `count` fp32 values (count % 4 == 0), written as fp32 and/or as the split-fp16 planes of
  * act(out).  Replaces the two element-wise steps of ResidualBackwardQuantizer that no convolution epilogue can absorb:

@@ -26,6 +26,7 @@ class ConvParams(_c.Structure):
         ("out1_hi", _c.c_void_p), ("out1_lo", _c.c_void_p), ("out1_act", _c.c_int32),
         ("passes", _c.c_int32), ("impl", _c.c_int32),
         ("ev_start", _c.c_void_p), ("ev_stop", _c.c_void_p),
+        ("gn_partials", _c.c_void_p), ("gn_groups", _c.c_int32),
     ]
 
 
@@ -51,6 +52,8 @@ SYMBOLS = {
     "mcq_vq_dequant": (_c.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _i32, _p, _p]),
     "mcq_code_histogram": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "mcq_groupnorm": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _p, _p, _i32, _p]),
+    "mcq_conv_gn_layout": (_c.c_int, [_c.POINTER(ConvParams), _c.POINTER(_i32), _c.POINTER(_i32)]),
+    "mcq_groupnorm_apply": (_c.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _p, _p, _p, _i32, _p]),
     "mcq_add_scaled": (_c.c_int, [_p, _p, _f, _i64, _p, _p, _p, _i32, _p]),
     "mcq_split_planes": (_c.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "mcq_nchw_to_nhwc": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _i32, _p]),

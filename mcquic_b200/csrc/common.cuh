@@ -51,6 +51,10 @@ struct ConvArgs {
   int debug_skip_store;           // MCQ_EPI_SKIP=1: drain TMEM but store nothing (profiling aid)
   int wait_sleep_ns;              // nanosleep between mbarrier polls of the producer / drain warps (MCQ_WAIT_SLEEP_NS)
   int direct_epilogue;            // 1 (default): transpose-free drain where it applies, see drain_tile (MCQ_DIRECT_EPI=0: off)
+  // GroupNorm statistics fused into the drain (pair kernel, GN instantiation only): every drain warp writes, per
+  // gn_unit consecutive channels, (sum y, sum y^2) over its 32 pixels to gn_ws[(n * gn_rb + row block) * gn_units + unit]
+  float2* gn_ws;
+  int gn_unit, gn_units, gn_rb;
   // per-tap TMA coordinate offsets in the 5-D view of A (see conv_tc.cuh)
   int tap_c[9], tap_dx[9], tap_py[9], tap_dy[9];
 };

@@ -72,7 +72,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
       : "memory");
 }
 
-template <int PASSES>
+template <int PASSES, bool GN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi_full, const __grid_constant__ CUtensorMap tmB_lo_full,
@@ -313,7 +313,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       mbar_wait(tfull_bar(buf), use & 1u, 26, p.wait_sleep_ns);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias);
+      drain_tile<PASSES, GN>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

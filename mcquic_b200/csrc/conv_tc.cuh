@@ -195,7 +195,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // the fused epilogue runs with 2 lanes per pixel x 8 consecutive channels each: residual / aux loads and all stores
 // are 64 B-contiguous per pixel (16 lines per instruction -> full sectors).
 // pix(row, n, oy, ox) -> valid maps a tile row to its output pixel.
-template <int PASSES, class PixFn>
+template <int PASSES, bool GN = false, class PixFn>
 __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, int bn, int ct, int cg, int q, int lane,
                                            uint32_t stage, PixFn pix, const float* bias_src) {
   int n_[2], oy_[2], ox_[2];
@@ -285,7 +285,8 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
 #pragma unroll
           for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
         }
-        if (!live) continue;
+        float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};   // GN: this lane's sums per channel quad
+        if (live) {
         {
           float b[16];
           load_f32v<16>(bias_src, c0, b);
@@ -338,6 +339,47 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
 #pragma unroll
             for (int j = 0; j < 8; ++j) h[j] = f2h2_sat(t[2 * j], t[2 * j + 1]);
             st_global_256(hi_p + off, h);
+          }
+        }
+        if constexpr (GN) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            gs[u] = (y[4 * u] + y[4 * u + 1]) + (y[4 * u + 2] + y[4 * u + 3]);
+            gq[u] = fmaf(y[4 * u + 3], y[4 * u + 3], fmaf(y[4 * u + 2], y[4 * u + 2],
+                         fmaf(y[4 * u + 1], y[4 * u + 1], y[4 * u] * y[4 * u])));
+          }
+        }
+        }   // live
+        if constexpr (GN) {
+          // GroupNorm partials of the fp32 output: (sum, sum of squares) per gn_unit channels over this warp's 32 pixels
+          // (dead lanes contribute zeros), fixed reduction order -> bit-reproducible; one float2 store per unit.
+          if (p.gn_ws != nullptr && c0 < p.cout) {          // warp-uniform
+            const int unit = p.gn_unit;                    // 4, 8 or 16 channels
+            if (unit >= 8) {
+              gs[0] += gs[1]; gq[0] += gq[1];
+              gs[1] = gs[2] + gs[3]; gq[1] = gq[2] + gq[3];
+            }
+            if (unit == 16) { gs[0] += gs[1]; gq[0] += gq[1]; }
+            const int nu = 16 / unit;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (u < nu) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  gs[u] += __shfl_xor_sync(0xffffffffu, gs[u], o);
+                  gq[u] += __shfl_xor_sync(0xffffffffu, gq[u], o);
+                }
+              }
+            }
+            const int n0 = __shfl_sync(0xffffffffu, n, 0), oy0 = __shfl_sync(0xffffffffu, oy, 0);
+            const int ox0 = __shfl_sync(0xffffffffu, ox, 0);
+            const bool ok0 = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;     // lane 0 = first pixel of the row block
+            if (ok0 && lane < nu) {
+              const int rb = (oy0 / (32 / p.tw)) * p.tiles_x + ox0 / p.tw;
+              const float sv = lane == 0 ? gs[0] : lane == 1 ? gs[1] : lane == 2 ? gs[2] : gs[3];
+              const float qv = lane == 0 ? gq[0] : lane == 1 ? gq[1] : lane == 2 ? gq[2] : gq[3];
+              p.gn_ws[((size_t)n0 * p.gn_rb + rb) * p.gn_units + c0 / unit + lane] = make_float2(sv, qv);
+            }
           }
         }
       }

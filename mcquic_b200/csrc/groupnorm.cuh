@@ -164,4 +164,88 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const GroupNormAr
   }
 }
 
+// ---- GroupNorm from statistics the producing convolution's epilogue already accumulated (drain_tile<.., GN = true>):
+// partials float2 [n][rb][units] = (sum y, sum y^2) per (32-pixel row block, `unit` consecutive channels).
+// gn_finalize_kernel: one CTA per (group, image) sums its partials in a fixed order in double -> stats[n][groups] =
+// (mean, rstd).  gn_apply_kernel: one streaming pass, y = x * (rstd * gamma) + (beta - mean * rstd * gamma).
+struct GroupNormApplyArgs {
+  const float* x;
+  const float2* partials;
+  float2* stats;
+  const float* gamma;
+  const float* beta;
+  float* out_f32;
+  __half* o_hi;
+  __half* o_lo;
+  int o_act;
+  int n, hw, c, groups, rb, unit;
+  float eps;
+};
+
+constexpr int GNF_THREADS = 256;
+
+__global__ void __launch_bounds__(GNF_THREADS) gn_finalize_kernel(const GroupNormApplyArgs a) {
+  __shared__ double red_s[GNF_THREADS], red_q[GNF_THREADS];
+  const int g = blockIdx.x, img = blockIdx.y;
+  const int cg_ = a.c / a.groups;
+  const int upg = cg_ / a.unit;                      // units per group
+  const int units = a.c / a.unit;
+  const float2* src = a.partials + (size_t)img * a.rb * units + (size_t)g * upg;
+  double S = 0.0, Q = 0.0;
+  const int total = a.rb * upg;
+  for (int i = threadIdx.x; i < total; i += GNF_THREADS) {
+    const float2 v = src[(size_t)(i / upg) * units + (i % upg)];
+    S += (double)v.x;
+    Q += (double)v.y;
+  }
+  red_s[threadIdx.x] = S;
+  red_q[threadIdx.x] = Q;
+  __syncthreads();
+  for (int o = GNF_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      red_s[threadIdx.x] += red_s[threadIdx.x + o];
+      red_q[threadIdx.x] += red_q[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double cnt = (double)a.hw * (double)cg_;
+    const double mean = red_s[0] / cnt;
+    double var = red_q[0] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    a.stats[(size_t)img * a.groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+  }
+}
+
+// One block = `ppb` consecutive pixels of one image (blockIdx.y); a thread keeps one channel quad, so its scale / shift
+// are computed once and the loop body is a load, four FFMAs, the split and the stores (32-bit index arithmetic only:
+// the first version spent 160 instructions per float4 on 64-bit div/mod and was issue-bound at 3.8 TB/s).
+constexpr int GNA_THREADS = 256;
+
+__global__ void __launch_bounds__(GNA_THREADS) gn_apply_kernel(const GroupNormApplyArgs a, int ppb) {
+  const int img = blockIdx.y;
+  const int c4 = a.c >> 2;
+  const int rows = GNA_THREADS / c4;
+  const int t = threadIdx.x;
+  if (t >= rows * c4) return;
+  const int q = t % c4, r = t / c4;
+  const int ch = 4 * q;
+  const float2 st = a.stats[(size_t)img * a.groups + ch / (a.c / a.groups)];   // channels per group % 4 == 0
+  const float4 gm = *reinterpret_cast<const float4*>(a.gamma + ch);
+  const float4 bt = *reinterpret_cast<const float4*>(a.beta + ch);
+  const float sc[4] = {st.y * gm.x, st.y * gm.y, st.y * gm.z, st.y * gm.w};
+  const float sh[4] = {fmaf(-sc[0], st.x, bt.x), fmaf(-sc[1], st.x, bt.y), fmaf(-sc[2], st.x, bt.z),
+                       fmaf(-sc[3], st.x, bt.w)};
+  const int p0 = blockIdx.x * ppb, p1 = min(a.hw, p0 + ppb);
+  const size_t base = (size_t)img * a.hw * a.c + ch;
+#pragma unroll 4
+  for (int p = p0 + r; p < p1; p += rows) {
+    const size_t off = base + (size_t)p * a.c;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(a.x + off));
+    float y[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
+    if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + off) = make_float4(y[0], y[1], y[2], y[3]);
+    if (a.o_hi) store_planes<4>(a.o_hi, a.o_lo, off, y, a.o_act);
+  }
+}
+
 }  // namespace mcq

@@ -173,6 +173,14 @@ int fill_args(const mcq_conv_params* p, ConvArgs& a) {
   a.mode = p->mode; a.store = p->store; a.o0_act = p->out0_act; a.o1_act = p->out1_act; a.passes = p->passes;
   static const int direct = env_int("MCQ_DIRECT_EPI", 1);
   a.direct_epilogue = direct;
+  a.gn_ws = nullptr;
+  if (p->gn_partials) {
+    int32_t rb = 0, unit = 0;
+    const int rc = mcq_conv_gn_layout(p, &rb, &unit);
+    if (rc) return rc;
+    a.gn_ws = (float2*)p->gn_partials;
+    a.gn_unit = unit; a.gn_units = p->cout / unit; a.gn_rb = rb;
+  }
   static const int wait_sleep = env_int("MCQ_WAIT_SLEEP_NS", 0);
   a.wait_sleep_ns = wait_sleep;
   return 0;
@@ -418,10 +426,10 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
 
 
 // ---- CTA-pair kernel (tcgen05.mma.cta_group::2): 3x3 stride-1 convs with a 128-column N tile
-template <int PASSES>
+template <int PASSES, bool GN = false>
 int launch_pair_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t smem, int grid, cudaStream_t st) {
   static bool attr = false;
-  auto kern = conv_pair_kernel<PASSES>;
+  auto kern = conv_pair_kernel<PASSES, GN>;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
@@ -532,6 +540,10 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
     clusters = hp.per_ct * a.tiles_c;
   }
   const int grid = clusters * 2;
+  if (a.gn_ws) {   // GroupNorm partials: the instantiation whose drain also reduces (sum, sum^2) per row block
+    if (a.passes == 3) return launch_pair_t<3, true>(a, hp, maps, smem, grid, st);
+    return launch_pair_t<1, true>(a, hp, maps, smem, grid, st);
+  }
   if (a.passes == 3) return launch_pair_t<3>(a, hp, maps, smem, grid, st);
   return launch_pair_t<1>(a, hp, maps, smem, grid, st);
 }
@@ -661,9 +673,11 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
     // (streaming weights); with a single 128-column N tile the weights stay resident in the pair's shared memory instead
     const bool pair_resident = a.passes == 1 && a.cout_pad % 128 == 0 && a.cout_pad <= 512 && a.cin == 128 &&
                                env_int("MCQ_PAIR_RESIDENT", 1);
+    if (a.gn_ws) rc = halo_supported(a) ? launch_pair(a, st) : MCQ_ERR_UNSUPPORTED;   // only the pair kernel has it
+    else
     if (halo_supported(a) && env_int("MCQ_PAIR", (a.passes == 3 || pair_resident) ? 1 : 0)) rc = launch_pair(a, st);
-    if (rc == MCQ_ERR_UNSUPPORTED && halo_supported(a) && env_int("MCQ_HALO", 1)) rc = launch_halo(a, st);
-    if (rc == MCQ_ERR_UNSUPPORTED) rc = launch_tc(a, st);
+    if (rc == MCQ_ERR_UNSUPPORTED && !a.gn_ws && halo_supported(a) && env_int("MCQ_HALO", 1)) rc = launch_halo(a, st);
+    if (rc == MCQ_ERR_UNSUPPORTED && !a.gn_ws) rc = launch_tc(a, st);
   }
   g_ev_start = g_ev_stop = nullptr;
   return rc;
@@ -929,6 +943,45 @@ int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, in
   }
   g_launches++;
   return e == cudaSuccess ? cuda_status() : (int)e;
+}
+
+int mcq_conv_gn_layout(const mcq_conv_params* p, int32_t* rowblocks_per_image, int32_t* unit) {
+  MCQ_CHECK_ARG(p && rowblocks_per_image && unit);
+  MCQ_CHECK_ARG(p->gn_groups > 0 && p->cout > 0 && p->cout % p->gn_groups == 0);
+  const int cg = p->cout / p->gn_groups;
+  const int hout = p->hin / (p->stride > 0 ? p->stride : 1), wout = p->win / (p->stride > 0 ? p->stride : 1);
+  if (p->impl != MCQ_IMPL_TCGEN05 || p->ksize != 3 || p->stride != 1 || p->store != MCQ_STORE_NHWC ||
+      p->mode != MCQ_EPI_LINEAR || p->cin % TC_BK != 0 || p->cout % 128 != 0 || p->cout_pad != p->cout ||
+      wout < HALO_TW || hout < HALO_TH || !p->out_f32 || !env_int("MCQ_DIRECT_EPI", 1) || !env_int("MCQ_GN_FUSED", 1))
+    return MCQ_ERR_UNSUPPORTED;
+  if ((long long)p->n * ((wout + HALO_TW - 1) / HALO_TW) * ((hout + HALO_TH - 1) / HALO_TH) < 2) return MCQ_ERR_UNSUPPORTED;
+  if (cg % 4 != 0 || (cg > 16 && cg % 16 != 0) || (cg < 16 && 16 % cg != 0)) return MCQ_ERR_UNSUPPORTED;
+  *unit = cg < 16 ? cg : 16;
+  // a drain warp owns 32 consecutive tile rows = (32 / HALO_TW) image rows of one HALO_TW-wide tile column
+  *rowblocks_per_image = ((hout + 32 / HALO_TW - 1) / (32 / HALO_TW)) * ((wout + HALO_TW - 1) / HALO_TW);
+  return 0;
+}
+
+int mcq_groupnorm_apply(const float* x, const void* partials, int32_t rowblocks_per_image, int32_t unit, int32_t n,
+                        int32_t h, int32_t w, int32_t c, int32_t groups, const float* gamma, const float* beta,
+                        float eps, void* stats, float* out_f32, void* out_hi, void* out_lo, int32_t out_act,
+                        mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && partials && stats && gamma && beta && (out_f32 || out_hi));
+  MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && groups > 0 && c % groups == 0 && eps >= 0.f && n <= 65535);
+  MCQ_CHECK_ARG(rowblocks_per_image > 0 && unit >= 4 && unit % 4 == 0 && (c / groups) % unit == 0);
+  GroupNormApplyArgs a;
+  a.x = x; a.partials = (const float2*)partials; a.stats = (float2*)stats; a.gamma = gamma; a.beta = beta;
+  a.out_f32 = out_f32; a.o_hi = (__half*)out_hi; a.o_lo = (__half*)out_lo; a.o_act = out_act;
+  a.n = n; a.hw = h * w; a.c = c; a.groups = groups; a.rb = rowblocks_per_image; a.unit = unit; a.eps = eps;
+  if (c % 4 != 0 || c > 4 * GNA_THREADS) return MCQ_ERR_UNSUPPORTED;
+  gn_finalize_kernel<<<dim3((unsigned)groups, (unsigned)n), GNF_THREADS, 0, (cudaStream_t)stream>>>(a);
+  g_launches++;
+  const int rows = GNA_THREADS / (c / 4);
+  static const int iters = env_int("MCQ_GN_APPLY_ITERS", 8);
+  const int ppb = rows * iters;
+  gn_apply_kernel<<<dim3((unsigned)((a.hw + ppb - 1) / ppb), (unsigned)n), GNA_THREADS, 0, (cudaStream_t)stream>>>(a, ppb);
+  g_launches++;
+  return cuda_status();
 }
 
 int mcq_add_scaled(const float* x, const float* y, float alpha, int64_t count, float* out_f32, void* out_hi,

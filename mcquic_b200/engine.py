@@ -8,8 +8,10 @@ runs in libmcquic_b200.so (`_lib.py`).  Fusion map (reference op -> where it wen
   GDN / IGDN (gdn.py:67-91)          -> 1x1 tensor-core conv over x^2 planes, epilogue x * rsqrt/sqrt(.)
   PixelShuffle (convs.py:252-255)    -> store addressing of the producing conv (weights row-permuted at load)
   a * sigmoid(b) + x (blocks.py:281) -> epilogue of the AttentionBlock's trailing 1x1 conv
-  nn.GroupNorm (blocks.py:198)       -> one cluster-per-image launch: statistics + affine + split into the next
-                                        conv's operand planes (csrc/groupnorm.cuh)
+  nn.GroupNorm (blocks.py:198)       -> statistics: (sum, sum^2) partials written by the producing conv's epilogue
+                                        (conv_pair_kernel<.., GN>); normalise + affine + split into the next conv's
+                                        operand planes: one streaming pass (mcq_groupnorm_apply).  Shapes the fused path
+                                        does not take: one cluster-per-image launch doing all of it (mcq_groupnorm)
   conv1x1 skip (blocks.py:189-192)   -> its fp32 output is the residual operand of the block's second conv
   z - dequant(code) (quantizer.py:318), q + side (quantizer.py:354) -> residual operands
   AlignedPadding (transforms.py:86)  -> index arithmetic of the stem kernel
@@ -43,6 +45,8 @@ class Act:
     raw: Optional[Planes] = None
     silu: Optional[Planes] = None
     sq: Optional[Planes] = None
+    # (partials float2 [n, rowblocks, units], rowblocks, unit): GroupNorm statistics the producing conv's epilogue wrote
+    gn: Optional[Tuple[torch.Tensor, int, int]] = None
 
     def batch_slice(self, n0: int, n1: int) -> "Act":
         """Images [n0, n1) of this activation (NHWC: a contiguous view of every representation)."""
@@ -209,7 +213,14 @@ class Engine:
             ev0.record()
             ev1.record()   # forces creation of the underlying cudaEvent_t handles
             p.ev_start, p.ev_stop = ev0.cuda_event, ev1.cuda_event
-        _lib.check(self.lib.mcq_conv2d(ctypes.byref(p), self._stream()), "mcq_conv2d")
+        rc = self.lib.mcq_conv2d(ctypes.byref(p), self._stream())
+        if rc == _lib.ERR_UNSUPPORTED and p.gn_partials:
+            # the statistics-fusing instantiation cannot take this layer after all (shared-memory budget): plain launch,
+            # the GroupNorm that follows computes its own statistics
+            p.gn_partials = None
+            _keep[1].gn = None
+            rc = self.lib.mcq_conv2d(ctypes.byref(p), self._stream())
+        _lib.check(rc, "mcq_conv2d")
         if self.profile is not None:
             self.profile.append(dict(info, ev=(ev0, ev1)))
 
@@ -298,8 +309,10 @@ class Engine:
     # ------------------------------------------------------------------ one fused conv launch
     def conv(self, pc: PackedConv, a: Planes, x: Act, want: Set[str], *, mode: int = _lib.EPI_LINEAR,
              res1: Optional[torch.Tensor] = None, res1_scale: float = 1.0, res2: Optional[torch.Tensor] = None,
-             aux: Optional[torch.Tensor] = None, into: Optional[Act] = None) -> Act:
-        """into: write the outputs into these caller-owned tensors (same shapes / representations as `want`) instead
+             aux: Optional[torch.Tensor] = None, into: Optional[Act] = None, gn_groups: int = 0) -> Act:
+        """gn_groups > 0: a nn.GroupNorm(gn_groups, cout) follows; where the kernel can (mcq_conv_gn_layout) its
+        epilogue also writes the per-row-block (sum, sum^2) partials of the fp32 output -> `out.gn`.
+        into: write the outputs into these caller-owned tensors (same shapes / representations as `want`) instead
         of allocating them -- used when a batch is processed in chunks that fill slices of one full-batch tensor."""
         assert pc.cin == x.c, (pc.cin, x.c)
         dev = a[0].device
@@ -359,12 +372,21 @@ class Engine:
                 p.out1_hi, p.out1_lo, p.out1_act = _ptr(slots[1][0][0]), _ptr(slots[1][0][1]), slots[1][1]
         p.passes = self.passes if a[1] is not None else 1
         p.impl = self.impl if (pc.cin % 64 == 0) else _lib.IMPL_SIMT
+        if gn_groups > 0 and out.f32 is not None and pc.cout % gn_groups == 0:
+            p.gn_groups = gn_groups
+            rb, unit = ctypes.c_int32(0), ctypes.c_int32(0)
+            if self.lib.mcq_conv_gn_layout(ctypes.byref(p), ctypes.byref(rb), ctypes.byref(unit)) == 0:
+                part = torch.empty((x.n, rb.value, pc.cout // unit.value, 2), dtype=torch.float32, device=dev)
+                p.gn_partials = _ptr(part)
+                out.gn = (part, rb.value, unit.value)
+                keep.append(part)
         info = {"flops": 2.0 * x.n * (x.h // pc.stride) * (x.w // pc.stride) * pc.cout * pc.cin * pc.ksize ** 2,
                 "passes": p.passes, "impl": p.impl, "shape": (x.n, x.h, x.w, pc.cin, pc.cout, pc.ksize, pc.stride)}
         # everything the launch touches stays referenced until it has been issued (a freed block could otherwise be
         # handed to a later layer of the same chain, whose clusters do not run in lock step)
         item = (p, (keep, out, pc, into), info)
-        if (self.chain and p.impl == _lib.IMPL_TCGEN05 and (x.h // pc.stride) * (x.w // pc.stride) <= self.CHAIN_MAX_PIXELS):
+        if (self.chain and p.impl == _lib.IMPL_TCGEN05 and out.gn is None
+                and (x.h // pc.stride) * (x.w // pc.stride) <= self.CHAIN_MAX_PIXELS):
             self._pending.append(item)
         else:
             self.flush()
@@ -406,6 +428,15 @@ class Engine:
             act = {"raw": _lib.ACT_NONE, "silu": _lib.ACT_SILU, "sq": _lib.ACT_SQUARE}[planes[0]]
         gamma = norm.weight.detach().to(device=dev, dtype=torch.float32).contiguous()
         beta = norm.bias.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if x.gn is not None:
+            # statistics came with the convolution: finalize (tiny) + ONE streaming normalise / split pass
+            part, rb, unit = x.gn
+            stats = torch.empty((x.n, norm.num_groups, 2), dtype=torch.float32, device=dev)
+            _lib.check(self.lib.mcq_groupnorm_apply(_ptr(x.f32), _ptr(part), rb, unit, x.n, x.h, x.w, x.c,
+                                                    norm.num_groups, _ptr(gamma), _ptr(beta), float(norm.eps),
+                                                    _ptr(stats), _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act,
+                                                    self._stream()), "mcq_groupnorm_apply")
+            return out
         _lib.check(self.lib.mcq_groupnorm(_ptr(x.f32), x.n, x.h, x.w, x.c, norm.num_groups, _ptr(gamma), _ptr(beta),
                                           float(norm.eps), _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act,
                                           self._stream()), "mcq_groupnorm")
@@ -417,7 +448,7 @@ class Engine:
         if mod._skip is not None:       # channel-changing block: conv1x1 on the un-activated x (blocks.py:73-75)
             identity = self.conv(self._packed_for(mod._skip), x.raw, x, {"f32"}).f32
         if isinstance(mod._branch[2], nn.GroupNorm):
-            t = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"f32"})
+            t = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"f32"}, gn_groups=mod._branch[2].num_groups)
             t = self.groupnorm(mod._branch[2], t, {"raw"})
             a = t.raw
         else:

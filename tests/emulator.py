@@ -99,6 +99,12 @@ class EmulatedLib:
         y = y.contiguous()
         if p.out_f32:
             _arr(p.out_f32, shape, np.float32)[...] = y.numpy()
+        if p.gn_partials:
+            # header contract: (sum, sum^2) per (row block, unit channels); this model uses ONE row block per image
+            unit = min(p.cout // p.gn_groups, 16)
+            yu = y.double().reshape(n, -1, p.cout // unit, unit)
+            part = torch.stack([yu.sum((1, 3)), (yu * yu).sum((1, 3))], -1).float()     # [n, units, 2]
+            _arr(p.gn_partials, (n, 1, p.cout // unit, 2), np.float32)[...] = part[:, None].numpy()
         _store_planes(p.out0_hi, p.out0_lo, shape, y, p.out0_act)
         _store_planes(p.out1_hi, p.out1_lo, shape, y, p.out1_act)
         self.launches += 1
@@ -185,6 +191,38 @@ class EmulatedLib:
         g = torch.from_numpy(_arr(gamma.value, (c,), np.float32).copy())
         b = torch.from_numpy(_arr(beta.value, (c,), np.float32).copy())
         y = F.group_norm(xi.permute(0, 3, 1, 2), groups, g, b, eps).permute(0, 2, 3, 1).contiguous()
+        v = lambda q: q.value if q is not None and q.value else 0
+        if v(out_f32):
+            _arr(v(out_f32), (n, h, w, c), np.float32)[...] = y.numpy()
+        _store_planes(v(out_hi), v(out_lo), (n, h, w, c), y, act)
+        self.launches += 1
+        return 0
+
+    def mcq_conv_gn_layout(self, pref, rb_ref, unit_ref):
+        p = pref._obj
+        cg = p.cout // p.gn_groups
+        if p.ksize != 3 or p.stride != 1 or p.store != _lib.STORE_NHWC or not p.out_f32 or cg % 4 or (cg > 16 and cg % 16) \
+                or (cg < 16 and 16 % cg) or p.cin % 64:
+            return _lib.ERR_UNSUPPORTED
+        rb_ref._obj.value, unit_ref._obj.value = 1, min(cg, 16)
+        return 0
+
+    def mcq_groupnorm_apply(self, x, partials, rb, unit, n, h, w, c, groups, gamma, beta, eps, stats, out_f32, out_hi,
+                            out_lo, act, stream):
+        xi = torch.from_numpy(_arr(x.value, (n, h, w, c), np.float32).copy())
+        part = torch.from_numpy(_arr(partials.value, (n, rb, c // unit, 2), np.float32).copy()).double().sum(1)
+        cg = c // groups
+        sums = part.reshape(n, groups, cg // unit, 2).sum(2)                # [n, groups, 2]
+        cnt = h * w * cg
+        mean = sums[..., 0] / cnt
+        var = (sums[..., 1] / cnt - mean * mean).clamp_min(0)
+        rstd = 1.0 / torch.sqrt(var + eps)
+        _arr(stats.value, (n, groups, 2), np.float32)[...] = torch.stack([mean, rstd], -1).float().numpy()
+        g = torch.from_numpy(_arr(gamma.value, (c,), np.float32).copy())
+        b = torch.from_numpy(_arr(beta.value, (c,), np.float32).copy())
+        m_c = mean.float().repeat_interleave(cg, 1)[:, None, None, :]
+        r_c = rstd.float().repeat_interleave(cg, 1)[:, None, None, :]
+        y = ((xi - m_c) * r_c * g + b).contiguous()
         v = lambda q: q.value if q is not None and q.value else 0
         if v(out_f32):
             _arr(v(out_f32), (n, h, w, c), np.float32)[...] = y.numpy()

@@ -158,6 +158,73 @@ def test_gpu_groupnorm_kernel(n, h, w, c, groups):
     assert eng.lib.mcq_device_error_flag() == 0
 
 
+FUSED_CASES = [
+    # n, h, w, c, groups, fused expected
+    (2, 64, 64, 128, 32, True),      # unit 4 (four groups per 16-channel chunk)
+    (3, 24, 20, 128, 1, True),       # one group, ragged tiles in both directions, unit 16
+    (2, 16, 8, 256, 32, True),       # smallest map the pair kernel takes, two N tiles, unit 8
+    (1, 40, 24, 128, 8, True),       # unit 16 = one group per chunk
+    (5, 18, 30, 128, 4, True),       # rows not a multiple of the 4-row block
+    (2, 16, 16, 128, 64, False),     # 2 channels per group: not expressible in channel quads -> stand-alone kernel
+    (2, 8, 8, 128, 32, False),       # map below the pair kernel's tile -> stand-alone kernel
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("passes", [3, 1])
+@pytest.mark.parametrize("n,h,w,c,groups,fused", FUSED_CASES)
+def test_gpu_groupnorm_statistics_fused_into_the_conv_epilogue(n, h, w, c, groups, fused, passes):
+    """conv3x3 whose epilogue also emits the GroupNorm partial sums (mcq_conv_params.gn_partials) + mcq_groupnorm_apply
+    == the same conv followed by the stand-alone mcq_groupnorm == fp64 GroupNorm of the conv's fp32 output."""
+    from convcase import make_planes
+    from mcquic_b200.engine import pack_conv
+    g = torch.Generator().manual_seed(h * 100 + c + groups)
+    x = torch.randn(n, h, w, c, generator=g).cuda()
+    wt = ((torch.rand(c, c, 3, 3, generator=g) * 2 - 1) / (9 * c) ** 0.5).cuda()
+    bias = (torch.rand(c, generator=g) - 0.3).cuda()            # non-zero mean in the conv output
+    norm = torch.nn.GroupNorm(groups, c)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.3 * torch.randn(c, generator=g))
+        norm.bias.copy_(0.2 * torch.randn(c, generator=g))
+    norm = norm.cuda()
+    eng = Engine("tcgen05")
+    eng.passes = passes
+    pc = pack_conv(wt, bias, 1, _lib.STORE_NHWC, "cuda")
+    a = make_planes(x, passes)
+    t = eng.conv(pc, a, Act(n, h, w, c), {"f32"}, gn_groups=groups)
+    plain = eng.conv(pc, a, Act(n, h, w, c), {"f32"})
+    eng.flush()
+    torch.cuda.synchronize()
+    assert (t.gn is not None) == fused
+    assert torch.equal(t.f32, plain.f32)                        # the statistics do not disturb the conv's own output
+    want = {"f32", "raw"}
+    y_fused = eng.groupnorm(norm, t, want)
+    y_alone = eng.groupnorm(norm, plain, want)
+    torch.cuda.synchronize()
+    exp = F.group_norm(t.f32.cpu().double().permute(0, 3, 1, 2), groups, norm.weight.detach().cpu().double(),
+                       norm.bias.detach().cpu().double(), norm.eps).permute(0, 2, 3, 1)
+    scale = float(exp.abs().max())
+    for y in (y_fused, y_alone):
+        assert float((y.f32.cpu().double() - exp).abs().max()) <= 4e-6 * scale
+        if passes == 3:
+            rec = y.raw[0].cpu().double() + y.raw[1].cpu().double() / 2048.0
+            assert float((rec - exp).abs().max()) <= (2.0 ** -19 + 4e-6) * scale
+        else:
+            assert y.raw[1] is None and float((y.raw[0].cpu().double() - exp).abs().max()) <= 2.0 ** -10 * scale
+    if fused:
+        part, rb, unit = t.gn
+        assert tuple(part.shape) == (n, rb, c // unit, 2) and rb == -(-h // 4) * -(-w // 8)
+        # every slot written exactly once: the partials add up to the image sums
+        tot = part.double().sum(1).reshape(n, c // unit, 2).cpu()
+        ref = t.f32.cpu().double().reshape(n, h * w, c // unit, unit)
+        assert float((tot[..., 0] - ref.sum((1, 3))).abs().max()) <= 1e-4 * float(ref.abs().sum((1, 3)).max())
+        assert float((tot[..., 1] - (ref * ref).sum((1, 3))).abs().max()) <= 1e-5 * float((ref * ref).sum((1, 3)).max())
+        # bit-reproducible (fixed-order reductions, no atomics)
+        t2 = eng.conv(pc, a, Act(n, h, w, c), {"f32"}, gn_groups=groups)
+        assert torch.equal(t2.gn[0], part) and torch.equal(eng.groupnorm(norm, t2, want).f32, y_fused.f32)
+    assert eng.lib.mcq_device_error_flag() == 0
+
+
 @pytest.mark.gpu
 def test_gpu_groupnorm_errors():
     lib = _lib.load()
