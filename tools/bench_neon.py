@@ -25,6 +25,7 @@ ap.add_argument("--k", type=int, default=4096)
 ap.add_argument("--dense", type=int, default=0)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--decode-passes", type=int, default=3)
+ap.add_argument("--layers", type=int, default=0, help="also print the N most expensive conv shapes of the eager pass")
 args = ap.parse_args()
 size = [16, 8, 8, 8, 8, 4, 4, 4, 4, 2, 2, 2, 2, 1, 1, 1, 1]
 
@@ -44,6 +45,12 @@ xhat = model.decode(codes)
 torch.cuda.synchronize()
 flops = sum(r["flops"] for r in eng.profile)
 launches_eager = len(eng.profile)
+layers = {}
+for r in eng.profile:
+    key = (tuple(r["shape"]), r["passes"], "simt" if r["impl"] == _lib.IMPL_SIMT else "tc")
+    ms = r["ev"][0].elapsed_time(r["ev"][1])
+    cur = layers.setdefault(key, [0, 0.0, 0.0])
+    cur[0] += 1; cur[1] += ms; cur[2] += r["flops"]
 eng.profile = None
 model.use_graphs = True
 setup_s = time.time() - t0
@@ -73,3 +80,8 @@ print(json.dumps({
     "passes": {"encode": 3, "decode": args.decode_passes}, "finite": bool(torch.isfinite(xhat).all()),
     "device_error_flag": int(_lib.load().mcq_device_error_flag()), "setup_s": setup_s,
     "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}))
+if args.layers:
+    tot = sum(v[1] for v in layers.values())
+    print(f"# eager conv time {tot:.1f} ms over {launches_eager} launches; (n,h,w,cin,cout,k,stride) passes impl: count, ms, share, executed TFLOP/s")
+    for key, (cnt, ms, fl) in sorted(layers.items(), key=lambda kv: -kv[1][1])[:args.layers]:
+        print(f"# {key[0]} p{key[1]} {key[2]}: {cnt:4d} {ms:8.2f} ms {ms / tot:6.1%} {fl * key[1] / ms / 1e9:8.1f}")
