@@ -33,7 +33,7 @@ def sharded_encode(model, x_local: torch.Tensor, group: Optional["dist.ProcessGr
     model's `_entropyCoder._freqEMA` gets the reference's EMA update (entropyCoder.py:38-43) from the global counts,
     identically on every rank."""
     q = model._quantizer
-    total = sum(q._m * k for k in q._k)
+    total = q.hist_size()
     hist = torch.zeros(total, dtype=torch.int32, device=x_local.device)
     codes = model.encode(x_local, hist=hist)
     global_hist = gather_histograms(hist, group)

@@ -28,6 +28,8 @@ ap.add_argument("--decode-passes", type=int, default=3)
 ap.add_argument("--layers", type=int, default=0, help="also print the N most expensive conv shapes of the eager pass")
 args = ap.parse_args()
 size = [16, 8, 8, 8, 8, 4, 4, 4, 4, 2, 2, 2, 2, 1, 1, 1, 1]
+if os.environ.get("NEON_SIZE"):
+    size = [int(v) for v in os.environ["NEON_SIZE"].split(",")]
 
 t0 = time.time()
 model = Neon(args.channel, args.k, size, bool(args.dense)).eval()
@@ -73,7 +75,7 @@ enc.sort(); dec.sort()
 e, d = enc[len(enc) // 2], dec[len(dec) // 2]
 tokens = sum(int(c[0].numel()) for c in codes)
 print(json.dumps({
-    "model": f"Neon({args.channel}, {args.k}, size17, denseNorm={bool(args.dense)})", "params_M": params / 1e6,
+    "model": f"Neon({args.channel}, {args.k}, {size if len(size) != 17 else 'size17'}, denseNorm={bool(args.dense)})", "params_M": params / 1e6,
     "n": args.n, "hw": args.hw, "encode_ms": e, "decode_ms": d, "images_per_s": args.n / (e + d) * 1e3,
     "tokens_per_image": tokens, "tokens_per_s": args.n * tokens / (e + d) * 1e3,
     "conv_tflop_per_step": flops / 1e12, "alg_tflops": flops / (e + d) / 1e9, "conv_launches": launches_eager,
