@@ -89,6 +89,8 @@ class BaseCompressor(nn.Module):
     def _check_image(self, x: torch.Tensor):
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError(f"expected an image batch [n, 3, h, w], got {tuple(x.shape)}")
+        if x.shape[0] == 0:      # upstream raises too (quantizer.py:158: reshape of 0 elements with -1 is ambiguous)
+            raise RuntimeError("cannot encode an empty batch")
         if not x.is_cuda and not self.engine.emulated and not self._host_batch_ok(x):
             raise RuntimeError("mcquic_b200 runs on CUDA tensors (or pinned fp32 host batches a CUDA-resident model "
                                "streams in); there is no CPU fallback")

@@ -76,6 +76,25 @@ def test_unaligned_image_is_reflect_padded_like_the_reference():
     assert float((model.decode(codes).cpu() - O.decode(sd, [c.cpu() for c in codes])).abs().max()) <= PIXEL_TOL
 
 
+def test_large_unaligned_image_like_the_cli_sees():
+    """one 1100 x 1900 photograph-sized image (the reference CLI's use case, demo.py:109-134): reflect-padded to
+    1152 x 1920, 576 x 960 feature maps after the stem, ragged tiles on every level -- codes vs the CPU oracle,
+    pixels within 1e-3"""
+    cfg = dict(channel=128, m=1, k=[8192, 2048, 512])
+    sd = synthetic_state_dict(128, 1, cfg["k"], seed=0)
+    x = uniform((1, 3, 1100, 1900), "large.image", 7)
+    model = _model(cfg, sd)
+    codes = model.encode(x.cuda())
+    ref, marg = O.encode(sd, x, with_margin=True)
+    assert [tuple(c.shape) for c in codes] == [tuple(r.shape) for r in ref] == [(1, 1, 72, 120), (1, 1, 36, 60), (1, 1, 18, 30)]
+    flips, total, at = code_report(codes, ref, marg)
+    assert flips == 0 or (flips <= 2 and max(at) < 2e-6), (flips, at)
+    xhat = model.decode([r.cuda() for r in ref])
+    assert tuple(xhat.shape) == (1, 3, 1152, 1920)
+    assert float((xhat.cpu() - O.decode(sd, ref)).abs().max()) <= PIXEL_TOL
+    assert model.engine.lib.mcq_device_error_flag() == 0
+
+
 def test_compress_decompress_and_identical_bpp():
     """compress()/decompress() on the CUDA path: the reference flow yields 424 + 96 + 24 bytes (0.0664 bpp) for the
     qp=1 golden image under the uniform prior; identical codes + bit-identical rANS => identical bpp."""

@@ -168,3 +168,16 @@ def test_product_refuses_cpu_tensors_and_missing_library(monkeypatch):
     monkeypatch.setattr(_lib._build, "build", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("no nvcc")))
     with pytest.raises(RuntimeError, match="missing|not found"):
         Engine()
+
+
+def test_empty_batch_raises_like_the_reference():
+    """upstream cannot encode an empty batch either: `_distance` reshapes 0 elements with a -1 (quantizer.py:158) ->
+    RuntimeError; same exception type here, before anything is launched"""
+    model = Compressor(32, 2, [16, 8, 4]).eval()
+    model._engine = Engine(lib=EmulatedLib())
+    with pytest.raises(RuntimeError):
+        model.encode(torch.zeros(0, 3, 200, 136))
+    assert model.engine.lib.launches == 0
+    from mcquic_b200.utils.synthetic import synthetic_state_dict
+    with pytest.raises(RuntimeError):
+        O.encode(synthetic_state_dict(32, 2, [16, 8, 4], seed=0), torch.zeros(0, 3, 200, 136))
