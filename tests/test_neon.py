@@ -223,6 +223,40 @@ def test_gpu_neon_against_reference_golden(name, graphs):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("graphs", [False, True])
+def test_gpu_neon_c128_groupnorm_statistics_fused_in_the_trunk(graphs):
+    """Neon(128, ..., denseNorm=True): the trunk's 128 / 256-channel convs take the tcgen05 CTA-pair kernel, whose
+    epilogue emits the GroupNorm partials (32 groups -> 4 / 8 channels per group) -- eager and under CUDA graphs,
+    against the CPU oracle evaluated here (no golden needed at this size: ~1 s on CPU)."""
+    from mcquic_b200.utils.synthetic import synthetic_block_state, uniform
+    size = [8, 8]
+    model = Neon(128, 64, size, True).eval()
+    model.load_state_dict(synthetic_block_state(model.state_dict(), "neon.c128", seed=0))
+    x = uniform((2, 3, 128, 128), "neon.c128.image", 1)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    ref, margins = O.neon_encode(sd, x, size, with_margin=True)
+    xref = O.neon_decode(sd, ref, size)
+    model = model.cuda()
+    model.use_graphs = graphs
+    # the fused-statistics path is really the one that runs for the trunk's first conv of every ResidualBlock
+    probe = _lib.ConvParams()
+    probe.n, probe.hin, probe.win, probe.cin, probe.cout, probe.cout_pad = 2, 128, 128, 128, 128, 128
+    probe.ksize, probe.stride, probe.passes, probe.gn_groups = 3, 1, 3, 32
+    probe.out_f32 = 1
+    import ctypes
+    rb, unit = ctypes.c_int32(0), ctypes.c_int32(0)
+    assert _lib.load().mcq_conv_gn_layout(ctypes.byref(probe), ctypes.byref(rb), ctypes.byref(unit)) == 0
+    assert (rb.value, unit.value) == (32 * 16, 4)
+    for _ in range(2):
+        codes = model.encode(x.cuda())
+        at = _flips(codes, ref, margins)
+        assert at == [] or max(at) < MARGIN_TIE, at
+        xhat = model.decode([cd.cuda() for cd in ref])
+        assert float((xhat.cpu() - xref).abs().max()) <= PIXEL_TOL * max(1.0, float(xref.abs().max()))
+    assert model.engine.lib.mcq_device_error_flag() == 0
+
+
+@pytest.mark.gpu
 def test_gpu_add_scaled():
     eng = Engine("tcgen05")
     eng.passes = 3
