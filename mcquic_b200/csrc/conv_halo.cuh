@@ -145,7 +145,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   pdl_wait_prior_grids();
   pdl_launch_dependents();
 
-  const int kchunks = p.cin / TC_BK;
+  // cin need not fill its last 64-channel K chunk: TMA zero-fills the A box beyond the tensor's channel extent, and
+  // whatever the weight box holds there (the next tap's columns, or zeros past the last one) is multiplied by those zeros
+  const int kchunks = (p.cin + TC_BK - 1) / TC_BK;
   const int total_work = hp.groups_m * p.tiles_c;        // one work item = CL neighbouring pixel tiles x one N tile
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
 

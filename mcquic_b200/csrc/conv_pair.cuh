@@ -150,7 +150,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   pdl_wait_prior_grids();
   pdl_launch_dependents();
 
-  const int kchunks = p.cin / TC_BK;
+  // cin need not fill its last 64-channel K chunk: TMA zero-fills the A box beyond the tensor's channel extent, and
+  // whatever the weight box holds there (the next tap's columns, or zeros past the last one) is multiplied by those zeros
+  const int kchunks = (p.cin + TC_BK - 1) / TC_BK;
   const int total_work = hp.groups_m * p.tiles_c;        // one work item = 2 neighbouring pixel tiles x one N tile
   const int cluster_id = blockIdx.x / 2, num_clusters = gridDim.x / 2;
   const int spc = 9 / hp.tps;                            // weight stages per 64-channel chunk

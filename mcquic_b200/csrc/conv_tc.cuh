@@ -528,7 +528,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int tiles_m = p.tiles_n * p.tiles_y * p.tiles_x;
   const int total_tiles = tiles_m * p.tiles_c;
   const int ntaps = p.ksize * p.ksize;
-  const int kchunks = p.cin / TC_BK;
+  // cin need not fill its last 64-channel K chunk: TMA zero-fills the A box beyond the tensor's channel extent, and
+  // whatever the weight box holds there (the next tap's columns, or zeros past the last one) is multiplied by those zeros
+  const int kchunks = (p.cin + TC_BK - 1) / TC_BK;
   const int kiters = ntaps * kchunks;
 
   if (warp == 0) {

@@ -195,8 +195,14 @@ int launch_simt(const ConvArgs& a, cudaStream_t st) {
   return cuda_status();
 }
 
+// channel counts the 64-channel K chunk does not divide (Neon's 8 / 32-channel nets): stride-1 convs over a whole
+// tensor run with a partly zero-filled last chunk (see kchunks in the kernels); fp16 rows must stay 16 B aligned
+bool partial_chunk_ok(const ConvArgs& a) {
+  return a.cin % 8 == 0 && a.stride == 1 && a.cin_total == a.cin && a.ch_off == 0;
+}
+
 bool tc_supported(const ConvArgs& a) {
-  if (a.cin % TC_BK != 0) return false;
+  if (a.cin % TC_BK != 0 && !partial_chunk_ok(a)) return false;
   if (a.cout_pad % 16 != 0) return false;
   return true;
 }
@@ -308,7 +314,8 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
 
 // ---- halo kernel (3x3, stride 1): tap reuse in smem + weight multicast across a cluster
 bool halo_supported(const ConvArgs& a) {
-  return a.ksize == 3 && a.stride == 1 && a.cin % TC_BK == 0 && a.wout >= HALO_TW && a.hout >= HALO_TH &&
+  return a.ksize == 3 && a.stride == 1 && (a.cin % TC_BK == 0 || partial_chunk_ok(a)) && a.wout >= HALO_TW &&
+         a.hout >= HALO_TH &&
          a.cout_pad % 16 == 0;
 }
 
@@ -485,7 +492,7 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
   int nbs = (int)((budget - a_buf * hp.na) / b_stage);
   if (nbs > 8) nbs = 8;
   // weight-stationary mode: 1-pass, one N tile, and all (cin / 64) * (9 / tps) weight stages fit beside two halo buffers
-  const int all_stages = (a.cin / TC_BK) * (9 / hp.tps);
+  const int all_stages = ((a.cin + TC_BK - 1) / TC_BK) * (9 / hp.tps);
   if (a.passes == 1 && a.tiles_c <= num_sms() / 2 && all_stages <= 8 && a_buf * 2 + b_stage * all_stages <= budget &&
       env_int("MCQ_PAIR_RESIDENT", 1)) {
     hp.resident = 1;
@@ -599,7 +606,7 @@ int launch_chain(const mcq_conv_params* params, int count, cudaStream_t st) {
     ConvArgs& a = L.p;
     int rc = fill_args(p, a);
     if (rc) return rc;
-    if (!tc_supported(a)) return MCQ_ERR_UNSUPPORTED;
+    if (!tc_supported(a) || a.cin % TC_BK != 0) return MCQ_ERR_UNSUPPORTED;
     fill_mtile(a);
     fill_taps(a);
     int bn = a.cout_pad < bn_max ? a.cout_pad : bn_max;

@@ -371,7 +371,9 @@ class Engine:
             if len(slots) > 1:
                 p.out1_hi, p.out1_lo, p.out1_act = _ptr(slots[1][0][0]), _ptr(slots[1][0][1]), slots[1][1]
         p.passes = self.passes if a[1] is not None else 1
-        p.impl = self.impl if (pc.cin % 64 == 0) else _lib.IMPL_SIMT
+        # tensor cores: 64-channel K chunks; stride-1 convs also take cin % 8 == 0 (partly zero-filled last chunk)
+        on_tc = pc.cin % 64 == 0 or (pc.cin % 8 == 0 and pc.stride == 1 and os.environ.get("MCQ_PARTIAL_CHUNK", "1") == "1")
+        p.impl = self.impl if on_tc else _lib.IMPL_SIMT
         if gn_groups > 0 and out.f32 is not None and pc.cout % gn_groups == 0:
             p.gn_groups = gn_groups
             rb, unit = ctypes.c_int32(0), ctypes.c_int32(0)
@@ -385,7 +387,7 @@ class Engine:
         # everything the launch touches stays referenced until it has been issued (a freed block could otherwise be
         # handed to a later layer of the same chain, whose clusters do not run in lock step)
         item = (p, (keep, out, pc, into), info)
-        if (self.chain and p.impl == _lib.IMPL_TCGEN05 and out.gn is None
+        if (self.chain and p.impl == _lib.IMPL_TCGEN05 and out.gn is None and pc.cin % 64 == 0
                 and (x.h // pc.stride) * (x.w // pc.stride) <= self.CHAIN_MAX_PIXELS):
             self._pending.append(item)
         else:

@@ -78,18 +78,45 @@ def test_weight_stationary_pair_kernel():
     _check("tcgen05", passes=1, want=("raw",), n=2, h=16, w=24, cin=128, cout=256)
 
 
+PARTIAL_CHUNK_SHAPES = [
+    # channel counts the 64-channel K chunk does not divide (Neon's 8 / 32-channel nets): the last chunk is zero-filled
+    # by TMA beyond the tensor's channel extent; stride 1 only
+    dict(n=2, h=64, w=64, cin=32, cout=32),                  # halo kernel, 2 tiles per image column
+    dict(n=3, h=24, w=20, cin=32, cout=32),                  # ragged
+    dict(n=2, h=16, w=16, cin=32, cout=128),                 # CTA-pair kernel (3-pass) / weight... 32 -> 128
+    dict(n=2, h=16, w=16, cin=32, cout=128, store=_lib.STORE_SHUFFLE_NHWC),
+    dict(n=4, h=4, w=4, cin=32, cout=32),                    # per-tap kernel, several images per tile
+    dict(n=2, h=8, w=8, cin=8, cout=32),                     # 8 of 64 channels real
+    dict(n=2, h=32, w=16, cin=32, cout=8),                   # 32 -> 8 (N tile 16)
+    dict(n=2, h=16, w=16, cin=96, cout=64),                  # 1.5 chunks
+    dict(n=2, h=16, w=16, cin=32, cout=32, ksize=1),
+    dict(n=1, h=12, w=40, cin=40, cout=64, ksize=1),
+]
+
+
+@pytest.mark.parametrize("passes", [3, 1])
+@pytest.mark.parametrize("shape", PARTIAL_CHUNK_SHAPES, ids=lambda s: "-".join(f"{k}{v}" for k, v in s.items()))
+def test_tcgen05_conv_partial_k_chunk(shape, passes):
+    from mcquic_b200.engine import Engine as E
+    before = _lib.launch_count()
+    _check("tcgen05", passes=passes, **shape)
+    assert _lib.launch_count() > before
+
+
 def test_simt_serves_channel_counts_the_tensor_core_tiling_does_not():
     _check("simt", n=1, h=9, w=7, cin=32, cout=40)
     _check("simt", n=2, h=16, w=24, cin=64, cout=64, stride=2)
+    _check("tcgen05", n=2, h=16, w=24, cin=32, cout=32, stride=2)      # engine routes stride 2 at cin % 64 != 0 to SIMT
+    _check("tcgen05", n=1, h=9, w=7, cin=36, cout=40)                   # cin % 8 != 0: SIMT
     eng = Engine("tcgen05")
     with pytest.raises(RuntimeError, match="not supported|bad argument"):
         p = _lib.ConvParams()
-        x = torch.zeros(1, 8, 8, 32, dtype=torch.float16, device="cuda")
-        w = torch.zeros(32, 9 * 32, dtype=torch.float16, device="cuda")
+        x = torch.zeros(1, 8, 8, 36, dtype=torch.float16, device="cuda")
+        w = torch.zeros(32, 9 * 36, dtype=torch.float16, device="cuda")
         b = torch.zeros(32, device="cuda")
         o = torch.zeros(1, 8, 8, 32, device="cuda")
         p.a_hi = p.a_lo = x.data_ptr(); p.w_hi = p.w_lo = w.data_ptr(); p.bias = b.data_ptr(); p.out_f32 = o.data_ptr()
-        p.n, p.hin, p.win, p.cin, p.cout, p.cout_pad, p.ksize, p.stride, p.passes = 1, 8, 8, 32, 32, 32, 3, 1, 3
+        p.n, p.hin, p.win, p.cin, p.cout, p.cout_pad, p.ksize, p.stride, p.passes = 1, 8, 8, 36, 32, 32, 3, 1, 3
         p.w_scale = 1.0
         p.impl = _lib.IMPL_TCGEN05
         import ctypes

@@ -1,5 +1,7 @@
 #!/bin/bash
 o=gpurun_out/${1:-t}
 mkdir -p $o
-( time timeout 500 python -m pytest tests/test_neon.py tests/test_gpu_model.py -m gpu -q -x -k "c128 or large_unaligned" ) > $o/pytest.log 2>&1
-tail -30 $o/pytest.log | cut -c1-400
+( time timeout 900 python -m pytest tests -m gpu -q -x ) > $o/pytest.log 2>&1
+tail -12 $o/pytest.log | cut -c1-600
+NEON_SIZE=16,8,4,2,2 timeout 400 python tools/bench_neon.py --n 8 --hw 512 --channel 32 --dense 1 --layers 8 --steps 3 > $o/neon_c32_dense.txt 2> $o/neon_c32.err; tail -3 $o/neon_c32.err; cat $o/neon_c32_dense.txt
+timeout 400 python tools/bench_neon.py --n 8 --hw 512 --layers 6 --steps 3 > $o/neon_a800_16.txt 2> $o/neon_a800.err; tail -3 $o/neon_a800.err; cat $o/neon_a800_16.txt
