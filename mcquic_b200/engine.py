@@ -96,14 +96,14 @@ def pack_codebook(codebook: torch.Tensor):
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, store: int, device) -> PackedConv:
     """nn.Conv2d weight [cout, cin, k, k] -> K-major GEMM matrix [cout_pad, (r, s, cin)] (split fp16).
     bias=None (conv1x1(..., bias=False) of the Neon quantizer) packs a zero bias.  Channel counts the kernels' vector
-    accesses cannot address are zero-padded: cin to a multiple of 4 (RGB input of Neon's first conv: the caller pads
-    the activation likewise) and, for plain NHWC stores, cout to a multiple of 8 (Neon's final C -> 3 conv: the
+    accesses cannot address are zero-padded: cin to a multiple of 8 (RGB input of Neon's first conv: the caller pads
+    the activation likewise; 8 fp16 channels = the 16 B row alignment TMA needs, so the layer runs on the tensor cores) and, for plain NHWC stores, cout to a multiple of 8 (Neon's final C -> 3 conv: the
     caller drops the extra channels); `PackedConv.cin / .cout` are the padded counts."""
     cout, cin, k, _ = weight.shape
     w4 = weight.detach().to(device=device, dtype=torch.float32)
     b = torch.zeros(cout, device=device) if bias is None else bias.detach().to(device=device, dtype=torch.float32)
     if cin % 4 != 0:
-        w4 = torch.cat([w4, torch.zeros(cout, 4 - cin % 4, k, k, device=device)], 1)
+        w4 = torch.cat([w4, torch.zeros(cout, 8 - cin % 8, k, k, device=device)], 1)
         cin = w4.shape[1]
     if store == _lib.STORE_NHWC and cout % 8 != 0:
         extra = 8 - cout % 8
@@ -573,7 +573,7 @@ class Engine:
         return out
 
     def from_nchw(self, x: torch.Tensor, want: Set[str], pad_channels_to: int = 1) -> Act:
-        """pad_channels_to: zero channels are appended up to a multiple of it (RGB -> 4 for Neon's first conv)."""
+        """pad_channels_to: zero channels are appended up to a multiple of it (RGB -> 8 for Neon's first conv)."""
         self.flush()
         if x.shape[1] % pad_channels_to != 0:
             extra = pad_channels_to - x.shape[1] % pad_channels_to

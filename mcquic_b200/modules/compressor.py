@@ -462,7 +462,7 @@ class Neon(BaseCompressor):
         top, left, hp, wp = aligned_pad_amounts(h, w)
         if (hp, wp) != (h, w):       # AlignedPadding (transforms.py:86-99): a copy with reflected borders, no arithmetic
             x = torch.nn.functional.pad(x, (left, wp - w - left, top, hp - h - top), "reflect")
-        a0 = eng.from_nchw(x, eng.needs_of(self._encoder[0]), pad_channels_to=4)
+        a0 = eng.from_nchw(x, eng.needs_of(self._encoder[0]), pad_channels_to=8)
         y = eng.run_seq(list(self._encoder), a0, self._quantizer.first_needs(eng))
         codes = self._quantizer.encode_act(eng, y, hist)
         eng.flush()
