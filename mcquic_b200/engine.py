@@ -16,6 +16,7 @@ runs in libmcquic_b200.so (`_lib.py`).  Fusion map (reference op -> where it wen
   z - dequant(code) (quantizer.py:318), q + side (quantizer.py:354) -> residual operands
   AlignedPadding (transforms.py:86)  -> index arithmetic of the stem kernel
 """
+import contextlib
 import ctypes
 import os
 import math
@@ -97,7 +98,8 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, s
     """nn.Conv2d weight [cout, cin, k, k] -> K-major GEMM matrix [cout_pad, (r, s, cin)] (split fp16).
     bias=None (conv1x1(..., bias=False) of the Neon quantizer) packs a zero bias.  Channel counts the kernels' vector
     accesses cannot address are zero-padded: cin to a multiple of 8 (RGB input of Neon's first conv: the caller pads
-    the activation likewise; 8 fp16 channels = the 16 B row alignment TMA needs, so the layer runs on the tensor cores) and, for plain NHWC stores, cout to a multiple of 8 (Neon's final C -> 3 conv: the
+    the activation likewise; 8 fp16 channels = the 16 B row alignment TMA needs, so the layer runs on the tensor cores)
+    and, for plain NHWC stores, cout to a multiple of 8 (Neon's final C -> 3 conv: the
     caller drops the extra channels); `PackedConv.cin / .cout` are the padded counts."""
     cout, cin, k, _ = weight.shape
     w4 = weight.detach().to(device=device, dtype=torch.float32)
@@ -151,6 +153,19 @@ class Engine:
         self._rec_depth = 0
 
     # ------------------------------------------------------------------ plumbing
+    @contextlib.contextmanager
+    def _prof(self, name: str):
+        """When profiling, bracket a non-convolution launch (stem, VQ, gather, GroupNorm, layout, ...) by events too:
+        entries {"other": name, "ev": (start, stop)} -- bench.py's share of the step is taken over ALL launches."""
+        if self.profile is None:
+            yield
+            return
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        yield
+        ev1.record()
+        self.profile.append({"other": name, "ev": (ev0, ev1)})
+
     def _stream(self):
         if self.emulated:
             return ctypes.c_void_p(0)
@@ -434,14 +449,16 @@ class Engine:
             # statistics came with the convolution: finalize (tiny) + ONE streaming normalise / split pass
             part, rb, unit = x.gn
             stats = torch.empty((x.n, norm.num_groups, 2), dtype=torch.float32, device=dev)
-            _lib.check(self.lib.mcq_groupnorm_apply(_ptr(x.f32), _ptr(part), rb, unit, x.n, x.h, x.w, x.c,
-                                                    norm.num_groups, _ptr(gamma), _ptr(beta), float(norm.eps),
-                                                    _ptr(stats), _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act,
-                                                    self._stream()), "mcq_groupnorm_apply")
+            with self._prof("mcq_groupnorm_apply"):
+                _lib.check(self.lib.mcq_groupnorm_apply(_ptr(x.f32), _ptr(part), rb, unit, x.n, x.h, x.w, x.c,
+                                                        norm.num_groups, _ptr(gamma), _ptr(beta), float(norm.eps),
+                                                        _ptr(stats), _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act,
+                                                        self._stream()), "mcq_groupnorm_apply")
             return out
-        _lib.check(self.lib.mcq_groupnorm(_ptr(x.f32), x.n, x.h, x.w, x.c, norm.num_groups, _ptr(gamma), _ptr(beta),
-                                          float(norm.eps), _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act,
-                                          self._stream()), "mcq_groupnorm")
+        with self._prof("mcq_groupnorm"):
+            _lib.check(self.lib.mcq_groupnorm(_ptr(x.f32), x.n, x.h, x.w, x.c, norm.num_groups, _ptr(gamma), _ptr(beta),
+                                              float(norm.eps), _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act,
+                                              self._stream()), "mcq_groupnorm")
         return out
 
     def residual_block(self, mod: ResidualBlock, x: Act, want: Set[str], res2: Optional[torch.Tensor] = None,
@@ -545,9 +562,10 @@ class Engine:
         wgt = conv.weight.detach().reshape(cout, 27).contiguous().float()
         bias = conv.bias.detach().contiguous().float()
         xc = x.contiguous().float()
-        _lib.check(self.lib.mcq_stem_conv(_ptr(xc), n, h, w, top, left, hp, wp, _ptr(wgt), _ptr(bias), cout,
-                                          _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act, self._stream()),
-                   "mcq_stem_conv")
+        with self._prof("mcq_stem_conv"):
+            _lib.check(self.lib.mcq_stem_conv(_ptr(xc), n, h, w, top, left, hp, wp, _ptr(wgt), _ptr(bias), cout,
+                                              _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act, self._stream()),
+                       "mcq_stem_conv")
         return out
 
     def add_scaled(self, x: torch.Tensor, y: torch.Tensor, alpha: float, shape: Tuple[int, int, int, int],
@@ -568,8 +586,9 @@ class Engine:
             pl = self._planes(n, h, w, c, x.device)
             setattr(out, planes[0], pl)
             act = {"raw": _lib.ACT_NONE, "silu": _lib.ACT_SILU, "sq": _lib.ACT_SQUARE}[planes[0]]
-        _lib.check(self.lib.mcq_add_scaled(_ptr(x), _ptr(y), float(alpha), x.numel(), _ptr(out.f32), _ptr(pl[0]),
-                                           _ptr(pl[1]), act, self._stream()), "mcq_add_scaled")
+        with self._prof("mcq_add_scaled"):
+            _lib.check(self.lib.mcq_add_scaled(_ptr(x), _ptr(y), float(alpha), x.numel(), _ptr(out.f32), _ptr(pl[0]),
+                                               _ptr(pl[1]), act, self._stream()), "mcq_add_scaled")
         return out
 
     def from_nchw(self, x: torch.Tensor, want: Set[str], pad_channels_to: int = 1) -> Act:
@@ -591,16 +610,18 @@ class Engine:
                 setattr(out, name, pl)
                 slots.append((pl, act))
         slots += [((None, None), 0)] * (2 - len(slots))
-        _lib.check(self.lib.mcq_nchw_to_nhwc(_ptr(xc), n, c, h, w, _ptr(out.f32), _ptr(slots[0][0][0]),
-                                             _ptr(slots[0][0][1]), slots[0][1], _ptr(slots[1][0][0]),
-                                             _ptr(slots[1][0][1]), slots[1][1], self._stream()), "mcq_nchw_to_nhwc")
+        with self._prof("mcq_nchw_to_nhwc"):
+            _lib.check(self.lib.mcq_nchw_to_nhwc(_ptr(xc), n, c, h, w, _ptr(out.f32), _ptr(slots[0][0][0]),
+                                                 _ptr(slots[0][0][1]), slots[0][1], _ptr(slots[1][0][0]),
+                                                 _ptr(slots[1][0][1]), slots[1][1], self._stream()), "mcq_nchw_to_nhwc")
         return out
 
     def to_nchw(self, x: Act) -> torch.Tensor:
         self.flush()
         out = torch.empty((x.n, x.c, x.h, x.w), dtype=torch.float32, device=x.f32.device)
-        _lib.check(self.lib.mcq_nhwc_to_nchw(_ptr(x.f32), x.n, x.c, x.h, x.w, _ptr(out), self._stream()),
-                   "mcq_nhwc_to_nchw")
+        with self._prof("mcq_nhwc_to_nchw"):
+            _lib.check(self.lib.mcq_nhwc_to_nchw(_ptr(x.f32), x.n, x.c, x.h, x.w, _ptr(out), self._stream()),
+                       "mcq_nhwc_to_nchw")
         return out
 
     def run_module_nchw(self, mod: nn.Module, x: torch.Tensor) -> torch.Tensor:
@@ -627,24 +648,27 @@ class Engine:
             if packed is None or len(packed) < 4:
                 packed = pack_codebook(codebook)
             lg = torch.empty((n, m, h, w, k), dtype=torch.float32, device=dev) if logits else None
-            _lib.check(self.lib.mcq_vq_assign_fused(_ptr(x_nhwc), _ptr(packed[3]), packed[2], _ptr(c2), _ptr(codes),
-                                                    _ptr(lg), _ptr(logit_scale), _ptr(hist), n, h, w, m, k, d,
-                                                    self._stream()), "mcq_vq_assign_fused")
+            with self._prof("mcq_vq_assign_fused"):
+                _lib.check(self.lib.mcq_vq_assign_fused(_ptr(x_nhwc), _ptr(packed[3]), packed[2], _ptr(c2), _ptr(codes),
+                                                        _ptr(lg), _ptr(logit_scale), _ptr(hist), n, h, w, m, k, d,
+                                                        self._stream()), "mcq_vq_assign_fused")
             return (codes, lg) if logits else codes
         use_tc = packed is not None and not logits and d % 64 == 0 and k % 32 == 0 and on_tc
         if use_tc:
             nbytes = int(self.lib.mcq_vq_workspace_bytes(n, h, w, m, k, d))
             ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
             off = (-ws.data_ptr()) % 256
-            _lib.check(self.lib.mcq_vq_assign_tc(_ptr(x_nhwc), _ptr(packed[0]), _ptr(packed[1]), packed[2], _ptr(c2),
-                                                 _ptr(codes), _ptr(hist), n, h, w, m, k, d,
-                                                 ctypes.c_void_p(ws.data_ptr() + off), nbytes, self._stream()),
-                       "mcq_vq_assign_tc")
+            with self._prof("mcq_vq_assign_tc"):
+                _lib.check(self.lib.mcq_vq_assign_tc(_ptr(x_nhwc), _ptr(packed[0]), _ptr(packed[1]), packed[2], _ptr(c2),
+                                                     _ptr(codes), _ptr(hist), n, h, w, m, k, d,
+                                                     ctypes.c_void_p(ws.data_ptr() + off), nbytes, self._stream()),
+                           "mcq_vq_assign_tc")
             return codes
         lg = torch.empty((n, m, h, w, k), dtype=torch.float32, device=dev) if logits else None
-        _lib.check(self.lib.mcq_vq_assign(_ptr(x_nhwc), _ptr(codebook), _ptr(c2), _ptr(codes), _ptr(lg),
-                                          _ptr(logit_scale), _ptr(hist), n, h, w, m, k, d, self._stream()),
-                   "mcq_vq_assign")
+        with self._prof("mcq_vq_assign"):
+            _lib.check(self.lib.mcq_vq_assign(_ptr(x_nhwc), _ptr(codebook), _ptr(c2), _ptr(codes), _ptr(lg),
+                                              _ptr(logit_scale), _ptr(hist), n, h, w, m, k, d, self._stream()),
+                       "mcq_vq_assign")
         return (codes, lg) if logits else codes
 
     def vq_dequant(self, codes: torch.Tensor, codebook: torch.Tensor, want: Set[str],
@@ -663,10 +687,11 @@ class Engine:
                 setattr(out, name, pl)
                 slots.append((pl, act))
         slots += [((None, None), 0)] * (2 - len(slots))
-        _lib.check(self.lib.mcq_vq_dequant(_ptr(codes), _ptr(codebook), n, h, w, m, k, d, _ptr(out.f32),
-                                           _ptr(slots[0][0][0]), _ptr(slots[0][0][1]), slots[0][1],
-                                           _ptr(slots[1][0][0]), _ptr(slots[1][0][1]), slots[1][1], _ptr(status),
-                                           self._stream()), "mcq_vq_dequant")
+        with self._prof("mcq_vq_dequant"):
+            _lib.check(self.lib.mcq_vq_dequant(_ptr(codes), _ptr(codebook), n, h, w, m, k, d, _ptr(out.f32),
+                                               _ptr(slots[0][0][0]), _ptr(slots[0][0][1]), slots[0][1],
+                                               _ptr(slots[1][0][0]), _ptr(slots[1][0][1]), slots[1][1], _ptr(status),
+                                               self._stream()), "mcq_vq_dequant")
         return out
 
     def code_histogram(self, codes: List[torch.Tensor], ks: Sequence[int], out: Optional[torch.Tensor] = None):
@@ -680,8 +705,9 @@ class Engine:
         for code, k in zip(codes, ks):
             n, mm, h, w = code.shape
             view = out[off:off + mm * k]
-            _lib.check(self.lib.mcq_code_histogram(_ptr(code.contiguous()), n, mm, h * w, k, _ptr(view),
-                                                   self._stream()), "mcq_code_histogram")
+            with self._prof("mcq_code_histogram"):
+                _lib.check(self.lib.mcq_code_histogram(_ptr(code.contiguous()), n, mm, h * w, k, _ptr(view),
+                                                       self._stream()), "mcq_code_histogram")
             off += mm * k
         return out
 

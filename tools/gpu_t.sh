@@ -1,7 +1,8 @@
 #!/bin/bash
 o=gpurun_out/${1:-t}
 mkdir -p $o
-timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_blocks_dense.py -m gpu -q -x -k "fused_into and (16-8-256 or 24-20-128 or 18-30)" > $o/sanitizer_memcheck_fused.log 2>&1; echo "memcheck rc=$?"
-tail -6 $o/sanitizer_memcheck_fused.log | cut -c1-300
-timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_conv.py -m gpu -q -x -k "partial_k_chunk and (cin8 or cin96 or cin40 or h4-w4)" > $o/sanitizer_memcheck_partial.log 2>&1; echo "memcheck rc=$?"
-tail -6 $o/sanitizer_memcheck_partial.log | cut -c1-300
+( time timeout 900 python -m pytest tests -m gpu -q -x ) > $o/pytest_gpu.log 2>&1
+tail -6 $o/pytest_gpu.log | cut -c1-300
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py --dump-profile $o/conv_profile.json > $o/bench_n1.json 2> $o/bench_n1.err; tail -3 $o/bench_n1.err
+cat $o/bench_n1.json
