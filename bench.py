@@ -163,6 +163,11 @@ def run_ours(args):
     from mcquic_b200.dist import gather_histograms
     from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
 
+    # Libraries write banners to fd 1 (NCCL prints "NCCL version ..." there on communicator creation): everything
+    # before the result goes to stderr, so that stdout carries exactly ONE JSON line.
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -321,8 +326,10 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)          # the JSON line is the only thing this process ever writes to its real stdout
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 def main():

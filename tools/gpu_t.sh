@@ -1,8 +1,6 @@
 #!/bin/bash
 o=gpurun_out/${1:-t}
 mkdir -p $o
-( time timeout 900 python -m pytest tests -m gpu -q -x ) > $o/pytest_gpu.log 2>&1
-tail -6 $o/pytest_gpu.log | cut -c1-300
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 600 python bench.py --dump-profile $o/conv_profile.json > $o/bench_n1.json 2> $o/bench_n1.err; tail -3 $o/bench_n1.err
-cat $o/bench_n1.json
+timeout 300 python bench.py --steps 3 --warmup 3 > $o/bench_n1.json 2> $o/bench_n1.err
+echo "stdout lines: $(wc -l < $o/bench_n1.json)"; cut -c1-200 $o/bench_n1.json; tail -2 $o/bench_n1.err
+python -c "import json; d=json.load(open('$o/bench_n1.json')); print('ok', d['value'], d['roofline']['conv_share_of_step'])"
