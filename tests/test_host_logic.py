@@ -181,3 +181,32 @@ def test_empty_batch_raises_like_the_reference():
     from mcquic_b200.utils.synthetic import synthetic_state_dict
     with pytest.raises(RuntimeError):
         O.encode(synthetic_state_dict(32, 2, [16, 8, 4], seed=0), torch.zeros(0, 3, 200, 136))
+
+
+def test_pack_conv_pads_channels_the_kernels_cannot_address():
+    """Neon's RGB-in / RGB-out / bias-free convs (compressor.py:188,227; quantizer.py:606): cin 3 -> 8 zero columns,
+    plain-NHWC cout 3 -> 8 zero rows with zero bias, bias=None -> zero bias; values of the real part untouched"""
+    w = torch.randn(16, 3, 3, 3)
+    pc = pack_conv(w, torch.arange(16.0), 1, _lib.STORE_NHWC, "cpu")
+    assert (pc.cin, pc.cout, pc.cout_pad) == (8, 16, 16) and pc.w_hi.shape == (16, 9 * 8)
+    rec = ((pc.w_hi.double() + pc.w_lo.double() / 2048.0) * pc.w_scale).reshape(16, 3, 3, 8)
+    assert float((rec[..., :3] - w.permute(0, 2, 3, 1).double()).abs().max()) <= float(w.abs().max()) * 2.0 ** -21
+    assert float(rec[..., 3:].abs().max()) == 0.0
+    pc = pack_conv(torch.randn(3, 64, 3, 3), torch.ones(3), 1, _lib.STORE_NHWC, "cpu")
+    assert (pc.cin, pc.cout) == (64, 8) and pc.bias.tolist() == [1.0, 1.0, 1.0, 0, 0, 0, 0, 0]
+    assert float(pc.w_hi[3:8].abs().max()) == 0.0
+    pc = pack_conv(torch.randn(32, 8, 1, 1), None, 1, _lib.STORE_NHWC, "cpu")
+    assert pc.bias.tolist() == [0.0] * 32 and pc.ksize == 1
+
+
+def test_code_frequency_with_one_codebook_count_per_level():
+    """VariousMCoder (entropyCoder.py:293-322): m is a list, EMA 0.998, flat histogram = level-major segments"""
+    from mcquic_b200.modules.quantizer import CodeFrequency
+    cf = CodeFrequency([1, 2], [4, 3], ema=0.998)
+    assert [tuple(f.shape) for f in cf._freqEMA] == [(1, 4), (2, 3)] and cf.hist_size() == 4 + 6
+    hist = torch.tensor([4, 0, 0, 0, 1, 1, 2, 0, 3, 0], dtype=torch.int32)
+    cf.update(hist)
+    want0 = 0.002 * torch.tensor([[1.0, 0, 0, 0]]) + 0.998 * 0.25
+    want1 = 0.002 * torch.tensor([[.25, .25, .5], [0, 1.0, 0]]) + 0.998 / 3
+    assert torch.allclose(cf._freqEMA[0], want0) and torch.allclose(cf._freqEMA[1], want1)
+    assert CodeFrequency(2, [4, 3]).hist_size() == 14
