@@ -88,6 +88,11 @@ typedef struct mcq_conv_params {
 
 /* Replaces nn.Conv2d 3x3 / 1x1 (+ the elementwise ops around it) as used by mcquic/nn/blocks.py:62-288,
  * mcquic/nn/convs.py:77-100,221-276 and mcquic/nn/gdn.py:67-91. */
+/* Channel counts: cin % 4 == 0 always (fp16 rows are read 8 bytes at a time).  MCQ_IMPL_TCGEN05 takes cin % 64 == 0 for
+ * every kernel shape and, for stride-1 convolutions, any cin % 8 == 0: the K loop then runs ceil(cin / 64) chunks and TMA
+ * zero-fills the part of the last 64-channel box that lies beyond the tensor (the 8 / 32-channel nets of
+ * ResidualBackwardQuantizer, mcquic/modules/quantizer.py:600-657); anything else returns MCQ_ERR_UNSUPPORTED and is
+ * served by MCQ_IMPL_SIMT.  cout % 8 == 0 for plain NHWC stores (the host mirror zero-pads RGB outputs to 8 channels). */
 int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream);
 
 /* `count` convolutions executed in order by ONE persistent launch (the low-resolution tail: 137 of the 165 convs per
