@@ -156,6 +156,25 @@ def run_reference(args):
     }))
 
 
+def _by_class(rows, peak):
+    """rows: [{"shape": (n,h,w,cin,cout,k,stride), "passes", "flops", "us"}] of the tcgen05 conv launches of one step ->
+    per class of layer: launches, ms, executed TFLOP/s (flops x passes / time) and its fraction of the measured peak."""
+    classes = {}
+    for r in rows:
+        n, h, w, cin, cout, k, stride = r["shape"]
+        big = (h // stride) * (w // stride) >= 1024
+        name = ("1x1 (GDN / IGDN / gate)" if k == 1 else
+                ("3x3 on >= 32x32 maps, %d-pass" % r["passes"]) if big else "3x3 on <= 16x16 maps (latency-bound)")
+        c = classes.setdefault(name, {"launches": 0, "ms": 0.0, "executed_tflop": 0.0})
+        c["launches"] += 1
+        c["ms"] += r["us"] * 1e-3
+        c["executed_tflop"] += r["flops"] * r["passes"] / 1e12
+    for c in classes.values():
+        c["executed_tflops"] = c.pop("executed_tflop") / (c["ms"] * 1e-3) if c["ms"] > 0 else 0.0
+        c["frac_of_peak"] = c["executed_tflops"] / peak
+    return classes
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -288,6 +307,8 @@ def run_ours(args):
                     "kernel": "tcgen05 convolutions: conv_pair_kernel / conv_halo_kernel / conv_tc_kernel, all %d launches "
                               "of one step" % len(tc),
                     "executed_tflops": f_exec / t_tc / 1e12, "executed_frac": f_exec / t_tc / 1e12 / peak,
+                    "by_layer_class": _by_class([{"shape": p["shape"], "passes": p["passes"], "flops": p["flops"],
+                                                  "us": 1e3 * p["ev"][0].elapsed_time(p["ev"][1])} for p in tc], peak),
                     "conv_ms_per_step": t_tc * 1e3, "conv_share_of_step": t_tc / t_all,
                     "share_basis": "device time of ALL %d launches of one single-stream eager step, each bracketed by CUDA "
                                    "events (%.2f ms in total, serialised like the ncu launch list "
