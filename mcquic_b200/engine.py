@@ -624,6 +624,16 @@ class Engine:
                        "mcq_nhwc_to_nchw")
         return out
 
+    def run_seq_nchw(self, mods: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
+        """A chain of blocks / convs on an NCHW fp32 tensor (the values-only `forward` paths of the quantizers)."""
+        if not x.is_cuda and not self.emulated:
+            raise RuntimeError("mcquic_b200 runs on CUDA tensors only (no CPU fallback)")
+        mods = list(mods)
+        with torch.no_grad():
+            out = self.run_seq(mods, self.from_nchw(x, self.needs_of(mods[0])), {"f32"})
+            self.flush()
+            return self.to_nchw(out)
+
     def run_module_nchw(self, mod: nn.Module, x: torch.Tensor) -> torch.Tensor:
         """Stand-alone execution of one block on an NCHW tensor (API parity with calling the reference module)."""
         if not x.is_cuda and not self.emulated:

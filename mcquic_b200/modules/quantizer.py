@@ -74,6 +74,20 @@ class CodeFrequency(nn.Module):
             normalized = total / total.sum(-1, keepdim=True)
             self._freqEMA[lv].copy_((1 - self._ema) * normalized + self._ema * self._freqEMA[lv])
 
+    @torch.no_grad()
+    def forward(self, oneHotCodes: List[torch.Tensor]):
+        """entropyCoder.py:28-44 / :306-322: per level, count = one-hot.sum((0, 2, 3)) -> all-reduce over the ranks (when a
+        process group is up) -> normalise -> EMA.  (On the inference path the same counts come out of the VQ launch as
+        an int32 histogram, see `update`.)"""
+        import torch.distributed as dist
+        for lv, code in enumerate(oneHotCodes):
+            total = code.sum((0, 2, 3))
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(total)
+            normalized = total / total.sum(-1, keepdim=True)
+            self._freqEMA[lv].copy_((1 - self._ema) * normalized + self._ema * self._freqEMA[lv])
+        self._cdfs = None
+
     def _check(self, codes: List[torch.Tensor]):
         # same messages as entropyCoder.py:79-93
         info = "Please give codes with correct shape, for example, [[1, 2, 24, 24], [1, 2, 12, 12], ...], which is a `level` length list. each code has shape [n, m, h, w]. "
@@ -207,18 +221,33 @@ class _multiCodebookQuantization(nn.Module):
         return eng.vq_assign(eng.from_nchw(x, {"f32"}).f32, cb, c2, n, h, w, logits=True, logit_scale=scale,
                              packed=packed)
 
+    def _randomDrop(self, logit: torch.Tensor) -> torch.Tensor:
+        """quantizer.py:194-200: frequently used codewords are masked out at random (logit -= 1e9) so that rare ones get
+        picked; the exponent falls from `bits` (no code used) to 1 (all codes used)."""
+        bits = math.log2(self._k)
+        freq = self._freqEMA.detach().to(logit.device)
+        usage = (freq > _EPS).float().mean().clamp(0.0, 1.0)
+        mask = (torch.rand_like(logit) ** (-(bits - 1) * (usage ** 2) + bits)) < freq[:, None, None, ...]
+        logit[mask] += -1e9
+        return logit
+
     @torch.no_grad()
     def forward(self, x: torch.Tensor):
-        """(sample, code, oneHot, logit) as quantizer.py:232-239, forward values only (no autograd through the
-        CUDA path).  The Gumbel noise is drawn by PyTorch (base.py:118-133); `_randomDrop` (quantizer.py:194-200)
-        is a no-op here because UMGMQuantizer never gives this module a usable freqEMA (quantizer.py:399)."""
+        """(sample, code, oneHot, logit) as quantizer.py:202-239 -- FORWARD VALUES ONLY (no autograd through the CUDA
+        path; training is SURVEY 8f NEXT-3).  distance / logits: the VQ launch; `_randomDrop` (only when the owner
+        registered a frequency Parameter, i.e. ResidualBackwardQuantizer -- UMGMQuantizer hands over a float upstream,
+        quantizer.py:399, and its `_randomDrop` would raise) and the hard Gumbel sample `y_hard - y_soft + y_soft`
+        (base.py:118-133) are the reference's own torch expressions, with PyTorch's RNG, on the logits' device."""
         _, logit = self.logits(x)
+        if isinstance(getattr(self, "_freqEMA", None), torch.Tensor):
+            logit = self._randomDrop(logit)
         eps = torch.finfo(logit.dtype).eps
         gumbels = -((-(torch.rand_like(logit).clamp_(eps, 1 - eps).log())).log())
         ySoft = (logit + gumbels).softmax(-1)
-        sample = torch.zeros_like(logit).scatter_(-1, ySoft.max(-1, keepdim=True)[1], 1.0)
+        yHard = torch.zeros_like(logit).scatter_(-1, ySoft.max(-1, keepdim=True)[1], 1.0)
+        sample = yHard - ySoft + ySoft
         code = logit.argmax(-1, keepdim=True)
-        oneHot = torch.zeros_like(logit).scatter_(-1, code, 1)
+        oneHot = torch.zeros_like(logit).scatter_(-1, code, 1).contiguous()
         return sample, code[..., 0].contiguous(), oneHot, logit
 
 
@@ -276,6 +305,16 @@ class _quantizerEncoder(nn.Module):
     def syncCodebook(self):                                             # quantizer.py:294-295
         return self._quantizer.syncCodebook()
 
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor):
+        """quantizer.py:320-328, forward values: (q, residual or None, code, oneHot, logit) on NCHW tensors"""
+        eng = default_engine()
+        z = eng.run_seq_nchw(self._latentStageEncoder, x)
+        q, code, oneHot, logit = self._quantizer(eng.run_seq_nchw(self._quantizationHead, z))
+        if self._latentHead is None:
+            return q, None, code, oneHot, logit
+        return q, eng.run_seq_nchw(self._latentHead, z) - self._dequantizer(q), code, oneHot, logit
+
     def encode_act(self, eng: Engine, x: Act, next_needs, hist: Optional[torch.Tensor]):
         """quantizer.py:310-318 on engine activations: returns (residual Act or None, codes)."""
         z = eng.run_seq(self._latentStageEncoder, x, {"f32", "silu"})
@@ -308,6 +347,15 @@ class _quantizerDecoder(nn.Module):
         self._dequantizationHead = dequantizationHead
         self._sideHead = sideHead
         self._restoreHead = restoreHead
+
+    @torch.no_grad()
+    def forward(self, q: torch.Tensor, formerLevel: Optional[torch.Tensor]):
+        """quantizer.py:359-365, forward values: q is the (relaxed) one-hot sample [n, m, h, w, k]"""
+        eng = default_engine()
+        xHat = eng.run_seq_nchw(self._dequantizationHead, self._dequantizer(q))
+        if self._sideHead is not None:
+            xHat = xHat + eng.run_seq_nchw(self._sideHead, formerLevel)
+        return eng.run_seq_nchw(self._restoreHead, xHat)
 
     def decode_act(self, eng: Engine, code: torch.Tensor, former: Optional[Act], next_needs,
                    status: Optional[torch.Tensor]) -> Act:
@@ -408,6 +456,25 @@ class UMGMQuantizer(nn.Module):
             nxt = final_needs if lv == 0 else eng.needs_of(self._decoders[lv - 1]._sideHead[0])
             former = self._decoders[lv].decode_act(eng, codes[lv], former, nxt, status)
         return former
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor):
+        """quantizer.py:443-467, FORWARD VALUES ONLY: (yHat, codes, logits); updates the frequency EMA from the one-hot
+        codes like upstream (:464).  (Upstream this method cannot run inside `Compressor`: the quantization modules get
+        a float where `_randomDrop` expects the frequency tensor, quantizer.py:399 / SURVEY 8a row a14; here the drop is
+        skipped in that case.)"""
+        quantizeds, codes, oneHots, logits = [], [], [], []
+        for enc in self._encoders:
+            quantized, x, code, oneHot, logit = enc(x)
+            quantizeds.append(quantized)
+            codes.append(code)
+            oneHots.append(oneHot)
+            logits.append(logit)
+        former = None
+        for dec, quantized in zip(self._decoders[::-1], quantizeds[::-1]):
+            former = dec(quantized, former)
+        self._entropyCoder(oneHots)
+        return former, codes, logits
 
     @torch.no_grad()
     def encode(self, x: torch.Tensor) -> List[torch.Tensor]:
@@ -567,6 +634,32 @@ class ResidualBackwardQuantizer(nn.Module):
     def decode(self, codes: List[torch.Tensor]) -> torch.Tensor:
         eng = default_engine()
         return eng.to_nchw(self.decode_act(eng, codes, {"f32"}))
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor):
+        """quantizer.py:727-765, FORWARD VALUES ONLY: (restored latent, codes, logits), codes / logits smallest level first;
+        the entropy coder's frequency EMA is updated from the one-hot codes like upstream (:763)."""
+        eng = default_engine()
+        latents = []
+        for enc in self._encoders:
+            x = eng.run_seq_nchw(enc, x)
+            latents.append(x)
+        quantizeds, codes, oneHots, logits = [], [], [], []
+        current = torch.zeros_like(latents[-1])
+        for lv in reversed(range(len(latents))):
+            sample, code, oneHot, logit = self._quantizers[lv](latents[lv] - current)
+            quantized = self._dequantizers[lv](sample)
+            quantizeds.append(quantized)
+            codes.append(code)
+            oneHots.append(oneHot)
+            logits.append(logit)
+            back = self._backwards[lv]
+            current = quantized if isinstance(back, nn.Identity) else eng.run_seq_nchw(back, quantized)
+        former = torch.zeros_like(quantizeds[0])
+        for lv, quantized in zip(reversed(range(len(latents))), quantizeds):
+            former = eng.run_seq_nchw(self._decoders[lv], former + quantized)
+        self._entropyCoder(oneHots)
+        return former, codes, logits
 
     @torch.no_grad()
     def residual_backward(self, code: torch.Tensor, level: int) -> torch.Tensor:

@@ -188,6 +188,94 @@ def test_sync_codebook_two_ranks_gloo():
     assert len(a) == 2 and all(torch.equal(x, y) for x, y in zip(a, b))
 
 
+# ------------------------------------------------------------------------------------------------ forward (values)
+def _one_rank_group():
+    import socket
+    import torch.distributed as dist
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    return dist
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_quantizer_forward_values_match_the_reference_under_the_same_seed():
+    """ResidualBackwardQuantizer.forward (quantizer.py:727-765; the soft path of SURVEY 8a row a11 in its only runnable
+    owner): same weights, same input, same torch RNG seed -> same codes, logits, restored latent and frequency EMA as
+    the reference module (forward values; the product path runs on the CPU model of the C ABI here)."""
+    ref_import.load()
+    from mcquic.modules.quantizer import ResidualBackwardQuantizer as RefQ
+    from mcquic_b200 import ResidualBackwardQuantizer, engine as E
+    from mcquic_b200.utils.synthetic import synthetic_block_state, uniform
+    size = [8, 8, 4, 4]
+    torch.manual_seed(0)
+    ref = RefQ(32, size, True).eval()
+    sd = synthetic_block_state(ref.state_dict(), "rbq.forward", seed=0)
+    # a non-uniform frequency table so that _randomDrop really masks something
+    for key in sd:
+        if key.startswith("_entropyCoder._freqEMA"):
+            f = uniform(tuple(sd[key].shape), key, 3).abs() ** 4
+            sd[key] = f / f.sum(-1, keepdim=True)
+    for key in list(sd):
+        if key.endswith("._freqEMA") and key.startswith("_quantizers."):
+            lv = int(key.split(".")[1])
+            sd[key] = sd[f"_entropyCoder._freqEMA.{len(size) - 1 - lv}"]
+    ref.load_state_dict(sd)
+    mine = ResidualBackwardQuantizer(32, size, True).eval()
+    assert list(mine.state_dict()) == list(ref.state_dict())
+    mine.load_state_dict(sd)
+    x = uniform((2, 8, 16, 16), "rbq.forward.x", 1) * 0.5
+    dist = _one_rank_group()
+    old, E._DEFAULT = E._DEFAULT, Engine(lib=EmulatedLib())
+    try:
+        E._DEFAULT.passes = 3
+        torch.manual_seed(123)
+        with torch.no_grad():
+            r_y, r_codes, r_logits = ref(x)
+        torch.manual_seed(123)
+        y, codes, logits = mine(x)
+    finally:
+        E._DEFAULT = old
+        dist.destroy_process_group()
+    assert [tuple(c.shape) for c in codes] == [tuple(c.shape) for c in r_codes] == [(2, 1, 4, 4)] * 2 + [(2, 1, 8, 8)] * 2
+    assert all(torch.equal(a, b) for a, b in zip(codes, r_codes))
+    for a, b in zip(logits, r_logits):
+        keep = b > -1e8                                     # entries _randomDrop pushed to -1e9 must coincide
+        assert torch.equal(a > -1e8, keep) and int((~keep).sum()) > 0
+        assert float((a[keep] - b[keep]).abs().max()) <= 2e-5 * float(b[keep].abs().max())
+    assert float((y - r_y).abs().max()) <= 2e-5 * max(1.0, float(r_y.abs().max()))
+    for a, b in zip(mine._entropyCoder._freqEMA, ref._entropyCoder._freqEMA):
+        assert torch.allclose(a, b, atol=1e-7)
+
+
+def test_quantizer_forward_values_properties():
+    """UMGMQuantizer.forward (quantizer.py:443-467) through the CPU model of the C ABI: shapes, code = argmax logit = the
+    hard code of encode(), relaxed sample is one-hot up to an ulp, EMA moves toward the observed code frequencies."""
+    from mcquic_b200 import Compressor, engine as E
+    from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
+    model = Compressor(32, 2, [16, 8]).eval()
+    model.load_state_dict(synthetic_state_dict(32, 2, [16, 8], seed=0))
+    q = model._quantizer
+    y = uniform((2, 32, 16, 16), "umgm.forward.y", 1) * 0.3
+    old, E._DEFAULT = E._DEFAULT, Engine(lib=EmulatedLib())
+    try:
+        E._DEFAULT.passes = 3
+        before = [f.clone() for f in q._entropyCoder._freqEMA]
+        torch.manual_seed(7)
+        yhat, codes, logits = q(y)
+        hard = q.encode(y)
+    finally:
+        E._DEFAULT = old
+    assert tuple(yhat.shape) == (2, 32, 16, 16)
+    assert [tuple(c.shape) for c in codes] == [(2, 2, 8, 8), (2, 2, 4, 4)]
+    assert [tuple(l.shape) for l in logits] == [(2, 2, 8, 8, 16), (2, 2, 4, 4, 8)]
+    assert torch.equal(codes[0], logits[0].argmax(-1)) and torch.equal(codes[0], hard[0])   # level 0 sees the same input
+    for lv, (f0, f1) in enumerate(zip(before, q._entropyCoder._freqEMA)):
+        cnt = torch.stack([torch.bincount(codes[lv][:, j].flatten(), minlength=f0.shape[1]) for j in range(2)]).float()
+        assert torch.allclose(f1, 0.1 * cnt / cnt.sum(-1, keepdim=True) + 0.9 * f0, atol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(NEON_CASES))
