@@ -345,6 +345,35 @@ def test_gpu_neon_c128_groupnorm_statistics_fused_in_the_trunk(graphs):
 
 
 @pytest.mark.gpu
+def test_gpu_quantizer_forward_values():
+    """the values-only training-time forward on the GPU (CUDA RNG, so only RNG-independent facts are asserted): shapes,
+    code = argmax of the returned logits, the un-dropped logits equal the deterministic ones, restored latent finite,
+    frequency EMA still a distribution; UMGMQuantizer.forward level 0 reproduces encode()'s codes."""
+    from mcquic_b200 import Compressor, ResidualBackwardQuantizer
+    from mcquic_b200.utils.synthetic import synthetic_block_state, synthetic_state_dict, uniform
+    size = [8, 8, 4, 4]
+    q = ResidualBackwardQuantizer(32, size, True).eval()
+    q.load_state_dict(synthetic_block_state(q.state_dict(), "rbq.forward", seed=0))
+    q = q.cuda()
+    x = (uniform((2, 8, 16, 16), "rbq.forward.x", 1) * 0.5).cuda()
+    before = _lib.launch_count()
+    y, codes, logits = q(x)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - before > 100 and _lib.load().mcq_device_error_flag() == 0
+    assert tuple(y.shape) == (2, 8, 16, 16) and bool(torch.isfinite(y).all())
+    assert [tuple(c.shape) for c in codes] == [(2, 1, 4, 4)] * 2 + [(2, 1, 8, 8)] * 2
+    assert all(torch.equal(c, l.argmax(-1)) for c, l in zip(codes, logits))
+    assert all(abs(float(f.sum()) - 1.0) < 1e-5 for f in q._entropyCoder._freqEMA)
+    model = Compressor(32, 2, [16, 8]).eval()
+    model.load_state_dict(synthetic_state_dict(32, 2, [16, 8], seed=0))
+    model = model.cuda()
+    yl = (uniform((2, 32, 16, 16), "umgm.forward.y", 1) * 0.3).cuda()
+    yhat, codes, logits = model._quantizer(yl)
+    assert tuple(yhat.shape) == (2, 32, 16, 16) and bool(torch.isfinite(yhat).all())
+    assert torch.equal(codes[0], model._quantizer.encode(yl)[0])
+
+
+@pytest.mark.gpu
 def test_gpu_add_scaled():
     eng = Engine("tcgen05")
     eng.passes = 3
