@@ -405,8 +405,38 @@ class BaseCompressor(nn.Module):
     def CDFs(self):
         return self._quantizer.CDFs
 
+    def _analysis_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        """y = self._encoder(x) on the engine, NCHW fp32 in / out (no padding: compressor.py:35-43 takes training crops)"""
+        eng = self.engine
+        n, _, h, w = x.shape
+        y0 = eng.stem(self._encoder[0], x, (0, 0, h, w), eng.needs_of(self._encoder[1]))
+        return eng.to_nchw(eng.run_seq(list(self._encoder)[1:], y0, {"f32"}))
+
+    def _synthesis_nchw(self, yHat: torch.Tensor) -> torch.Tensor:
+        eng = self.engine
+        act = eng.from_nchw(yHat, eng.needs_of(self._decoder[0]))
+        return eng.run_seq(list(self._decoder), act, set()).f32        # the final pixel-shuffle conv stores NCHW
+
+    @torch.no_grad()
     def forward(self, x: torch.Tensor):
-        raise NotImplementedError("mcquic_b200 accelerates inference (encode/decode); training forward is out of scope")
+        """compressor.py:35-43, FORWARD VALUES ONLY: (xHat, yHat, codes, logits) of the training-time path (soft
+        quantizer: Gumbel sample with PyTorch's RNG, frequency EMA updated) -- no autograd graph is built, so this is
+        for monitoring / validation of a training run, not for back-propagation (SURVEY 8f NEXT-3 is not built).
+        Upstream returns this tuple in training mode only; here the mode is not consulted."""
+        self._check_image(x)
+        if x.shape[2] % 16 or x.shape[3] % 16:
+            raise RuntimeError("forward() takes training crops whose sides the strided stages divide (multiples of 16)")
+        from .. import engine as E
+        old, E._DEFAULT = E._DEFAULT, self.engine       # the quantizer's values path runs on this model's engine
+        try:
+            self.engine.passes = self.encode_passes
+            y = self._analysis_nchw(x.contiguous().float())
+            yHat, codes, logits = self._quantizer(y)
+            xHat = self._synthesis_nchw(yHat)
+            self.engine.flush()
+        finally:
+            E._DEFAULT = old
+        return xHat, yHat, codes, logits
 
 
 class Compressor(BaseCompressor):
@@ -475,6 +505,16 @@ class Neon(BaseCompressor):
         out = eng.run_seq(list(self._decoder), yHat, {"f32"})      # final conv C -> 3 runs with 8 stored channels
         eng.flush()
         return eng.to_nchw(out)[:, :3].contiguous()
+
+    def _analysis_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        eng = self.engine
+        a0 = eng.from_nchw(x, eng.needs_of(self._encoder[0]), pad_channels_to=8)
+        return eng.to_nchw(eng.run_seq(list(self._encoder), a0, {"f32"}))
+
+    def _synthesis_nchw(self, yHat: torch.Tensor) -> torch.Tensor:
+        eng = self.engine
+        act = eng.from_nchw(yHat, eng.needs_of(self._decoder[0]))
+        return eng.to_nchw(eng.run_seq(list(self._decoder), act, {"f32"}))[:, :3].contiguous()
 
     def residual_backward(self, code: torch.Tensor, level: int) -> torch.Tensor:
         return self._quantizer.residual_backward(code, level)       # compressor.py:235-237

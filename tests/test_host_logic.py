@@ -211,3 +211,24 @@ def test_code_frequency_with_one_codebook_count_per_level():
     want1 = 0.002 * torch.tensor([[.25, .25, .5], [0, 1.0, 0]]) + 0.998 / 3
     assert torch.allclose(cf._freqEMA[0], want0) and torch.allclose(cf._freqEMA[1], want1)
     assert CodeFrequency(2, [4, 3]).hist_size() == 14
+
+
+def test_compressor_forward_values_through_emulated_abi():
+    """BaseCompressor.forward (compressor.py:35-43), forward values only: shapes, finiteness, codes = argmax of the
+    returned logits, level-0 codes = encode()'s (same deterministic logits), EMA updated"""
+    from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
+    model = Compressor(32, 2, [16, 8]).eval()
+    model.load_state_dict(synthetic_state_dict(32, 2, [16, 8], seed=0))
+    model._engine = Engine(lib=EmulatedLib())
+    x = uniform((2, 3, 64, 96), "forward.image", 2)
+    before = model._quantizer._entropyCoder._freqEMA[0].clone()
+    torch.manual_seed(1)
+    xhat, yhat, codes, logits = model(x)
+    assert tuple(xhat.shape) == (2, 3, 64, 96) and tuple(yhat.shape) == (2, 32, 8, 12)
+    assert bool(torch.isfinite(xhat).all()) and [tuple(c.shape) for c in codes] == [(2, 2, 4, 6), (2, 2, 2, 3)]
+    assert all(torch.equal(c, l.argmax(-1)) for c, l in zip(codes, logits))
+    assert not torch.equal(before, model._quantizer._entropyCoder._freqEMA[0])
+    xa = uniform((1, 3, 128, 128), "forward.image.aligned", 2)     # encode() pads to multiples of 128, forward() does not
+    assert torch.equal(model(xa)[2][0], model.encode(xa)[0])
+    with pytest.raises(RuntimeError):
+        model(x[:, :, :60])

@@ -249,6 +249,34 @@ def test_quantizer_forward_values_match_the_reference_under_the_same_seed():
         assert torch.allclose(a, b, atol=1e-7)
 
 
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_neon_forward_values_match_the_reference_under_the_same_seed():
+    """BaseCompressor.forward (compressor.py:35-43) on Neon: (xHat, yHat, codes, logits) equal the reference model's in
+    training mode, same weights / input / RNG seed (forward values; product path on the CPU model of the C ABI)."""
+    ref_import.load()
+    from mcquic.modules.compressor import Neon as RefNeon
+    name = "neon_c32_gn"
+    ref_model, _ = neon_inputs(name, RefNeon)
+    mine, _ = neon_inputs(name, Neon)
+    from mcquic_b200.utils.synthetic import uniform
+    x = uniform((2, 3, 64, 64), "neon.forward.image", 4)
+    mine._engine = Engine(lib=EmulatedLib())
+    dist = _one_rank_group()
+    try:
+        ref_model.train()
+        torch.manual_seed(9)
+        r_xhat, r_yhat, r_codes, r_logits = ref_model(x.clone())
+        torch.manual_seed(9)
+        xhat, yhat, codes, logits = mine(x)
+    finally:
+        dist.destroy_process_group()
+    assert all(torch.equal(a, b) for a, b in zip(codes, r_codes))
+    assert float((yhat - r_yhat.detach()).abs().max()) <= 2e-5 * max(1.0, float(r_yhat.detach().abs().max()))
+    assert tuple(xhat.shape) == tuple(r_xhat.shape) == (2, 3, 64, 64)
+    assert float((xhat - r_xhat.detach()).abs().max()) <= 2e-5 * max(1.0, float(r_xhat.detach().abs().max()))
+    assert all(float((a - b.detach()).abs()[b > -1e8].max()) <= 2e-5 * float(b[b > -1e8].abs().max()) for a, b in zip(logits, [l.detach() for l in r_logits]))
+
+
 def test_quantizer_forward_values_properties():
     """UMGMQuantizer.forward (quantizer.py:443-467) through the CPU model of the C ABI: shapes, code = argmax logit = the
     hard code of encode(), relaxed sample is one-hot up to an ulp, EMA moves toward the observed code frequencies."""
@@ -371,6 +399,18 @@ def test_gpu_quantizer_forward_values():
     yhat, codes, logits = model._quantizer(yl)
     assert tuple(yhat.shape) == (2, 32, 16, 16) and bool(torch.isfinite(yhat).all())
     assert torch.equal(codes[0], model._quantizer.encode(yl)[0])
+    # BaseCompressor.forward (compressor.py:35-43), values only
+    img = uniform((2, 3, 64, 96), "forward.image", 2).cuda()
+    xhat, yhat, codes, logits = model(img)
+    assert tuple(xhat.shape) == (2, 3, 64, 96) and tuple(yhat.shape) == (2, 32, 8, 12) and bool(torch.isfinite(xhat).all())
+    assert [tuple(c.shape) for c in codes] == [(2, 2, 4, 6), (2, 2, 2, 3)]
+    neon, ximg = neon_inputs("neon_c32_gn", Neon)
+    neon = neon.cuda()
+    xhat, yhat, codes, logits = neon(ximg[:, :, :96].cuda())
+    assert tuple(xhat.shape) == (2, 3, 96, 128) and tuple(yhat.shape) == (2, 8, 12, 16) and bool(torch.isfinite(xhat).all())
+    assert len(codes) == 4 and all(torch.equal(c, l.argmax(-1)) for c, l in zip(codes, logits))
+    with pytest.raises(RuntimeError):
+        neon(ximg[:, :, :90].cuda())                        # sides must be multiples of 16
 
 
 @pytest.mark.gpu
