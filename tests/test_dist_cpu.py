@@ -66,6 +66,46 @@ def test_two_rank_histogram_all_gather(tmp_path):
         assert torch.allclose(parts[0]["freq"][lv], want) and torch.equal(parts[0]["freq"][lv], parts[1]["freq"][lv])
 
 
+def _neon_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from common import neon_inputs
+    from emulator import EmulatedLib
+    from mcquic_b200 import Neon
+    from mcquic_b200.dist import shard_bounds, sharded_encode
+    from mcquic_b200.engine import Engine
+    model, x = neon_inputs("neon_c64_plain", Neon)
+    model._engine = Engine(lib=EmulatedLib())
+    x = torch.cat([x, x.flip(-1), x.flip(-2)])               # 3 images over 2 ranks: shards of 2 + 1
+    lo, hi = shard_bounds(3, world, rank)
+    codes, ghist = sharded_encode(model, x[lo:hi], update_frequencies=True)
+    torch.save({"codes": codes, "hist": ghist, "freq": [f.clone() for f in model._quantizer._entropyCoder._freqEMA]},
+               os.path.join(out_dir, f"neon_rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_histogram_all_gather_neon(tmp_path):
+    """the same exchange step for the Neon tokenizer: one codebook per level (m is a list upstream), histogram
+    segment j = codes[j] (smallest level first), EMA 0.998 (VariousMCoder, entropyCoder.py:293-322)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    world, port = 2, _free_port()
+    mp.spawn(_neon_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    parts = [torch.load(tmp_path / f"neon_rank{r}.pt") for r in range(world)]
+    k, levels = 128, 2
+    allc = [torch.cat([p["codes"][j] for p in parts]) for j in range(levels)]
+    assert [tuple(c.shape) for c in allc] == [(3, 1, 8, 8), (3, 1, 8, 8)]
+    exp = torch.cat([torch.bincount(c.flatten(), minlength=k) for c in allc]).int()
+    assert torch.equal(parts[0]["hist"], exp) and torch.equal(parts[1]["hist"], exp)
+    for j in range(levels):
+        cnt = exp[j * k:(j + 1) * k].reshape(1, k).float()
+        want = 0.002 * cnt / cnt.sum(-1, keepdim=True) + 0.998 * torch.ones(1, k) / k
+        assert torch.allclose(parts[0]["freq"][j], want, atol=1e-7) and torch.equal(parts[0]["freq"][j], parts[1]["freq"][j])
+
+
 def test_shard_bounds_cover_everything():
     from mcquic_b200.dist import shard_bounds
     for total in (0, 1, 7, 64, 512):
