@@ -35,8 +35,12 @@ enum {
   MCQ_EPI_GDN    = 2, /* y = aux * rsqrt(conv + bias)   (conv over aux^2)    GenDivNorm, gdn.py:67-86              */
   MCQ_EPI_IGDN   = 3  /* y = aux *  sqrt(conv + bias)                        InvGenDivNorm, gdn.py:89-91           */
 };
-/* activation applied to y before it is written as a split-fp16 plane pair */
+/* activation applied to y before it is written as a split-fp16 plane pair.
+ * MCQ_ACT_SQUARE planes (the GDN / IGDN operand, gdn.py:74) hold y^2 * MCQ_SQUARE_SCALE: the power-of-two pre-scale keeps
+ * squares of activations up to |y| < 2047 inside fp16's range (65504); the convolution that consumes such planes folds
+ * 1 / MCQ_SQUARE_SCALE into its w_scale (exact). */
 enum { MCQ_ACT_NONE = 0, MCQ_ACT_SILU = 1, MCQ_ACT_SQUARE = 2 };
+#define MCQ_SQUARE_SCALE 0.015625f /* 2^-6 */
 /* output addressing */
 enum {
   MCQ_STORE_NHWC         = 0, /* [n, hout, wout, cout]                                                       */

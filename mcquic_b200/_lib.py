@@ -32,6 +32,7 @@ class ConvParams(_c.Structure):
 
 EPI_LINEAR, EPI_GATE, EPI_GDN, EPI_IGDN = 0, 1, 2, 3
 ACT_NONE, ACT_SILU, ACT_SQUARE = 0, 1, 2
+SQUARE_SCALE = 2.0 ** -6      # MCQ_SQUARE_SCALE: ACT_SQUARE planes hold y^2 * 2^-6 (fp16 range)
 STORE_NHWC, STORE_SHUFFLE_NHWC, STORE_SHUFFLE_NCHW = 0, 1, 2
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_DRIVER, ERR_CODE_RANGE, ERR_WATCHDOG = -1, -2, -3, -4, -5

@@ -98,7 +98,7 @@ __device__ __forceinline__ float silu_f(float x) {
 template <bool FAST>
 __device__ __forceinline__ float apply_act(float y, int act) {
   if (act == MCQ_ACT_SILU) return silu_f<FAST>(y);
-  if (act == MCQ_ACT_SQUARE) return y * y;
+  if (act == MCQ_ACT_SQUARE) return y * y * MCQ_SQUARE_SCALE;
   return y;
 }
 
@@ -136,7 +136,7 @@ __device__ __forceinline__ void act_group(const float (&y)[NV], float (&t)[NV], 
     for (int j = 0; j < NV; ++j) t[j] = silu_f<FAST>(y[j]);
   } else if (act == MCQ_ACT_SQUARE) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) t[j] = y[j] * y[j];
+    for (int j = 0; j < NV; ++j) t[j] = y[j] * y[j] * MCQ_SQUARE_SCALE;
   } else {
 #pragma unroll
     for (int j = 0; j < NV; ++j) t[j] = y[j];

@@ -40,10 +40,23 @@ inline void put_raw(uint64_t& x, uint32_t*& w, uint32_t value) {
   x = (x << kBypassBits) | value;
 }
 
-inline uint32_t get_raw(uint64_t& x, const uint32_t*& r) {
+// Every stream word is read through next_word(): a truncated or crafted stream (symbol count from an untrusted header)
+// runs out of words instead of reading past the buffer -- `bad` is set and zeros are fed from then on.
+struct Reader {
+  const uint32_t* r;
+  const uint32_t* end;
+  bool bad = false;
+  uint32_t next_word() {
+    if (r < end) return *r++;
+    bad = true;
+    return 0u;
+  }
+};
+
+inline uint32_t get_raw(uint64_t& x, Reader& rd) {
   const uint32_t v = (uint32_t)x & kBypassMax;
   x >>= kBypassBits;
-  if (x < kLow) x = (x << 32) | *r++;
+  if (x < kLow) x = (x << 32) | rd.next_word();
   return v;
 }
 
@@ -91,9 +104,12 @@ int64_t encode_stream(const int64_t* sym, int m, int hw, int k, const uint32_t* 
   return (int64_t)((buf + cap_words) - w) * 4;
 }
 
-void decode_stream(const uint32_t* r, int m, int hw, int k, const uint32_t* cdfs, const uint16_t* luts, int64_t* out) {
+// returns 0, or -3 when the stream ends before m * hw symbols were decoded (truncated / header does not match the stream)
+int decode_stream(const uint32_t* r, const uint32_t* end, int m, int hw, int k, const uint32_t* cdfs,
+                  const uint16_t* luts, int64_t* out) {
+  if (end - r < 2) return -3;
   uint64_t x = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
-  r += 2;
+  Reader rd{r + 2, end};
   const int cdf_len = k + 1;
   const uint64_t mask = (1ull << kPrec) - 1;
   for (int mi = 0; mi < m; ++mi) {
@@ -104,20 +120,22 @@ void decode_stream(const uint32_t* r, int m, int hw, int k, const uint32_t* cdfs
       const uint32_t s = lut[cum];
       const uint32_t lo = cdf[s], range = cdf[s + 1] - lo;
       x = (uint64_t)range * (x >> kPrec) + (x & mask) - lo;
-      if (x < kLow) x = (x << 32) | *r++;
+      if (x < kLow) x = (x << 32) | rd.next_word();
       int64_t v = s;
       if ((int)s == k) {   // bypass (never produced for codes in [0, k))
-        uint32_t val = get_raw(x, r);
+        uint32_t val = get_raw(x, rd);
         int nb = (int)val;
-        while (val == kBypassMax) { val = get_raw(x, r); nb += (int)val; }
+        while (val == kBypassMax && !rd.bad) { val = get_raw(x, rd); nb += (int)val; }
         uint32_t raw = 0;
-        for (int b = 0; b < nb; ++b) raw |= get_raw(x, r) << (b * kBypassBits);
+        for (int b = 0; b < nb && b < 8; ++b) raw |= get_raw(x, rd) << (b * kBypassBits);
         v = raw >> 1;
         v = (raw & 1) ? -v - 1 : v + k;
       }
+      if (rd.bad) return -3;
       out[(size_t)mi * hw + j] = v;
     }
   }
+  return 0;
 }
 
 template <class F>
@@ -195,6 +213,7 @@ int mcq_rans_decode_level(const uint8_t* in, const int32_t* in_sizes, int64_t st
   for (int mi = 0; mi < m; ++mi) {
     const uint32_t* cdf = cdfs + (size_t)mi * (k + 1);
     uint16_t* lut = luts.data() + ((size_t)mi << kPrec);
+    if (cdf[0] != 0 || cdf[k] != (1u << kPrec)) return -1;     // the table must cover [0, 2^16) completely
     for (int s = 0; s < k; ++s) {
       if (cdf[s + 1] < cdf[s] || cdf[s + 1] > (1u << kPrec)) return -1;
       for (uint32_t c = cdf[s]; c < cdf[s + 1]; ++c) lut[c] = (uint16_t)s;
@@ -202,11 +221,15 @@ int mcq_rans_decode_level(const uint8_t* in, const int32_t* in_sizes, int64_t st
   }
   for (int i = 0; i < n; ++i)
     if (in_sizes[i] < 8 || in_sizes[i] % 4 != 0 || in_sizes[i] > stride) return -2;
+  std::vector<int> status((size_t)n, 0);
   parallel_for(n, n_threads, [&](int i) {
-    std::vector<uint32_t> words((size_t)in_sizes[i] / 4 + 2, 0u);   // aligned copy (+2 words of slack)
+    const size_t nwords = (size_t)in_sizes[i] / 4;
+    std::vector<uint32_t> words(nwords, 0u);   // aligned copy
     std::memcpy(words.data(), in + (size_t)i * stride, (size_t)in_sizes[i]);
-    decode_stream(words.data(), m, hw, k, cdfs, luts.data(), codes_out + (size_t)i * m * hw);
+    status[i] = decode_stream(words.data(), words.data() + nwords, m, hw, k, cdfs, luts.data(),
+                              codes_out + (size_t)i * m * hw);
   });
+  for (int s : status) if (s) return s;
   return 0;
 }
 

@@ -324,8 +324,10 @@ class Engine:
     # ------------------------------------------------------------------ one fused conv launch
     def conv(self, pc: PackedConv, a: Planes, x: Act, want: Set[str], *, mode: int = _lib.EPI_LINEAR,
              res1: Optional[torch.Tensor] = None, res1_scale: float = 1.0, res2: Optional[torch.Tensor] = None,
-             aux: Optional[torch.Tensor] = None, into: Optional[Act] = None, gn_groups: int = 0) -> Act:
-        """gn_groups > 0: a nn.GroupNorm(gn_groups, cout) follows; where the kernel can (mcq_conv_gn_layout) its
+             aux: Optional[torch.Tensor] = None, into: Optional[Act] = None, gn_groups: int = 0,
+             a_scale: float = 1.0) -> Act:
+        """a_scale: power-of-two factor the A planes carry (x^2 planes: _lib.SQUARE_SCALE); undone through w_scale.
+        gn_groups > 0: a nn.GroupNorm(gn_groups, cout) follows; where the kernel can (mcq_conv_gn_layout) its
         epilogue also writes the per-row-block (sum, sum^2) partials of the fp32 output -> `out.gn`.
         into: write the outputs into these caller-owned tensors (same shapes / representations as `want`) instead
         of allocating them -- used when a batch is processed in chunks that fill slices of one full-batch tensor."""
@@ -341,7 +343,7 @@ class Engine:
         p.n, p.hin, p.win, p.cin = x.n, x.h, x.w, x.c
         p.w_hi, p.w_lo = _ptr(pc.w_hi), _ptr(pc.w_lo)
         p.cout, p.cout_pad, p.ksize, p.stride = pc.cout, pc.cout_pad, pc.ksize, pc.stride
-        p.w_scale = pc.w_scale
+        p.w_scale = pc.w_scale / a_scale
         p.bias = _ptr(pc.bias)
         p.mode, p.store = mode, pc.store
         p.res1, p.res1_scale, p.res2, p.aux = _ptr(res1), res1_scale, _ptr(res2), _ptr(aux)
@@ -477,14 +479,16 @@ class Engine:
 
     def residual_block_stride(self, mod: ResidualBlockWithStride, x: Act, want: Set[str]) -> Act:
         u = self.conv(self._packed_for(mod._branch[1]), x.silu, x, {"f32", "sq"})
-        t = self.conv(self._packed_for(mod._branch[2]), u.sq, u, {"raw"}, mode=_lib.EPI_GDN, aux=u.f32)
+        t = self.conv(self._packed_for(mod._branch[2]), u.sq, u, {"raw"}, mode=_lib.EPI_GDN, aux=u.f32,
+                      a_scale=_lib.SQUARE_SCALE)
         s = self.conv(self._packed_for(mod._skip), x.raw, x, {"f32"})
         return self.conv(self._packed_for(mod._branch[3]), t.raw, t, want, res1=s.f32)
 
     def residual_block_shuffle(self, mod: ResidualBlockShuffle, x: Act, want: Set[str]) -> Act:
         sh = _lib.STORE_SHUFFLE_NHWC
         u = self.conv(self._packed_for(mod._branch[1][0], sh), x.silu, x, {"f32", "sq"})
-        t = self.conv(self._packed_for(mod._branch[2]), u.sq, u, {"raw"}, mode=_lib.EPI_IGDN, aux=u.f32)
+        t = self.conv(self._packed_for(mod._branch[2]), u.sq, u, {"raw"}, mode=_lib.EPI_IGDN, aux=u.f32,
+                      a_scale=_lib.SQUARE_SCALE)
         s = self.conv(self._packed_for(mod._skip[0], sh), x.raw, x, {"f32"})
         return self.conv(self._packed_for(mod._branch[3]), t.raw, t, want, res1=s.f32)
 

@@ -33,10 +33,12 @@ def build(force: bool = False) -> str:
         gxx = shutil.which("g++")
         if gxx is None:
             raise RuntimeError("g++ not found: cannot build libmcquic_entropy.so")
-        res = subprocess.run([gxx, "-O3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", _LIB_PATH, _SRC],
+        tmp = f"{_LIB_PATH}.{os.getpid()}.tmp"      # concurrent ranks must never dlopen a half-written library
+        res = subprocess.run([gxx, "-O3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", tmp, _SRC],
                              capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("g++ failed:\n" + res.stderr)
+        os.replace(tmp, _LIB_PATH)
     return _LIB_PATH
 
 
@@ -81,8 +83,20 @@ def encode_level(codes: torch.Tensor, cdfs: np.ndarray, threads: int = 0) -> Lis
     return [out[i, :sizes[i]].tobytes() for i in range(n)]
 
 
+MAX_SYMBOLS_PER_STREAM = 1 << 26      # 64 Mi codes per image and level (an 8192 x 8192 code map): header sanity bound
+
+
 def decode_level(streams: Sequence[bytes], m: int, h: int, w: int, cdfs: np.ndarray, threads: int = 0) -> torch.Tensor:
+    """inverse of encode_level.  m, h, w usually come from an untrusted `.mcq` header: they are checked against the CDF
+    table and a sanity bound before anything is allocated, and the C++ decoder stops with an error when a stream runs
+    out of words (truncated file / header claiming more symbols than the stream holds)."""
     n = len(streams)
+    if n < 1:
+        raise RuntimeError("rANS decode: no streams")
+    if cdfs.ndim != 2 or m != cdfs.shape[0]:
+        raise RuntimeError(f"rANS decode: header says m = {m}, the model's CDF table has {cdfs.shape[0]} codebooks")
+    if h < 1 or w < 1 or m * h * w > MAX_SYMBOLS_PER_STREAM:
+        raise RuntimeError(f"rANS decode: implausible code map {m} x {h} x {w}")
     k = cdfs.shape[1] - 1
     stride = max(len(s) for s in streams)
     stride = (stride + 3) // 4 * 4

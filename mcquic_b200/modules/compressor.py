@@ -5,6 +5,7 @@
     codes = model.encode(x)        # x fp32 [n,3,H,W] in [-1,1]  ->  L x int64 [n, m, h_l, w_l]
     xHat  = model.decode(codes)    # fp32 [n, 3, H_pad, W_pad]
 """
+from collections import OrderedDict
 from typing import List, Optional, Tuple
 
 import torch
@@ -24,6 +25,41 @@ def aligned_pad_amounts(h: int, w: int, base: int = ALIGN_BASE) -> Tuple[int, in
     return hPadding // 2, wPadding // 2, h + hPadding, w + wPadding
 
 
+class _ShapeCache:
+    """LRU of per-input-shape CUDA graphs / host-I/O pipelines (static buffers + captured activations: hundreds of MB per
+    shape at batch 64).  Bounded by entry count and by the device bytes the entries hold, so that a service fed
+    arbitrary image sizes does not grow without limit; evicted graphs are re-captured on their next use."""
+
+    def __init__(self, max_entries: int = 12, max_bytes: int = 24 << 30):
+        self.max_entries, self.max_bytes = max_entries, max_bytes
+        self._d: "OrderedDict[object, Tuple[object, int]]" = OrderedDict()
+
+    def get(self, key):
+        hit = self._d.get(key)
+        if hit is None:
+            return None
+        self._d.move_to_end(key)
+        return hit[0]
+
+    def put(self, key, value, nbytes: int):
+        self._d[key] = (value, max(0, int(nbytes)))
+        self._d.move_to_end(key)
+        while len(self._d) > 1 and (len(self._d) > self.max_entries or self.bytes() > self.max_bytes):
+            self._d.popitem(last=False)
+
+    def bytes(self) -> int:
+        return sum(b for _, b in self._d.values())
+
+    def clear(self):
+        self._d.clear()
+
+    def __len__(self):
+        return len(self._d)
+
+    def __contains__(self, key):
+        return key in self._d
+
+
 class BaseCompressor(nn.Module):
     def __init__(self, encoder: nn.Module, quantizer: UMGMQuantizer, decoder: nn.Module):
         super().__init__()
@@ -36,11 +72,12 @@ class BaseCompressor(nn.Module):
         self.decode_passes = 1  # single fp16 pass: TF32-grade, pixels within 1e-3
         # encode/decode are ~170 dependent launches each: replay them as one CUDA graph per input shape
         self.use_graphs = True
-        self._graphs = {}
+        self._graphs = _ShapeCache()
+        self._weights_seen = None  # fingerprint of the parameters the cached graphs / packed weights were built from
         self.graph_launches = 0  # kernels launched through graph replays (the library counts eager launches)
         # host I/O pipeline: a pinned host batch is processed in up to 4 slices through the first (encode) / last
         # (decode) full-resolution layers so that the PCIe copies overlap the convolutions
-        self._pipes = {}
+        self._pipes = _ShapeCache()
         self._copy_stream = None
 
     @property
@@ -121,18 +158,48 @@ class BaseCompressor(nn.Module):
                 and isinstance(self._encoder[1], ResidualBlock) and isinstance(self._decoder[5], ResidualBlock))
 
     def invalidate(self):
-        """Drop captured graphs and repacked weights (call after changing parameters in place)."""
+        """Drop captured graphs and repacked weights.  Called automatically when the parameters change (see
+        `_check_weights`); only writes that bypass autograd's version counters (`p.data.copy_()`) need an explicit call."""
         self._graphs.clear()
         self._pipes.clear()
+        self._weights_seen = None
         if self._engine is not None:
             self._engine._packed.clear()
 
+    def _weights_fingerprint(self) -> int:
+        """cheap identity of the current parameter values: the sum of the in-place version counters of every parameter
+        and buffer -- an optimizer step, `load_state_dict`, `p.copy_()` all bump one (`.to()` / `load_state_dict` also go
+        through `invalidate`)"""
+        ts = self.__dict__.get("_fp_tensors")
+        if ts is None:
+            ts = []
+            for t in list(self.parameters()) + list(self.buffers()):
+                try:
+                    t._version
+                    ts.append(t)
+                except RuntimeError:      # inference tensor: immutable, nothing to track
+                    pass
+            self.__dict__["_fp_tensors"] = ts
+        return sum(t._version for t in ts) + (len(ts) << 40)
+
+    def _check_weights(self):
+        """graphs replay launches whose operands (packed weights, packed codebooks) were baked in at capture time: before
+        any replay make sure the parameters are still the ones they were captured from"""
+        fp = self._weights_fingerprint()
+        if fp != self._weights_seen:
+            if self._weights_seen is not None:
+                self._graphs.clear()
+                self._pipes.clear()
+            self._weights_seen = fp
+
     def load_state_dict(self, *args, **kwargs):
         self.invalidate()
+        self.__dict__.pop("_fp_tensors", None)
         return super().load_state_dict(*args, **kwargs)
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate()
+        self.__dict__.pop("_fp_tensors", None)
         return super()._apply(fn, *args, **kwargs)
 
     # ------------------------------------------------------------------ eager bodies
@@ -154,11 +221,13 @@ class BaseCompressor(nn.Module):
         eng.flush()
         return out
 
-    def _graph(self, key, make_static, body):
-        """Capture `body(*static)` once per key; returns (graph, static inputs, static outputs, #launches)."""
-        entry = self._graphs.get(key)
+    def _graph(self, key, make_static, body, cache: bool = True):
+        """Capture `body(*static)` once per key; returns (graph, static inputs, static outputs, #launches).
+        cache=False: the caller (a host-I/O pipeline, itself an LRU entry) owns the graph."""
+        entry = self._graphs.get(key) if cache else None
         if entry is None:
             from .. import _lib
+            mem0 = torch.cuda.memory_allocated()
             static = make_static()
             cur = torch.cuda.current_stream()
             warm = torch.cuda.Stream()
@@ -172,7 +241,8 @@ class BaseCompressor(nn.Module):
             with torch.cuda.graph(graph):
                 out = body(*static)
             entry = (graph, static, out, _lib.launch_count() - before)
-            self._graphs[key] = entry
+            if cache:
+                self._graphs.put(key, entry, torch.cuda.memory_allocated() - mem0)
         return entry
 
     # ------------------------------------------------------------------ host I/O pipeline
@@ -224,6 +294,7 @@ class BaseCompressor(nn.Module):
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
             if pipe is None:
+                mem0 = torch.cuda.memory_allocated()
                 eng = self.engine
                 eng.passes = self.encode_passes
                 total = self._quantizer.hist_size()
@@ -235,7 +306,8 @@ class BaseCompressor(nn.Module):
                 heads, launches = [], 0
                 for c, (n0, n1) in enumerate(bounds):
                     g, _, _, l = self._graph(key + ("head", c), list,
-                                             lambda n0=n0, n1=n1: self._encode_head(sx[n0:n1], y1.batch_slice(n0, n1)))
+                                             lambda n0=n0, n1=n1: self._encode_head(sx[n0:n1], y1.batch_slice(n0, n1)),
+                                             cache=False)
                     heads.append(g)
                     launches += l
 
@@ -243,16 +315,17 @@ class BaseCompressor(nn.Module):
                     sh.zero_()
                     return self._encode_tail(y1, sh)
 
-                gt, _, codes, l = self._graph(key + ("tail",), list, tail)
-                pipe = self._pipes[key] = dict(sx=sx, sh=sh, y1=y1, heads=heads, tail=gt, codes=codes,
-                                               launches=launches + l,
-                                               events=[torch.cuda.Event() for _ in bounds])
+                gt, _, codes, l = self._graph(key + ("tail",), list, tail, cache=False)
+                pipe = dict(sx=sx, sh=sh, y1=y1, heads=heads, tail=gt, codes=codes, launches=launches + l,
+                            events=[torch.cuda.Event() for _ in bounds], done=torch.cuda.Event())
+                self._pipes.put(key, pipe, torch.cuda.memory_allocated() - mem0)
             main, copy = self._streams(dev)
             copy.wait_stream(main)          # the previous step's graphs may still read the staging buffer
             with torch.cuda.stream(copy):
                 for c, (n0, n1) in enumerate(bounds):
                     pipe["sx"][n0:n1].copy_(x[n0:n1], non_blocking=True)
                     pipe["events"][c].record(copy)
+                pipe["done"].record(copy)
             for c in range(len(bounds)):
                 main.wait_event(pipe["events"][c])
                 pipe["heads"][c].replay()
@@ -260,7 +333,11 @@ class BaseCompressor(nn.Module):
             self.graph_launches += pipe["launches"]
             if hist is not None:
                 hist += pipe["sh"]
-            return [c.clone() for c in pipe["codes"]]
+            out = [c.clone() for c in pipe["codes"]]
+            # the caller may refill its pinned batch as soon as encode() returns (double buffering): all H2D copies of
+            # `x` have completed by then (they finished long before the graphs queued behind them do)
+            pipe["done"].synchronize()
+            return out
 
     def _decode_pipelined(self, codes: List[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
         """out: pinned host batch.  The pixels of chunk c travel to the host while chunk c+1 runs the last layers."""
@@ -271,6 +348,7 @@ class BaseCompressor(nn.Module):
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
             if pipe is None:
+                mem0 = torch.cuda.memory_allocated()
                 sc = [torch.zeros_like(c) for c in codes]
                 status = torch.zeros(1, dtype=torch.int32, device=dev)
                 sout = torch.empty(tuple(out.shape), dtype=torch.float32, device=dev)
@@ -279,17 +357,19 @@ class BaseCompressor(nn.Module):
                     status.zero_()
                     return self._decode_main(sc, status)
 
-                gm, _, y4, launches = self._graph(key + ("main",), list, main_body)
+                gm, _, y4, launches = self._graph(key + ("main",), list, main_body, cache=False)
                 if (y4.n, 2 * y4.h, 2 * y4.w) != (out.shape[0], out.shape[2], out.shape[3]) or out.shape[1] != 3:
                     raise RuntimeError(f"`out` must be [n, 3, H_pad, W_pad] = [{y4.n}, 3, {2 * y4.h}, {2 * y4.w}]")
                 tails = []
                 for c, (n0, n1) in enumerate(bounds):
                     g, _, _, l = self._graph(key + ("tail", c), list,
-                                             lambda n0=n0, n1=n1: self._decode_tail(y4.batch_slice(n0, n1), sout[n0:n1]))
+                                             lambda n0=n0, n1=n1: self._decode_tail(y4.batch_slice(n0, n1), sout[n0:n1]),
+                                             cache=False)
                     tails.append(g)
                     launches += l
-                pipe = self._pipes[key] = dict(sc=sc, status=status, sout=sout, main=gm, tails=tails, y4=y4,
-                                               launches=launches, events=[torch.cuda.Event() for _ in bounds])
+                pipe = dict(sc=sc, status=status, sout=sout, main=gm, tails=tails, y4=y4, launches=launches,
+                            events=[torch.cuda.Event() for _ in bounds])
+                self._pipes.put(key, pipe, torch.cuda.memory_allocated() - mem0)
             main, copy = self._streams(dev)
             for dst, src in zip(pipe["sc"], codes):
                 dst.copy_(src)
@@ -313,6 +393,7 @@ class BaseCompressor(nn.Module):
         x may also be a pinned fp32 host batch: it is then streamed to the GPU in chunks that overlap the first layers
         (codes are returned on the model's device)."""
         self._check_image(x)
+        self._check_weights()
         if not x.is_cuda and self._host_batch_ok(x):
             return self._encode_pipelined(x, hist)
         if not (self.use_graphs and x.is_cuda):
@@ -342,6 +423,7 @@ class BaseCompressor(nn.Module):
         that overlap the last layers, and `out` is returned (complete when the call returns)."""
         if len(codes) == 0:
             raise RuntimeError("Length of codes is 0.")
+        self._check_weights()
         dev = codes[0].device
         if out is not None:
             ok = all(c.is_cuda and c.dtype == torch.int64 and c.dim() == 4 and c.is_contiguous() for c in codes)

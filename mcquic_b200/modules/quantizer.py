@@ -118,7 +118,23 @@ class CodeFrequency(nn.Module):
     def decompress(self, binaries, codeSizes) -> List[torch.Tensor]:
         """inverse of `compress` (entropyCoder.py:128-154): L x int64 [n, m, h, w] on this module's device."""
         from .. import entropy
+        if len(binaries) < 1 or len(binaries) != len(codeSizes):
+            raise RuntimeError("decompress: one CodeSize record per image is required")
         size = codeSizes[0]
+        levels = len(self._k)
+        # the header comes from a file: everything in it is checked against the model before the coder sees it
+        for cs in codeSizes:
+            if (list(cs.m), list(cs.heights), list(cs.widths), list(cs.k)) != \
+                    (list(size.m), list(size.heights), list(size.widths), list(size.k)):
+                raise RuntimeError("decompress: all images of a batch must share one CodeSize")
+        if not (len(size.m) == len(size.heights) == len(size.widths) == len(size.k) == levels):
+            raise RuntimeError(f"decompress: header describes {len(size.k)} code levels, the model has {levels}")
+        if list(size.k) != list(self._k) or list(size.m) != self.level_m():
+            raise RuntimeError(f"decompress: header (m = {list(size.m)}, k = {list(size.k)}) does not match the model "
+                               f"(m = {self.level_m()}, k = {list(self._k)})")
+        for b in binaries:
+            if len(b) != levels:
+                raise RuntimeError(f"decompress: expected {levels} streams per image, got {len(b)}")
         out = []
         for lv, cdf in enumerate(self.CDFs):
             streams = [b[lv] for b in binaries]
@@ -164,7 +180,7 @@ class _multiCodebookQuantization(nn.Module):
             order = torch.argsort(row, descending=True)
             new[j, never] = self._codebook.detach()[j][order][:count]
         moved = ((new - self._codebook.detach()) ** 2).sum(-1) > 1e-4
-        self._codebook.data.copy_(new)
+        self._codebook.copy_(new)        # in place under no_grad: bumps the version counter the weight caches key on
         return moved.flatten()
 
     @torch.no_grad()
@@ -173,7 +189,7 @@ class _multiCodebookQuantization(nn.Module):
         import torch.distributed as dist
         codebook = self._codebook.detach().clone()
         dist.broadcast(codebook, 0)
-        self._codebook.data.copy_(codebook)
+        self._codebook.copy_(codebook)
 
     def _tables(self):
         """Per codebook version: fp32 codebook, |c_k|^2 [m, k] (quantizer.py:165) and the split-fp16 packing the

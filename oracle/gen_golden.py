@@ -127,13 +127,89 @@ def neon():
               "xhat absmax", float(xhat.abs().max()))
 
 
+def _codes_rec(codes, margins):
+    """codes as int16 (k <= 8192 everywhere), the oracle's top-2 relative margins next to them"""
+    rec = {"codes_sha256": np.array(sha(torch.cat([q.flatten() for q in codes])))}
+    for lv, (q, mg) in enumerate(zip(codes, margins)):
+        assert int(q.max()) < 32768
+        rec[f"codes_{lv}"] = q.numpy().astype(np.int16)
+        rec[f"margin_{lv}"] = mg.numpy().astype(np.float32)
+    rec["min_margin"] = np.array(min(float(mg.min()) for mg in margins))
+    return rec
+
+
+def baseline_configs():
+    """The BASELINE.json configurations themselves, from the imported reference:
+    * tests/golden/bench_qp1_n64.npz: ALL codes of the 64 images `bench.py` times (configs[1]: qp=1, 64x3x256x256,
+      input = uniform(.., "bench.image.0", 0)), pixels sampled every 16th row / column + sha256;
+    * tests/golden/compressor_q6_512.npz: Q6 = Compressor(192, 6, [2048]*3) on 10 images of 512x512 (configs[2]'s model);
+    * tests/golden/vq_cfg3_full.npz: configs[2]'s VQ alone at FULL size (N=32, 32x32 grid, M=6, K=2048, d=32), the
+      reference `_multiCodebookQuantization.encode` run image by image (images are independent in the bmm)."""
+    ref_import.load()
+    from mcquic.modules.compressor import Compressor
+    from mcquic.modules.quantizer import _multiCodebookQuantization
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_num_threads(8)
+
+    def run(c, m, k, x, chunk, stride, with_pixels=True):
+        sd = synthetic_state_dict(c, m, k, seed=0)
+        model = Compressor(c, m, list(k)).eval()
+        model.load_state_dict(sd)
+        codes, margins, xs = [], [], []
+        for i in range(0, x.shape[0], chunk):
+            with torch.inference_mode():
+                cd = model.encode(x[i:i + chunk])
+                if with_pixels:
+                    xs.append(model.decode(cd)[..., ::stride, ::stride].clone())
+            # the oracle must agree with the reference bit for bit here as well (it supplies the margins)
+            oc, mg = O.encode(sd, x[i:i + chunk], with_margin=True)
+            assert all(torch.equal(a, b) for a, b in zip(cd, oc)), "oracle != reference"
+            codes.append(cd)
+            margins.append(mg)
+            print("  images", i, "..", i + chunk, flush=True)
+        codes = [torch.cat([cc[lv] for cc in codes]) for lv in range(len(k))]
+        margins = [torch.cat([mm[lv] for mm in margins]) for lv in range(len(k))]
+        rec = _codes_rec(codes, margins)
+        if with_pixels:
+            rec["xhat_sample"] = torch.cat(xs).numpy().astype(np.float32)
+        rec["config"] = np.array([c, m, x.shape[0], x.shape[2], x.shape[3], stride] + list(k), dtype=np.int64)
+        return rec
+
+    x = uniform((64, 3, 256, 256), "bench.image.0", 0)
+    rec = run(128, 1, [8192, 2048, 512], x, 8, 16)
+    np.savez_compressed(os.path.join(OUT, "bench_qp1_n64.npz"), **rec)
+    print("bench_qp1_n64", sum(rec[f"codes_{lv}"].size for lv in range(3)), "codes, min margin", float(rec["min_margin"]))
+
+    x = uniform((10, 3, 512, 512), "q6.image", 5)
+    rec = run(192, 6, [2048, 2048, 2048], x, 1, 32)
+    np.savez_compressed(os.path.join(OUT, "compressor_q6_512.npz"), **rec)
+    print("compressor_q6_512", sum(rec[f"codes_{lv}"].size for lv in range(3)), "codes, min margin", float(rec["min_margin"]))
+
+    m, k, d, n, h, w = 6, 2048, 32, 32, 32, 32
+    cb = uniform((m, k, d), "vq.codebook", 3) * ((2.0 / (5 * d)) ** 0.5 * 3 ** 0.5)
+    x = uniform((n, m * d, h, w), "vq.latent.full", 3) * 0.26
+    q = _multiCodebookQuantization(torch.nn.Parameter(cb.clone()), 0.0)
+    with torch.inference_mode():
+        code = torch.cat([q.encode(x[i:i + 1]) for i in range(n)])
+    margin = torch.cat([O.vq_margin(x[i:i + 1], cb) for i in range(n)])
+    assert torch.equal(code, torch.cat([O.vq_assign(x[i:i + 1], cb) for i in range(n)]))
+    np.savez_compressed(os.path.join(OUT, "vq_cfg3_full.npz"), config=np.array([m, k, d, n, h, w], dtype=np.int64),
+                        codes=code.numpy().astype(np.int16), margin=margin.numpy().astype(np.float16),
+                        min_margin=np.array(float(margin.min())), codes_sha256=np.array(sha(code)))
+    print("vq_cfg3_full", code.numel(), "codes, min margin", float(margin.min()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if "--blocks" in sys.argv:
         blocks()
     elif "--neon" in sys.argv:
         neon()
+    elif "--baseline" in sys.argv:
+        baseline_configs()
     else:
         main()
         blocks()
         neon()
+        baseline_configs()

@@ -27,6 +27,19 @@ def golden_codes(g, levels):
     return [torch.from_numpy(g[f"codes_{lv}"].astype(np.int64)) for lv in range(levels)]
 
 
+# every oracle / golden comparison of code indices reports here; tests/conftest.py prints the list at the end of the run,
+# so the driver's log shows how many indices flipped (the green run must show 0 everywhere) and how thin the oracle's
+# smallest top-2 margin was for that case
+PARITY_LOG = []
+
+
+def log_parity(case, flips, total, at=(), min_margin=None):
+    PARITY_LOG.append(dict(case=case, flips=int(flips), total=int(total), flip_margins=[float(a) for a in at][:8],
+                           min_margin=None if min_margin is None else float(min_margin)))
+    print(f"[parity] {case}: flips {flips}/{total}" + ("" if min_margin is None else f", oracle min top-2 margin {min_margin:.3e}")
+          + (f", margins at the flips {sorted(float(a) for a in at)[:8]}" if flips else ""))
+
+
 def code_report(got, ref, margins=None):
     """(#mismatches, total, margins at the mismatching positions)"""
     flips, total, at = 0, 0, []

@@ -25,3 +25,23 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """code-index parity of every oracle / golden comparison that ran (tests/common.py:log_parity)"""
+    try:
+        from common import PARITY_LOG
+    except Exception:
+        return
+    if not PARITY_LOG:
+        return
+    tr = terminalreporter
+    tr.write_sep("-", "code-index parity vs oracle / reference goldens")
+    total = flips = 0
+    for r in PARITY_LOG:
+        total += r["total"]
+        flips += r["flips"]
+        mm = "" if r["min_margin"] is None else f"  (oracle min top-2 margin {r['min_margin']:.2e})"
+        extra = f"  margins at flips {r['flip_margins']}" if r["flips"] else ""
+        tr.write_line(f"{r['case']}: {r['flips']} flips / {r['total']} codes{mm}{extra}")
+    tr.write_line(f"TOTAL: {flips} flips / {total} codes compared")

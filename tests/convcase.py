@@ -72,7 +72,7 @@ def run_case(eng: Engine, *, n, h, w, cin, cout, ksize=3, stride=1, passes=3, st
         y = aux.double() / torch.sqrt(y)
     else:
         y = aux.double() * torch.sqrt(y)
-    exp = {"f32": y, "raw": y, "silu": F.silu(y), "sq": y * y}
+    exp = {"f32": y, "raw": y, "silu": F.silu(y), "sq": y * y * _lib.SQUARE_SCALE}
     return out, exp, pc
 
 

@@ -34,7 +34,7 @@ def _act(y, act):
     if act == _lib.ACT_SILU:
         return F.silu(y)
     if act == _lib.ACT_SQUARE:
-        return y * y
+        return y * y * _lib.SQUARE_SCALE
     return y
 
 

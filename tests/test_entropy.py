@@ -100,6 +100,56 @@ def test_streams_match_python_oracle_and_round_trip():
         entropy.decode_level([b"\x00" * 6], m, h, w, cdfs)                     # truncated stream
 
 
+def test_decoder_never_reads_past_a_stream_and_headers_are_validated():
+    """the symbol count comes from an untrusted `.mcq` header.  A valid 12-byte stream decoded with
+    h = w = 4096 used to walk off the buffer (segfault); now the C++ decoder stops with -3 when the words run out, and the
+    Python layer checks header fields against the model before the coder sees them."""
+    rng = np.random.default_rng(5)
+    k = 64
+    cdfs = np.stack([entropy.pmf_to_quantized_cdf(rng.random(k))])
+    codes = torch.from_numpy(rng.integers(0, k, (1, 1, 2, 2)))
+    stream = entropy.encode_level(codes, cdfs)[0]
+    assert len(stream) <= 16
+    assert torch.equal(entropy.decode_level([stream], 1, 2, 2, cdfs), codes)
+    for h, w in ((4096, 4096), (64, 64), (3, 3)):                      # header claims more symbols than the stream holds
+        with pytest.raises(RuntimeError, match="rANS decode"):
+            entropy.decode_level([stream], 1, h, w, cdfs)
+    big = entropy.encode_level(torch.from_numpy(rng.integers(0, k, (1, 1, 32, 32))), cdfs)[0]
+    for cut in (8, 12, len(big) // 2 // 4 * 4, len(big) - 4):           # truncated files
+        with pytest.raises(RuntimeError, match="rANS decode"):
+            entropy.decode_level([big[:cut]], 1, 32, 32, cdfs)
+    with pytest.raises(RuntimeError, match="rANS decode"):
+        entropy.decode_level([stream], 2, 2, 2, cdfs)                  # m larger than the CDF table
+    with pytest.raises(RuntimeError, match="implausible"):
+        entropy.decode_level([stream], 1, 1 << 20, 1 << 20, cdfs)      # would be a multi-terabyte allocation
+    with pytest.raises(RuntimeError):
+        entropy.decode_level([], 1, 2, 2, cdfs)
+    bad = cdfs.copy()
+    bad[0, -1] = 60000                                                # table does not cover [0, 2^16)
+    with pytest.raises(RuntimeError, match="rANS decode"):
+        entropy.decode_level([stream], 1, 2, 2, bad)
+    # CodeFrequency.decompress: header vs model
+    from mcquic_b200 import Compressor
+    model = Compressor(32, 2, [16, 8]).eval()
+    coder = model._quantizer._entropyCoder
+    cds = [torch.from_numpy(rng.integers(0, 16, (2, 2, 4, 4))), torch.from_numpy(rng.integers(0, 8, (2, 2, 2, 2)))]
+    bins, sizes = coder.compress(cds)
+    assert all(torch.equal(a, b) for a, b in zip(coder.decompress(bins, sizes), cds))
+    def header(**kw):
+        f = dict(m=[2, 2], heights=[4, 2], widths=[4, 2], k=[16, 8])
+        f.update(kw)
+        return [entropy.CodeSize(**f)] * 2
+    for hd in (header(m=[3, 2]), header(k=[16, 16]), header(m=[2], heights=[4], widths=[4], k=[16]),
+               header(heights=[4096, 2], widths=[4096, 2]), header(heights=[4, 2, 1]),
+               [entropy.CodeSize([2, 2], [4, 2], [4, 2], [16, 8]), entropy.CodeSize([2, 2], [8, 2], [4, 2], [16, 8])]):
+        with pytest.raises(RuntimeError):
+            coder.decompress(bins, hd)
+    with pytest.raises(RuntimeError):
+        coder.decompress([b[:1] for b in bins], sizes)                 # a level's stream is missing
+    with pytest.raises(RuntimeError):
+        coder.decompress(bins[:1], sizes)
+
+
 def test_compress_decompress_api_and_bpp_known_answer():
     """qp=1, 256x256, uniform prior: the reference flow gives 424 + 96 + 24 bytes = 0.0664 bpp.
     Uses the golden codes (reference outputs); compress()/decompress() run through the emulated engine on CPU."""
