@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 CHANNEL, M, K = 128, 1, [8192, 2048, 512]   # qp=1
 BATCH, H, W = 64, 256, 256
+STRONG_TOTAL = 512                           # BASELINE configs[3]: qp=1 batch 512 sharded over the ranks
 ALG_GFLOP_PER_IMAGE = 89.44                  # encode 37.33 + decode 52.11 at 256x256
 METRIC = "encode+decode MPix/s at qp=1, batch 64x3x256x256"
 
@@ -103,12 +104,42 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+CPU_SAMPLE = 8      # images per CPU step: the SAME bounded sample for `cpu_baseline` and for `--impl reference`
+
+
+def _physical_cores() -> int:
+    """physical cores this process may run on (k = physical cores of the box, stated): distinct
+    (package, core) pairs of /proc/cpuinfo restricted to the affinity mask; falls back to psutil / os.cpu_count()"""
+    try:
+        allowed = os.sched_getaffinity(0)
+        cores, cpu, phys = set(), None, 0
+        with open("/proc/cpuinfo") as fp:
+            for line in fp:
+                key, _, val = line.partition(":")
+                key, val = key.strip(), val.strip()
+                if key == "processor":
+                    cpu = int(val)
+                elif key == "physical id":
+                    phys = int(val)
+                elif key == "core id" and cpu in allowed:
+                    cores.add((phys, int(val)))
+        if cores:
+            return len(cores)
+    except Exception:
+        pass
+    try:
+        import psutil
+        return psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def _cpu_oracle_throughput(sample_images: int, repeats: int):
     """encode+decode MPix/s of the CPU oracle on `sample_images` synthetic 256x256 images, best of `repeats`."""
     import torch
     from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
     from oracle import mcquic_oracle as oracle
-    cores = os.cpu_count() or 1
+    cores = _physical_cores()
     torch.set_num_threads(cores)
     sd = synthetic_state_dict(CHANNEL, M, K, seed=0)
     x = uniform((sample_images, 3, H, W), "bench.image", 0)
@@ -127,12 +158,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 4
+    sample = CPU_SAMPLE
     times = []
     import torch
     from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
     from oracle import mcquic_oracle as oracle
-    cores = os.cpu_count() or 1
+    cores = _physical_cores()
     torch.set_num_threads(cores)
     sd = synthetic_state_dict(CHANNEL, M, K, seed=0)
     x = uniform((sample, 3, H, W), "bench.image", 0)
@@ -143,7 +174,8 @@ def run_reference(args):
             times.append(time.perf_counter() - t0)
     total = sum(times)
     value = sample * H * W * len(times) / total / 1e6
-    desc = f"{sample} of the 64 images of a step (CPU time scales linearly in batch, SURVEY.md section 8d)"
+    desc = (f"{sample} of the 64 images of a step per CPU step (CPU time scales linearly in batch, SURVEY.md section 8d), "
+            f"{cores} threads = physical cores of {os.cpu_count()} logical CPUs")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
@@ -173,6 +205,44 @@ def _by_class(rows, peak):
         c["executed_tflops"] = c.pop("executed_tflop") / (c["ms"] * 1e-3) if c["ms"] > 0 else 0.0
         c["frac_of_peak"] = c["executed_tflops"] / peak
     return classes
+
+
+def _eager_gpu_baseline(dev, x_dev):
+    """The reference's own GPU path on THIS GPU in THIS run: its algorithm executed op by op through ATen / cuDNN / cuBLAS
+    (the functional restatement oracle/mcquic_oracle.py on CUDA tensors -- the reference package cannot be imported on the
+    GPU box; the restatement is bit-identical to it on CPU).  Two settings: PyTorch's default (TF32 convolutions; its code
+    indices differ from the fp32 reference's) and true fp32 (`allow_tf32 = False`: the only setting whose codes are
+    comparable, and the one this framework matches bit for bit).  A reported baseline, like cpu_baseline: nothing of the
+    product runs through it."""
+    import torch
+    from mcquic_b200.utils.synthetic import synthetic_state_dict
+    from oracle import mcquic_oracle as oracle
+    sd = {k: v.to(dev) for k, v in synthetic_state_dict(CHANNEL, M, K, seed=0).items()}
+    out = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        with torch.no_grad():
+            for name, tf32 in (("tf32_default", True), ("fp32", False)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                torch.backends.cudnn.benchmark = True
+                for _ in range(2):
+                    oracle.decode(sd, oracle.encode(sd, x_dev))
+                torch.cuda.synchronize()
+                reps = 3
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    oracle.decode(sd, oracle.encode(sd, x_dev))
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                out[name] = {"ms_per_step": ms, "value": x_dev.shape[0] * H * W / ms / 1e3, "unit": "MPix/s"}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    del sd
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -261,10 +331,30 @@ def run_ours(args):
         launches = _lib.launch_count() + model.graph_launches - launches_before
         ms_e2e = timed(step_e2e, args.steps)
         barrier()
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    # ---- strong-scaling leg (BASELINE configs[3]): 512 images in total, 512 / N per rank, same step (encode, the one
+    # histogram all-gather, decode); device-resident inputs, L2 flushed, max over ranks.  At N = 1 this is a batch-512 step.
+    strong_ms, strong_steps = None, 3
+    per_rank = STRONG_TOTAL // world
+    if STRONG_TOTAL % world == 0 and not args.no_strong:
+        xs = uniform((per_rank, 3, H, W), f"strong.image.{rank}", 0).to(dev)
+
+        def step_strong():
+            hist = torch.zeros(hist_total, dtype=torch.int32, device=dev)
+            codes = model.encode(xs, hist=hist)
+            if world > 1:
+                gather_histograms(hist)
+            return model.decode(codes)
+
+        for _ in range(2):
+            step_strong()
+        barrier()
+        strong_ms = timed(step_strong, strong_steps)
+        barrier()
+        del xs
+    t = torch.tensor([ms, ms_e2e, strong_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, strong_ms = float(t[0]), float(t[1]), float(t[2])
     pix = world * BATCH * H * W * args.steps
     value = pix / (ms * 1e-3) / 1e6
     e2e_value = pix / (ms_e2e * 1e-3) / 1e6
@@ -297,36 +387,69 @@ def run_ours(args):
                             "us": 1e3 * p["ev"][0].elapsed_time(p["ev"][1])} for p in prof] +
                           [{"other": p["other"], "us": 1e3 * p["ev"][0].elapsed_time(p["ev"][1])} for p in others], fp)
         tc = [p for p in prof if p["impl"] == _lib.IMPL_TCGEN05]
-        t_tc = sum(p["ev"][0].elapsed_time(p["ev"][1]) for p in tc) * 1e-3
-        f_tc = sum(p["flops"] for p in tc)
-        f_exec = sum(p["flops"] * p["passes"] for p in tc)
-        achieved = f_tc / t_tc / 1e12
+        rows = [{"shape": p["shape"], "passes": p["passes"], "flops": p["flops"],
+                 "us": 1e3 * p["ev"][0].elapsed_time(p["ev"][1])} for p in tc]
+        t_tc = sum(r["us"] for r in rows) * 1e-6
+        f_tc = sum(r["flops"] for r in rows)
+        f_exec = sum(r["flops"] * r["passes"] for r in rows)
         peak = peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None,
-                    "kernel": "tcgen05 convolutions: conv_pair_kernel / conv_halo_kernel / conv_tc_kernel, all %d launches "
-                              "of one step" % len(tc),
-                    "executed_tflops": f_exec / t_tc / 1e12, "executed_frac": f_exec / t_tc / 1e12 / peak,
-                    "by_layer_class": _by_class([{"shape": p["shape"], "passes": p["passes"], "flops": p["flops"],
-                                                  "us": 1e3 * p["ev"][0].elapsed_time(p["ev"][1])} for p in tc], peak),
-                    "conv_ms_per_step": t_tc * 1e3, "conv_share_of_step": t_tc / t_all,
-                    "share_basis": "device time of ALL %d launches of one single-stream eager step, each bracketed by CUDA "
-                                   "events (%.2f ms in total, serialised like the ncu launch list "
-                                   "profiles/r1d_launch_summary.txt, which gives the same share; wall time of that eager step "
-                                   "%.2f ms, graph-replayed two-stream timed step %.2f ms)"
-                                   % (len(prof) + len(others), t_all * 1e3, eager_ms, ms / args.steps),
-                    "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained (fp16 dense = bf16 dense)",
-                    "note": "achieved counts algorithmic (fp32-semantics) FLOPs; the 3-pass split-fp16 encode executes 3x of them"}
+        # the dominant kernel: conv_pair_kernel<3> = the 3-pass (fp32-grade) 3x3 stride-1 convolutions of the encoder on
+        # >= 32x32 maps (CTA-pair tcgen05 kernel).  Algorithmic FLOPs per launch = 2 * n*h*w * cout * 9*cin (SURVEY 8d's
+        # hook-counted figure restricted to these layers); duration = CUDA events around each launch on its stream.
+        dom = [r for r in rows if r["passes"] == 3 and r["shape"][5] == 3 and r["shape"][6] == 1
+               and r["shape"][1] * r["shape"][2] >= 1024]
+        t_dom = sum(r["us"] for r in dom) * 1e-6
+        f_dom = sum(r["flops"] for r in dom)
+        traffic, traffic_src = None, None
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             with open(traffic_file) as fp:
-                roofline["traffic"] = json.load(fp).get("dram_bytes_per_step")
+                tj = json.load(fp)
+            if "dominant_kernel_dram_bytes_per_launch" in tj:
+                traffic = tj["dominant_kernel_dram_bytes_per_launch"]
+                traffic_src = "static: " + tj.get("dominant_kernel_source", "profiles/traffic.json") + \
+                              " (an ncu --set full capture of the same kernel and shape, NOT measured by this run)"
+        achieved = f_dom / t_dom / 1e12 if t_dom > 0 else 0.0
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "kernel": "conv_pair_kernel<3>: 3-pass split-fp16 3x3 stride-1 convolutions on >= 32x32 maps, "
+                              "%d launches per step" % len(dom),
+                    "launches": len(dom), "avg_launch_us": 1e6 * t_dom / max(1, len(dom)),
+                    "alg_gflop_per_launch": f_dom / max(1, len(dom)) / 1e9,
+                    "executed_tflops": 3 * achieved, "executed_frac": 3 * achieved / peak,
+                    "kernel_ms_per_step": t_dom * 1e3, "kernel_share_of_step": t_dom / t_all,
+                    "timing": "CUDA events around every launch of one single-stream eager step run right after the timed "
+                              "region (inside the graph-replayed two-stream timed step individual launches cannot be "
+                              "bracketed); shares are over the device time of ALL %d launches of that eager step (%.2f ms; "
+                              "its wall time %.2f ms; the timed step %.2f ms)"
+                              % (len(prof) + len(others), t_all * 1e3, eager_ms, ms / args.steps),
+                    "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained (fp16 dense = bf16 dense; the "
+                                   "kernel is timed inside a long step)",
+                    "note": "achieved counts algorithmic (fp32-semantics) FLOPs; the 3-pass split-fp16 kernel executes 3x of "
+                            "them on the tensor pipe, so frac is capped at 1/3 and executed_frac is the tensor-pipe figure",
+                    "all_tcgen05_convs": {"launches": len(rows), "alg_tflops": f_tc / t_tc / 1e12,
+                                          "alg_frac": f_tc / t_tc / 1e12 / peak, "executed_tflops": f_exec / t_tc / 1e12,
+                                          "executed_frac": f_exec / t_tc / 1e12 / peak, "ms_per_eager_step": t_tc * 1e3,
+                                          "share_of_eager_step": t_tc / t_all},
+                    "whole_step": {"alg_tflops": BATCH * ALG_GFLOP_PER_IMAGE / 1e3 / (ms / args.steps * 1e-3),
+                                   "alg_frac": BATCH * ALG_GFLOP_PER_IMAGE / 1e3 / (ms / args.steps * 1e-3) / peak,
+                                   "basis": "5.724 algorithmic TFLOP per 64-image step / the timed ms_per_step"},
+                    "by_layer_class": _by_class(rows, peak)}
         cpu = None
+        gpu_base = None
         if world == 1:
-            cpu_val, cpu_s, cores = _cpu_oracle_throughput(sample_images=16, repeats=5)
+            if not args.no_gpu_baseline:
+                gpu_base = _eager_gpu_baseline(dev, x_dev)
+                for leg in gpu_base.values():
+                    leg["ours_over_it"] = value / leg["value"]
+                gpu_base["what"] = ("the reference algorithm as eager PyTorch (ATen / cuDNN / cuBLAS) on this GPU in this "
+                                    "run, batch 64x3x256x256, encode+decode, device-resident input: PyTorch's default "
+                                    "(TF32 convolutions) and true fp32 (the setting whose code indices are comparable)")
+            cpu_val, cpu_s, cores = _cpu_oracle_throughput(sample_images=CPU_SAMPLE, repeats=5)
             cpu = {"value": cpu_val, "unit": "MPix/s", "cores": cores, "kind": "port",
-                   "sample": f"16 of the 64 images of a step, encode+decode, best of 5 ({cpu_s:.2f} s each), "
-                             "oracle/mcquic_oracle.py (CPU PyTorch fp32, all host threads)"}
+                   "sample": f"{CPU_SAMPLE} of the 64 images of a step, encode+decode, best of 5 ({cpu_s:.2f} s each), "
+                             f"oracle/mcquic_oracle.py (CPU PyTorch fp32), {cores} threads = physical cores "
+                             f"({os.cpu_count()} logical CPUs)"}
         out = {
             "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -342,6 +465,14 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "gpu_baseline": gpu_base,
+            "strong_scaling": None if not strong_ms else {
+                "total_images": STRONG_TOTAL, "images_per_gpu": STRONG_TOTAL // world, "n_gpus": world,
+                "ms_per_step": strong_ms / strong_steps, "value": STRONG_TOTAL * H * W / (strong_ms / strong_steps) / 1e3,
+                "unit": "MPix/s", "steps": strong_steps,
+                "what": "BASELINE configs[3]: qp=1, 512 images in total sharded over the ranks (512 / N each), encode + "
+                        "histogram all-gather + decode, device-resident inputs, L2 flushed, max over ranks; the 1 -> 8 curve "
+                        "is this value across the driver's N = 1, 2, 4, 8 runs"},
             "alg_tflops": pix * ALG_GFLOP_PER_IMAGE / (H * W) * 1e9 / (ms * 1e-3) / 1e12,
         }
     if world > 1:
@@ -360,6 +491,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dump-profile", default=None, help="write the per-conv-launch timing list of the roofline leg here")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 512-image strong-scaling leg")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch-on-this-GPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

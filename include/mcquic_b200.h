@@ -208,6 +208,11 @@ int mcq_nhwc_to_nchw(const float* x, int32_t n, int32_t c, int32_t h, int32_t w,
 /* Introspection */
 const char* mcq_error_string(int code);
 int mcq_version(void);            /* ABI version */
+/* Tuning / A-B knobs (kernel selection, grid caps, profiling aids -- the table at the top of csrc/mcq_api.cu).  They are
+ * explicit process-wide settings with fixed defaults: nothing on the launch path reads the environment.
+ * mcq_set_option returns MCQ_ERR_BAD_ARG for an unknown name; mcq_get_option returns INT32_MIN for one. */
+int mcq_set_option(const char* name, int32_t value);
+int32_t mcq_get_option(const char* name);
 int mcq_device_error_flag(void);  /* last device-side watchdog code (0 = none); resets on read */
 int mcq_kernel_launch_count(void); /* number of kernels this library has launched in this process */
 

@@ -61,6 +61,8 @@ SYMBOLS = {
     "mcq_nhwc_to_nchw": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "mcq_error_string": (_c.c_char_p, [_c.c_int]),
     "mcq_version": (_c.c_int, []),
+    "mcq_set_option": (_c.c_int, [_c.c_char_p, _i32]),
+    "mcq_get_option": (_i32, [_c.c_char_p]),
     "mcq_device_error_flag": (_c.c_int, []),
     "mcq_kernel_launch_count": (_c.c_int, []),
 }
@@ -97,6 +99,22 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().mcq_error_string(rc).decode()
         raise RuntimeError(f"{what}: {msg} (code {rc})")
+
+
+def set_option(name: str, value: int):
+    """explicit tuning / A-B knob of the library (include/mcquic_b200.h: mcq_set_option)"""
+    check(load().mcq_set_option(name.encode(), int(value)), f"mcq_set_option({name})")
+
+
+def apply_options(spec: str):
+    """"name=value,name=value" -> set_option for each (measurement scripts under tools/ take such a string)"""
+    for item in filter(None, (t.strip() for t in (spec or "").split(","))):
+        name, _, value = item.partition("=")
+        set_option(name.strip(), int(value))
+
+
+def get_option(name: str) -> int:
+    return int(load().mcq_get_option(name.encode()))
 
 
 def launch_count() -> int:

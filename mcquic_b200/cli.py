@@ -158,6 +158,55 @@ def run(debug: bool, quiet: bool, qp: int, local: Optional[pathlib.Path], disabl
     raise ValueError("Invalid input file.")
 
 
+PUBLISHED_MPPS = {2: (25.45, 22.03), 12: (11.07, 10.21)}      # reference README.md:304-308, one RTX 3090
+
+
+def speed(model: Compressor, device, reps: int = 50, batch: int = 10, height: int = 768, width: int = 512):
+    """`Validator.speed` of the reference (mcquic/validate/validator.py:60-97), step for step: `torch.rand(10, 3, 768,
+    512)` on the device, one warm-up `compress` + `decompress`, then 50 x `model.compress(tensor)` and 50 x
+    `model.decompress(binaries, headers)` between CUDA events; Mpps = 50 * 10 * 768 * 512 / 1000 / ms.  Like upstream the
+    figure INCLUDES the host rANS coder and the device-to-host reads of the codes, and excludes file I/O and model loading
+    (README.md:308).  Returns ((encoder Mpps, decoder Mpps), summary string)."""
+    with torch.inference_mode():
+        tensor = torch.rand(batch, 3, height, width).to(device)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        codes, binaries, headers = model.compress(tensor)          # warm up
+        restored = model.decompress(binaries, headers)
+        start.record()
+        for _ in range(reps):
+            codes, binaries, headers = model.compress(tensor)
+        end.record()
+        torch.cuda.synchronize()
+        encoder_ms = start.elapsed_time(end)
+        start.record()
+        for _ in range(reps):
+            restored = model.decompress(binaries, headers)
+        end.record()
+        torch.cuda.synchronize()
+        decoder_ms = start.elapsed_time(end)
+    del restored, codes
+    mp = reps * batch * height * width / 1000
+    result = (mp / encoder_ms, mp / decoder_ms)
+    return result, f"Coding throughput: encoder: {result[0]:.2f} Mpps, decoder: {result[1]:.2f} Mpps"
+
+
+def run_speed(qp: int, local: Optional[pathlib.Path], mse: bool, synthetic: bool, quiet: bool = False):
+    """`python -m mcquic_b200 --speed [-qp N] [--local ckpt | --synthetic]`"""
+    logging.basicConfig(level=logging.CRITICAL if quiet else logging.INFO, format="%(message)s")
+    logger = logging.getLogger("mcquic_b200")
+    if not torch.cuda.is_available():
+        raise RuntimeError("mcquic_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    device = torch.device("cuda")
+    model = load_model(qp, local, device, mse, logger, synthetic)
+    result, summary = speed(model, device)
+    print(summary)
+    if local is None and qp in PUBLISHED_MPPS:
+        e, d = PUBLISHED_MPPS[qp]
+        print(f"Published for qp={qp} (reference README, 1x RTX 3090, trained weights): encoder {e:.2f} Mpps, decoder "
+              f"{d:.2f} Mpps -> x{result[0] / e:.1f} / x{result[1] / d:.1f}")
+    return result
+
+
 def build_parser() -> argparse.ArgumentParser:
     ap = argparse.ArgumentParser(prog="mcquic_b200", description="Compress/restore a file (B200 path of `mcquic`).")
     ap.add_argument("-v", "--version", action="version", version=f"mcquic_b200 (container of mcquic {REFERENCE_VERSION})")
@@ -170,13 +219,22 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--mse", action="store_true", help="Use model optimized for PSNR other than MsSSIM.")
     ap.add_argument("--crop", action="store_true", help="Crop the image to align feature patches.")
     ap.add_argument("--synthetic", action="store_true", help="Seeded random weights instead of a pretrained checkpoint (no network here).")
-    ap.add_argument("input", type=pathlib.Path, help="Image to compress, or `.mcq` file to restore.")
+    ap.add_argument("--speed", action="store_true",
+                    help="Run the reference's throughput protocol (Validator.speed: 10x3x768x512, 50x compress then 50x "
+                         "decompress incl. rANS) instead of coding a file.")
+    ap.add_argument("input", type=pathlib.Path, nargs="?", help="Image to compress, or `.mcq` file to restore.")
     ap.add_argument("output", type=pathlib.Path, nargs="?", help="Output file path or dir; omitted: only print the file information.")
     return ap
 
 
 def main(argv=None) -> int:
     args = build_parser().parse_args(argv)
+    if args.speed:
+        run_speed(args.qp, args.local, args.mse, args.synthetic, args.quiet)
+        return 0
+    if args.input is None:
+        print("Error: Missing argument 'INPUT'.", file=sys.stderr)
+        return 2
     if not args.input.is_file():
         print(f"Error: Invalid value for 'INPUT': File '{args.input}' does not exist.", file=sys.stderr)
         return 2

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -61,9 +62,32 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int env_int(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
+// Tuning / debugging knobs.  They are plain process-wide values with fixed defaults, changed ONLY through the explicit
+// mcq_set_option() call (tools/ and tests use it for A/B measurements); nothing on the launch path reads the environment.
+struct Option { const char* name; int value; };
+Option g_options[] = {
+    {"direct_epi", 1},        // transpose-free drain: 1 = every NHWC / PixelShuffle store, 2 = plane-only outputs, 0 = never
+    {"wait_sleep_ns", 0},     // nanosleep between mbarrier polls of the producer / drain warps
+    {"tc_spread", 33},        // conv_tc: narrow the N tile until this % of the SMs have a tile
+    {"pdl", 1},               // programmatic dependent launch
+    {"epi_skip", 0},          // profiling aid: drain TMEM but store nothing
+    {"pair", -1},             // CTA-pair kernel: -1 = auto (3-pass and weight-resident 1-pass layers), 0 / 1 = force
+    {"pair_resident", 1},     // weight-stationary 1-pass mode of the pair kernel
+    {"halo", 1},              // single-CTA halo kernel for 3x3 stride-1 layers the pair kernel does not take
+    {"halo_pitch", 10}, {"halo_base", 0}, {"halo_cl", 2}, {"halo_tps", 0}, {"halo_nbs", 0},
+    {"small_grid_pct", 100},  // grid cap (% of the SMs) of launches with fewer work items than clusters
+    {"chain", 1}, {"chain_ipc", 0}, {"chain_nosync", 0}, {"chain_sync_mode", 0},
+    {"gn_threads", 256}, {"gn_ctas_per_sm", 4}, {"gn_apply_iters", 8}, {"gn_fused", 1},
+    {"vq128_fused", 1},       // one-launch tcgen05 VQ for d = 128 (qp = 1); 0 = prep + GEMM-epilogue argmin + finalize
+};
+int* find_option(const char* name) {
+  for (auto& o : g_options)
+    if (std::strcmp(o.name, name) == 0) return &o.value;
+  return nullptr;
+}
+int opt(const char* name) {
+  const int* v = find_option(name);
+  return v ? *v : 0;
 }
 
 int pow2_ceil(int v) {
@@ -79,16 +103,35 @@ struct TcPlan {
   int grid;
 };
 
-int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
 }
+int num_sms() {   // per device ordinal (a process may drive several GPUs)
+  static std::atomic<int> sms[kMaxDevices];
+  const int dev = current_device();
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    sms[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: opt in once per (kernel, device),
+// raising it when a later launch needs more.  One slot per kernel template instantiation (the `Tag` type).
+template <class Tag, class K>
+cudaError_t ensure_dyn_smem(K kernel, size_t bytes) {
+  static std::atomic<size_t> have[kMaxDevices];
+  const int dev = current_device();
+  if (have[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) have[dev].store(bytes, std::memory_order_release);
+  return e;
+}
+template <int> struct KTag {};
 
 // Encode the 5-D view of an NHWC fp16 plane that makes every filter tap a unit-stride TMA box.
 //   stride 1: dims {C,  W,   1, H,   N}
@@ -171,7 +214,7 @@ int fill_args(const mcq_conv_params* p, ConvArgs& a) {
   a.ktotal = p->ksize * p->ksize * p->cin;
   a.cin_total = p->cin; a.ch_off = 0;
   a.mode = p->mode; a.store = p->store; a.o0_act = p->out0_act; a.o1_act = p->out1_act; a.passes = p->passes;
-  static const int direct = env_int("MCQ_DIRECT_EPI", 1);
+  const int direct = opt("direct_epi");
   a.direct_epilogue = direct;
   a.gn_ws = nullptr;
   if (p->gn_partials) {
@@ -181,7 +224,7 @@ int fill_args(const mcq_conv_params* p, ConvArgs& a) {
     a.gn_ws = (float2*)p->gn_partials;
     a.gn_unit = unit; a.gn_units = p->cout / unit; a.gn_rb = rb;
   }
-  static const int wait_sleep = env_int("MCQ_WAIT_SLEEP_NS", 0);
+  const int wait_sleep = opt("wait_sleep_ns");
   a.wait_sleep_ns = wait_sleep;
   return 0;
 }
@@ -247,7 +290,7 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   // small feature maps: narrow the N tile so that the few pixel tiles still spread over the SMs
   // (these layers are latency-bound; re-reading A per N tile is free compared with idle SMs)
   const int tiles_m = a.tiles_x * a.tiles_y * a.tiles_n;
-  static const int spread_pct = env_int("MCQ_TC_SPREAD", 33);
+  const int spread_pct = opt("tc_spread");
   while (tiles_m * (a.cout_pad / bn) < num_sms() * spread_pct / 100 && bn >= 32 && (bn / 2) % 16 == 0) bn /= 2;
   a.bn = bn;
   a.tiles_c = a.cout_pad / bn;
@@ -261,7 +304,7 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   if (stages < 2) return MCQ_ERR_UNSUPPORTED;
   a.stages = stages;
   const size_t smem = stage_bytes * stages + 8 * (2 * stages + 4) + 16 + 1024 + epi_bytes;
-  a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
+  a.debug_skip_store = opt("epi_skip");
 
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   int rc = encode_act_map(&tmA_hi, a.a_hi, a.n, a.hin, a.win, a.cin_total, a.stride, a.tw, a.th, a.tn);
@@ -289,23 +332,15 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = env_int("MCQ_PDL", 1) ? 1 : 0;
+  cfg.numAttrs = opt("pdl") ? 1 : 0;
   EvScope ev(st);
   if (a.passes == 3) {
-    static bool attr3 = false;
-    if (!attr3) {
-      e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return (int)e;
-      attr3 = true;
-    }
+    e = ensure_dyn_smem<KTag<103>>(conv_tc_kernel<3>, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
     e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
   } else {
-    static bool attr1 = false;
-    if (!attr1) {
-      e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return (int)e;
-      attr1 = true;
-    }
+    e = ensure_dyn_smem<KTag<101>>(conv_tc_kernel<1>, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
     e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
   }
   g_launches++;
@@ -321,12 +356,10 @@ bool halo_supported(const ConvArgs& a) {
 
 template <int PASSES, int CL>
 int launch_halo_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t smem, int grid, cudaStream_t st) {
-  static bool attr = false;
   auto kern = conv_halo_kernel<PASSES, CL>;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    cudaError_t e = ensure_dyn_smem<KTag<200 + PASSES * 10 + CL>>(kern, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -341,7 +374,7 @@ int launch_halo_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t sme
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = env_int("MCQ_PDL", 1) ? 2 : 1;
+  cfg.numAttrs = opt("pdl") ? 2 : 1;
   EvScope ev(st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], a, hp);
   g_launches++;
@@ -361,29 +394,29 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
   a.tiles_y = (a.hout + HALO_TH - 1) / HALO_TH;
   a.tiles_n = a.n;
   HaloArgs hp{};
-  hp.pitch = env_int("MCQ_HALO_PITCH", 10);
+  hp.pitch = opt("halo_pitch");
   hp.box_w = hp.pitch;
-  hp.base_mode = env_int("MCQ_HALO_BASE", 0);
+  hp.base_mode = opt("halo_base");
   hp.a_bytes = ((hp.pitch * HALO_ROWS * 128) + 1023) / 1024 * 1024;
   hp.tiles_m = a.tiles_x * a.tiles_y * a.tiles_n;
-  int cl = env_int("MCQ_HALO_CL", 2);
+  int cl = opt("halo_cl");
   if (cl != 1 && cl != 2 && cl != 4) return MCQ_ERR_BAD_ARG;
   while (cl > 1 && ((bn / cl) % 8 != 0 || hp.tiles_m < cl)) cl /= 2;
   hp.groups_m = (hp.tiles_m + cl - 1) / cl;
   // smem budget: A buffers (double/triple) + as many weight stages as fit
   const size_t a_buf = (size_t)hp.a_bytes * np;
-  hp.tps = env_int("MCQ_HALO_TPS", a.passes == 3 ? 1 : 3);
+  hp.tps = opt("halo_tps") ? opt("halo_tps") : (a.passes == 3 ? 1 : 3);
   if (hp.tps != 1 && hp.tps != 3) return MCQ_ERR_BAD_ARG;
   const size_t b_stage = (size_t)bn * TC_BK * 2 * np * hp.tps;
   const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + TC_BIAS_SMEM_FLOATS * 4;
   const size_t budget = 227 * 1024 - 1024 - 256 - epi_bytes;
-  a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
+  a.debug_skip_store = opt("epi_skip");
   hp.na = (a.passes == 3) ? 2 : 3;
   int nbs = (int)((budget - a_buf * hp.na) / b_stage);
   if (nbs < 3 && hp.na > 2) { hp.na = 2; nbs = (int)((budget - a_buf * hp.na) / b_stage); }
   if (nbs < 2 && hp.tps > 1) return MCQ_ERR_UNSUPPORTED;
   if (nbs > 8) nbs = 8;
-  if (env_int("MCQ_HALO_NBS", 0) > 0 && env_int("MCQ_HALO_NBS", 0) < nbs) nbs = env_int("MCQ_HALO_NBS", 0);
+  if (opt("halo_nbs") > 0 && opt("halo_nbs") < nbs) nbs = opt("halo_nbs");
   if (nbs < 2) return MCQ_ERR_UNSUPPORTED;
   hp.nbs = nbs;
   const size_t smem = a_buf * hp.na + b_stage * nbs + 8 * (2 * hp.na + 2 * nbs + 4) + 16 + 1024 + epi_bytes;
@@ -417,7 +450,7 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
   const int work = hp.groups_m * a.tiles_c;
   int clusters = num_sms() / cl;
   if (work < clusters) {
-    static const int small_pct = env_int("MCQ_SMALL_GRID_PCT", 100);
+    const int small_pct = opt("small_grid_pct");
     clusters = work < clusters * small_pct / 100 ? work : clusters * small_pct / 100;
   }
   const int grid = clusters * cl;
@@ -435,12 +468,10 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
 // ---- CTA-pair kernel (tcgen05.mma.cta_group::2): 3x3 stride-1 convs with a 128-column N tile
 template <int PASSES, bool GN = false>
 int launch_pair_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t smem, int grid, cudaStream_t st) {
-  static bool attr = false;
   auto kern = conv_pair_kernel<PASSES, GN>;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    cudaError_t e = ensure_dyn_smem<KTag<300 + PASSES * 10 + (GN ? 1 : 0)>>(kern, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -455,7 +486,7 @@ int launch_pair_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t sme
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = env_int("MCQ_PDL", 1) ? 2 : 1;
+  cfg.numAttrs = opt("pdl") ? 2 : 1;
   EvScope ev(st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], a, hp);
   g_launches++;
@@ -480,21 +511,21 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
   hp.tiles_m = a.tiles_x * a.tiles_y * a.tiles_n;
   if (hp.tiles_m < 2) return MCQ_ERR_UNSUPPORTED;
   hp.groups_m = (hp.tiles_m + 1) / 2;
-  hp.tps = env_int("MCQ_HALO_TPS", a.passes == 3 ? 1 : 3);
+  hp.tps = opt("halo_tps") ? opt("halo_tps") : (a.passes == 3 ? 1 : 3);
   if (hp.tps != 1 && hp.tps != 3) return MCQ_ERR_BAD_ARG;
   const size_t a_buf = (size_t)hp.a_bytes * np;
   const size_t b_plane = (size_t)bn * TC_BK * 2;
   const size_t b_stage = (a.passes == 3 ? b_plane + b_plane / 2 : b_plane / 2) * hp.tps;
   const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + TC_BIAS_SMEM_FLOATS * 4;
   const size_t budget = 227 * 1024 - 1024 - 256 - epi_bytes;
-  a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
+  a.debug_skip_store = opt("epi_skip");
   hp.na = (a.passes == 3) ? 2 : 3;
   int nbs = (int)((budget - a_buf * hp.na) / b_stage);
   if (nbs > 8) nbs = 8;
   // weight-stationary mode: 1-pass, one N tile, and all (cin / 64) * (9 / tps) weight stages fit beside two halo buffers
   const int all_stages = ((a.cin + TC_BK - 1) / TC_BK) * (9 / hp.tps);
   if (a.passes == 1 && a.tiles_c <= num_sms() / 2 && all_stages <= 8 && a_buf * 2 + b_stage * all_stages <= budget &&
-      env_int("MCQ_PAIR_RESIDENT", 1)) {
+      opt("pair_resident")) {
     hp.resident = 1;
     hp.na = 2;
     nbs = all_stages;
@@ -536,7 +567,7 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
   int clusters = num_sms() / 2;
   if (work < clusters) {
     // small layer (<= one work item per cluster): experiment knob -- leave SMs to the sibling branch's launch
-    static const int small_pct = env_int("MCQ_SMALL_GRID_PCT", 100);
+    const int small_pct = opt("small_grid_pct");
     clusters = work < clusters * small_pct / 100 ? work : clusters * small_pct / 100;
   }
   if (hp.resident && a.tiles_c > 1) {
@@ -558,12 +589,10 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
 // ---- layer chain (conv_chain.cuh): `count` dependent convolutions on small maps in one persistent launch
 template <int PASSES>
 int launch_chain_t(const ChainParams& cp, size_t smem, int grid, cudaStream_t st) {
-  static bool attr = false;
   auto kern = conv_chain_kernel<PASSES>;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    cudaError_t e = ensure_dyn_smem<KTag<400 + PASSES>>(kern, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -578,7 +607,7 @@ int launch_chain_t(const ChainParams& cp, size_t smem, int grid, cudaStream_t st
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = env_int("MCQ_PDL", 1) ? 2 : 1;
+  cfg.numAttrs = opt("pdl") ? 2 : 1;
   EvScope ev(st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, cp);
   g_launches++;
@@ -592,7 +621,7 @@ int launch_chain(const mcq_conv_params* params, int count, cudaStream_t st) {
   const int passes = params[0].passes;
   const int n = params[0].n;
   const int bn_max = passes == 3 ? 64 : 128;
-  int ipc = env_int("MCQ_CHAIN_IPC", 0);
+  int ipc = opt("chain_ipc");
   if (ipc <= 0) ipc = (n + 15) / 16;    // <= 16 clusters = 128 CTAs
   const int nclusters = (n + ipc - 1) / ipc;
   int bias_total = 0;
@@ -615,7 +644,7 @@ int launch_chain(const mcq_conv_params* params, int count, cudaStream_t st) {
     while (tiles_m * (a.cout_pad / bn) < CHAIN_CL && bn >= 32 && (bn / 2) % 16 == 0) bn /= 2;
     a.bn = bn;
     a.tiles_c = a.cout_pad / bn;
-    a.debug_skip_store = env_int("MCQ_EPI_SKIP", 0);
+    a.debug_skip_store = opt("epi_skip");
     // dependency on anything written since the last barrier?
     const void* ins[5] = {p->a_hi, p->a_lo, p->res1, p->res2, p->aux};
     int dep = 0;
@@ -653,7 +682,7 @@ int launch_chain(const mcq_conv_params* params, int count, cudaStream_t st) {
   cp.ipc = ipc;
   cp.stages = stages;
   cp.bias_total = bias_total;
-  cp.debug = (env_int("MCQ_CHAIN_NOSYNC", 0) ? 1 : 0) | (env_int("MCQ_CHAIN_SYNC_MODE", 0) << 1);
+  cp.debug = (opt("chain_nosync") ? 1 : 0) | (opt("chain_sync_mode") << 1);
   cp.dbg = g_chain_dbg;
   const size_t smem = stage_bytes * stages + 8 * (2 * stages + 4) + 16 + 1024 + epi_bytes;
   const int grid = nclusters * CHAIN_CL;
@@ -679,11 +708,11 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
     // CTA pairs (cta_group::2) pay off where the tensor pipe is the limiter (3-pass); the 1-pass path is epilogue-bound
     // (streaming weights); with a single 128-column N tile the weights stay resident in the pair's shared memory instead
     const bool pair_resident = a.passes == 1 && a.cout_pad % 128 == 0 && a.cout_pad <= 512 && a.cin == 128 &&
-                               env_int("MCQ_PAIR_RESIDENT", 1);
+                               opt("pair_resident");
     if (a.gn_ws) rc = halo_supported(a) ? launch_pair(a, st) : MCQ_ERR_UNSUPPORTED;   // only the pair kernel has it
     else
-    if (halo_supported(a) && env_int("MCQ_PAIR", (a.passes == 3 || pair_resident) ? 1 : 0)) rc = launch_pair(a, st);
-    if (rc == MCQ_ERR_UNSUPPORTED && !a.gn_ws && halo_supported(a) && env_int("MCQ_HALO", 1)) rc = launch_halo(a, st);
+    if (halo_supported(a) && (opt("pair") >= 0 ? opt("pair") : ((a.passes == 3 || pair_resident) ? 1 : 0))) rc = launch_pair(a, st);
+    if (rc == MCQ_ERR_UNSUPPORTED && !a.gn_ws && halo_supported(a) && opt("halo")) rc = launch_halo(a, st);
     if (rc == MCQ_ERR_UNSUPPORTED && !a.gn_ws) rc = launch_tc(a, st);
   }
   g_ev_start = g_ev_stop = nullptr;
@@ -695,7 +724,7 @@ int mcq_conv_chain(const mcq_conv_params* params, int32_t count, mcq_stream_t st
   cudaStream_t st = (cudaStream_t)stream;
   g_ev_start = (cudaEvent_t)params[0].ev_start;
   g_ev_stop = (cudaEvent_t)params[count - 1].ev_stop;
-  int rc = env_int("MCQ_CHAIN", 1) ? launch_chain(params, count, st) : MCQ_ERR_UNSUPPORTED;
+  int rc = opt("chain") ? launch_chain(params, count, st) : MCQ_ERR_UNSUPPORTED;
   g_ev_start = g_ev_stop = nullptr;
   return rc;
 }
@@ -735,11 +764,9 @@ int mcq_vq_assign(const float* x, const float* codebook, const float* c2, int64_
   a.P = n * h * w; a.hw = h * w; a.m = m; a.k = k; a.d = d;
   a.inv_sqrt_k = 1.0f / sqrtf((float)k);
   const size_t smem = ((size_t)d * (VQ_TP + VQ_TK) + VQ_TP) * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(vq_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_dyn_smem<KTag<500>>(vq_assign_kernel, smem);
     if (e != cudaSuccess) return (int)e;
-    smem_set = smem;
   }
   dim3 grid((unsigned)((a.P + VQ_TP - 1) / VQ_TP), (unsigned)m);
   vq_assign_kernel<<<grid, VQ_THREADS, smem, (cudaStream_t)stream>>>(a);
@@ -814,12 +841,10 @@ int mcq_vq_assign_fused(const float* x, const void* cb_lohi, float cb_scale, con
   } else {
     tmL = tmB;
   }
-  static size_t smem_set[2] = {0, 0};
   auto kern = logits ? vq_fused_kernel<true> : vq_fused_kernel<false>;
-  if (smem > smem_set[logits ? 1 : 0]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = logits ? ensure_dyn_smem<KTag<601>>(kern, smem) : ensure_dyn_smem<KTag<600>>(kern, smem);
     if (e != cudaSuccess) return (int)e;
-    smem_set[logits ? 1 : 0] = smem;
   }
   int grid = a.tiles_p * m;
   if (grid > num_sms()) grid = num_sms();
@@ -919,8 +944,8 @@ int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, in
   // a cluster per image in flight; as many CTAs per cluster as leave every CTA >= 32 pixels (tiny maps: a single CTA)
   int slices = GN_MAX_CLUSTER;
   while (slices > 1 && a.hw < slices * 32) slices >>= 1;
-  static const int threads = env_int("MCQ_GN_THREADS", 256);
-  static const int ctas_per_sm = env_int("MCQ_GN_CTAS_PER_SM", 4);
+  const int threads = opt("gn_threads");
+  const int ctas_per_sm = opt("gn_ctas_per_sm");
   // persistent clusters, ctas_per_sm CTAs per SM's worth of them (never more than images)
   long long clusters = ((long long)ctas_per_sm * num_sms()) / slices;
   if (clusters < 1) clusters = 1;
@@ -939,7 +964,7 @@ int mcq_groupnorm(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, in
   cfg.numAttrs = 1;
   cudaError_t e;
   if (threads == 1024) {
-    static const cudaError_t attr = cudaFuncSetAttribute(groupnorm_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, gn_smem_bytes(1024));
+    const cudaError_t attr = ensure_dyn_smem<KTag<700>>(groupnorm_kernel<1024>, (size_t)gn_smem_bytes(1024));
     e = attr != cudaSuccess ? attr : cudaLaunchKernelEx(&cfg, groupnorm_kernel<1024>, a);
   } else if (threads == 512) {
     e = cudaLaunchKernelEx(&cfg, groupnorm_kernel<512>, a);
@@ -959,7 +984,7 @@ int mcq_conv_gn_layout(const mcq_conv_params* p, int32_t* rowblocks_per_image, i
   const int hout = p->hin / (p->stride > 0 ? p->stride : 1), wout = p->win / (p->stride > 0 ? p->stride : 1);
   if (p->impl != MCQ_IMPL_TCGEN05 || p->ksize != 3 || p->stride != 1 || p->store != MCQ_STORE_NHWC ||
       p->mode != MCQ_EPI_LINEAR || p->cin % TC_BK != 0 || p->cout % 128 != 0 || p->cout_pad != p->cout ||
-      wout < HALO_TW || hout < HALO_TH || !p->out_f32 || !env_int("MCQ_DIRECT_EPI", 1) || !env_int("MCQ_GN_FUSED", 1))
+      wout < HALO_TW || hout < HALO_TH || !p->out_f32 || !opt("direct_epi") || !opt("gn_fused"))
     return MCQ_ERR_UNSUPPORTED;
   if ((long long)p->n * ((wout + HALO_TW - 1) / HALO_TW) * ((hout + HALO_TH - 1) / HALO_TH) < 2) return MCQ_ERR_UNSUPPORTED;
   if (cg % 4 != 0 || (cg > 16 && cg % 16 != 0) || (cg < 16 && 16 % cg != 0)) return MCQ_ERR_UNSUPPORTED;
@@ -984,7 +1009,7 @@ int mcq_groupnorm_apply(const float* x, const void* partials, int32_t rowblocks_
   gn_finalize_kernel<<<dim3((unsigned)groups, (unsigned)n), GNF_THREADS, 0, (cudaStream_t)stream>>>(a);
   g_launches++;
   const int rows = GNA_THREADS / (c / 4);
-  static const int iters = env_int("MCQ_GN_APPLY_ITERS", 8);
+  const int iters = opt("gn_apply_iters");
   const int ppb = rows * iters;
   gn_apply_kernel<<<dim3((unsigned)((a.hw + ppb - 1) / ppb), (unsigned)n), GNA_THREADS, 0, (cudaStream_t)stream>>>(a, ppb);
   g_launches++;
@@ -1043,7 +1068,19 @@ const char* mcq_error_string(int code) {
   }
 }
 
-int mcq_version(void) { return 1; }
+int mcq_version(void) { return 2; }
+
+int mcq_set_option(const char* name, int32_t value) {
+  int* v = name ? find_option(name) : nullptr;
+  if (!v) return MCQ_ERR_BAD_ARG;
+  *v = value;
+  return 0;
+}
+
+int32_t mcq_get_option(const char* name) {
+  const int* v = name ? find_option(name) : nullptr;
+  return v ? *v : INT32_MIN;
+}
 
 int mcq_device_error_flag(void) {
   int v = 0;

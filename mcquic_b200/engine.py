@@ -76,9 +76,12 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def split_weight(w2d: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, float]:
-    """fp32 [rows, K] -> (hi, lo) fp16 with  w * 2^e ~= hi + lo / 2048  and the accumulator scale 2^-e."""
-    amax = float(w2d.abs().max())
+def split_weight(w2d: torch.Tensor, amax: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor, float]:
+    """fp32 [rows, K] -> (hi, lo) fp16 with  w * 2^e ~= hi + lo / 2048  and the accumulator scale 2^-e.
+    amax: max |w| when the caller already knows it (Engine.prepare computes it for ALL layers with one device
+    reduction and one host read instead of a device-to-host sync per layer)."""
+    if amax is None:
+        amax = float(w2d.abs().max())
     e = 0 if amax == 0.0 or not math.isfinite(amax) else int(max(-14, min(14, math.floor(math.log2(256.0 / amax)))))
     ws = w2d.double() * (2.0 ** e)
     hi = ws.to(torch.float16)
@@ -94,7 +97,8 @@ def pack_codebook(codebook: torch.Tensor):
     return hi, lo, scale, torch.cat([lo, hi], dim=1).contiguous()
 
 
-def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, store: int, device) -> PackedConv:
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, store: int, device,
+              amax: Optional[float] = None) -> PackedConv:
     """nn.Conv2d weight [cout, cin, k, k] -> K-major GEMM matrix [cout_pad, (r, s, cin)] (split fp16).
     bias=None (conv1x1(..., bias=False) of the Neon quantizer) packs a zero bias.  Channel counts the kernels' vector
     accesses cannot address are zero-padded: cin to a multiple of 8 (RGB input of Neon's first conv: the caller pads
@@ -121,7 +125,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, s
     cout_pad = cout if cout % 128 == 0 or (cout <= 256 and cout % 32 == 0) else ((cout + 15) // 16) * 16
     if cout_pad != cout:
         w = torch.cat([w, torch.zeros(cout_pad - cout, w.shape[1], device=device)], 0)
-    hi, lo, scale = split_weight(w)
+    hi, lo, scale = split_weight(w, amax)        # zero padding and row permutation leave max |w| unchanged
     return PackedConv(hi, lo, b.contiguous(), cin, cout, cout_pad, k, stride, scale, store)
 
 
@@ -148,9 +152,11 @@ class Engine:
         # persistent layer-chain launch (mcq_conv_chain).  Measured on B200 a chained layer costs
         # as much as a stand-alone launch that overlaps a second stream, so the default stays layer-by-layer launches
         # on two streams; the emulated ABI keeps chains on so that the CPU tests cover the recording/merge logic.
-        self.chain = self.emulated or os.environ.get("MCQ_CHAIN", "0") == "1"
+        self.chain = self.emulated
         self._pending: list = []
         self._rec_depth = 0
+        # stride-1 convs with cin % 8 == 0 run on the tensor cores with a partly zero-filled last K chunk (A/B knob)
+        self.partial_chunk = True
 
     # ------------------------------------------------------------------ plumbing
     @contextlib.contextmanager
@@ -287,7 +293,7 @@ class Engine:
                 setattr(out, name, self._planes(n, h, w, c, device))
         return out
 
-    def _packed_for(self, mod: nn.Module, store: int = _lib.STORE_NHWC) -> PackedConv:
+    def _packed_for(self, mod: nn.Module, store: int = _lib.STORE_NHWC, amax: Optional[float] = None) -> PackedConv:
         key = (id(mod), store)
         def version(t):          # tensors created under torch.inference_mode() (the reference CLI runs that way,
             try:                 # mcquic/cli.py:60) have no version counter: they are immutable, so 0 is exact
@@ -306,20 +312,39 @@ class Engine:
             return hit[1]
         if isinstance(mod, GenDivNorm):
             beta, gamma = mod.effective()
-            pc = pack_conv(gamma[:, :, None, None], beta, 1, _lib.STORE_NHWC, gamma.device)
+            pc = pack_conv(gamma[:, :, None, None], beta, 1, _lib.STORE_NHWC, gamma.device, amax)
         else:
-            pc = pack_conv(mod.weight, mod.bias, mod.stride[0], store, mod.weight.device)
+            pc = pack_conv(mod.weight, mod.bias, mod.stride[0], store, mod.weight.device, amax)
         self._packed[key] = (ver, pc)
         return pc
 
     def prepare(self, root: nn.Module):
-        """Repack every convolution under `root` now (otherwise done lazily on first use)."""
+        """Repack every convolution / GDN under `root` now (otherwise done lazily on first use, with one host sync per
+        layer for its max |w|): max |w| of ALL layers comes from one batched device reduction and one host read."""
+        jobs = []        # (module, store)
+        shuffled = set()
         for mod in root.modules():
             if isinstance(mod, ResidualBlockShuffle):
-                self._packed_for(mod._branch[1][0], _lib.STORE_SHUFFLE_NHWC)
-                self._packed_for(mod._skip[0], _lib.STORE_SHUFFLE_NHWC)
-            elif isinstance(mod, GenDivNorm):
-                self._packed_for(mod)
+                shuffled.update((id(mod._branch[1][0]), id(mod._skip[0])))
+        final = None
+        for mod in root.modules():
+            if isinstance(mod, nn.Sequential) and len(mod) == 2 and isinstance(mod[1], nn.PixelShuffle) \
+                    and isinstance(mod[0], nn.Conv2d) and id(mod[0]) not in shuffled:
+                final = id(mod[0])      # stand-alone pixelShuffle3x3 = last decoder layer (NCHW pixel store)
+        for mod in root.modules():
+            if isinstance(mod, GenDivNorm):
+                jobs.append((mod, _lib.STORE_NHWC))
+            elif isinstance(mod, nn.Conv2d) and mod.kernel_size[0] in (1, 3) and mod.in_channels != 3:
+                store = _lib.STORE_SHUFFLE_NHWC if id(mod) in shuffled else (
+                    _lib.STORE_SHUFFLE_NCHW if id(mod) == final else _lib.STORE_NHWC)
+                jobs.append((mod, store))
+        if not jobs:
+            return
+        with torch.no_grad():
+            ws = [(m.effective()[1] if isinstance(m, GenDivNorm) else m.weight).detach().float() for m, _ in jobs]
+            amax = torch.stack(torch._foreach_norm(ws, float("inf"))).tolist()       # the ONE host sync
+        for (mod, store), am in zip(jobs, amax):
+            self._packed_for(mod, store, amax=float(am))
 
     # ------------------------------------------------------------------ one fused conv launch
     def conv(self, pc: PackedConv, a: Planes, x: Act, want: Set[str], *, mode: int = _lib.EPI_LINEAR,
@@ -389,7 +414,7 @@ class Engine:
                 p.out1_hi, p.out1_lo, p.out1_act = _ptr(slots[1][0][0]), _ptr(slots[1][0][1]), slots[1][1]
         p.passes = self.passes if a[1] is not None else 1
         # tensor cores: 64-channel K chunks; stride-1 convs also take cin % 8 == 0 (partly zero-filled last chunk)
-        on_tc = pc.cin % 64 == 0 or (pc.cin % 8 == 0 and pc.stride == 1 and os.environ.get("MCQ_PARTIAL_CHUNK", "1") == "1")
+        on_tc = pc.cin % 64 == 0 or (pc.cin % 8 == 0 and pc.stride == 1 and self.partial_chunk)
         p.impl = self.impl if on_tc else _lib.IMPL_SIMT
         if gn_groups > 0 and out.f32 is not None and pc.cout % gn_groups == 0:
             p.gn_groups = gn_groups

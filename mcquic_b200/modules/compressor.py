@@ -191,6 +191,8 @@ class BaseCompressor(nn.Module):
                 self._graphs.clear()
                 self._pipes.clear()
             self._weights_seen = fp
+            if not self.engine.emulated and self._device().type == "cuda":
+                self.engine.prepare(self)       # all layers repacked with one host sync instead of one per layer
 
     def load_state_dict(self, *args, **kwargs):
         self.invalidate()

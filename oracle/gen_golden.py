@@ -200,8 +200,41 @@ def baseline_configs():
     print("vq_cfg3_full", code.numel(), "codes, min margin", float(margin.min()))
 
 
+CONTAINER_CASES = [
+    # (version, qp, m, heights, widths, k, (height, width, channel), contents)
+    ("0.1.40", "qp_1_msssim", [1, 1, 1], [16, 8, 4], [16, 8, 4], [8192, 2048, 512], (256, 256, 3),
+     [b"\x01\x02", b"\x03", b"\x04\x05\x06"]),
+    ("0.1.40", "qp_2_msssim", [2, 2, 2], [72, 36, 18], [120, 60, 30], [8192, 2048, 512], (1100, 1900, 3),
+     [bytes(range(256)) * 40, bytes(range(200)), b"\xff" * 33]),
+    ("0.1.3", "-1", [6, 6, 6], [32, 16, 8], [32, 16, 8], [2048, 2048, 2048], (512, 512, 3),
+     [b"a" * 70000, b"\x00" * 300, b"\xc4"]),                      # bin8 / bin16 / bin32 length prefixes
+]
+
+
+def container():
+    """tests/golden/container_reference.json: the bytes the reference's OWN `File.serialize` (specification.py:147-149,
+    run unmodified through the functional marshmallow stand-in of oracle/ref_import.py) produces for CONTAINER_CASES."""
+    import json
+    ref_import.load()
+    from mcquic.utils.specification import CodeSize, File, FileHeader, ImageSize
+    rec = []
+    for version, qp, m, hs, ws, k, (ih, iw, ic), contents in CONTAINER_CASES:
+        f = File(FileHeader(version, qp, CodeSize(m, hs, ws, k), ImageSize(ih, iw, ic)), list(contents))
+        data = f.serialize()
+        back = File.deserialize(data)
+        assert back.fileHeader.codeSize.k == k and list(back.contents) == list(contents)
+        rec.append({"sha256": hashlib.sha256(data).hexdigest(), "size": len(data), "head_hex": data[:160].hex(),
+                    "bpp": f.BPP, "str": str(f)})
+        print("container", qp, len(data), "bytes")
+    with open(os.path.join(OUT, "container_reference.json"), "w") as fp:
+        json.dump(rec, fp, indent=1)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--container" in sys.argv:
+        container()
+        sys.exit(0)
     if "--blocks" in sys.argv:
         blocks()
     elif "--neon" in sys.argv:
@@ -213,3 +246,4 @@ if __name__ == "__main__":
         blocks()
         neon()
         baseline_configs()
+        container()

@@ -69,6 +69,149 @@ class _Registry:
         return str(sorted(cls._map))
 
 
+def _mini_marshmallow():
+    """A FUNCTIONAL minimal stand-in for the parts of marshmallow 3 the reference's schemas use
+    (mcquic/utils/specification.py:14-54, mcquic/config.py): declared-field collection in declaration order, `dump` (object
+    or mapping -> plain dict, field by field, nested schemas and lists recursed), `load` (unknown keys raise, field
+    deserialisation + `_validate`, then the schema's `@post_load` hook).  With it the reference's own `File.serialize` /
+    `File.deserialize` run unmodified, so the `.mcq` container bytes can be pinned against them."""
+
+    class ValidationError(ValueError):
+        pass
+
+    class Field:
+        def __init__(self, *a, **k):
+            self.required = k.get("required", False)
+
+        def _serialize(self, value):
+            return value
+
+        def _deserialize(self, value):
+            return value
+
+        def _validate(self, value):
+            pass
+
+        def serialize(self, value):
+            return None if value is None else self._serialize(value)
+
+        def deserialize(self, value):
+            out = self._deserialize(value)
+            self._validate(out)
+            return out
+
+    class Int(Field):
+        def _serialize(self, value):
+            return int(value)
+
+        def _deserialize(self, value):
+            if isinstance(value, bool) or not isinstance(value, (int, float, str)):
+                raise ValidationError("Not a valid integer.")
+            try:
+                return int(value)
+            except (TypeError, ValueError):
+                raise ValidationError("Not a valid integer.")
+
+    class Float(Field):
+        def _serialize(self, value):
+            return float(value)
+
+        _deserialize = _serialize
+
+    class Bool(Field):
+        def _serialize(self, value):
+            return bool(value)
+
+        _deserialize = _serialize
+
+    class Str(Field):
+        def _serialize(self, value):
+            return value.decode() if isinstance(value, bytes) else str(value)
+
+        def _deserialize(self, value):
+            if not isinstance(value, (str, bytes)):
+                raise ValidationError("Not a valid string.")
+            return value.decode() if isinstance(value, bytes) else value
+
+    class List(Field):
+        def __init__(self, inner, *a, **k):
+            super().__init__(*a, **k)
+            self.inner = inner() if isinstance(inner, type) else inner
+
+        def _serialize(self, value):
+            return [self.inner.serialize(v) for v in value]
+
+        def _deserialize(self, value):
+            if isinstance(value, (str, bytes, dict)) or not hasattr(value, "__iter__"):
+                raise ValidationError("Not a valid list.")
+            return [self.inner.deserialize(v) for v in value]
+
+    class Dict(Field):
+        pass
+
+    class Raw(Field):
+        pass
+
+    class Nested(Field):
+        def __init__(self, schema, *a, **k):
+            super().__init__(*a, **k)
+            self.schema = schema() if isinstance(schema, type) else schema
+
+        def _serialize(self, value):
+            return self.schema.dump(value)
+
+        def _deserialize(self, value):
+            return self.schema.load(value)
+
+    def post_load(fn=None, **kw):
+        def mark(f):
+            f.__post_load__ = True
+            return f
+        return mark(fn) if fn is not None else mark
+
+    class SchemaMeta(type):
+        def __new__(mcs, name, bases, attrs):
+            declared = [(k, v) for k, v in attrs.items() if isinstance(v, Field)]      # class body order
+            hooks = [v for v in attrs.values() if getattr(v, "__post_load__", False)]
+            for k, _ in declared:
+                del attrs[k]
+            cls = super().__new__(mcs, name, bases, attrs)
+            inherited = []
+            for base in bases:
+                inherited += getattr(base, "_declared_fields", [])
+            cls._declared_fields = inherited + declared
+            cls._post_load_hooks = hooks or [h for base in bases for h in getattr(base, "_post_load_hooks", [])]
+            return cls
+
+    class Schema(metaclass=SchemaMeta):
+        def __init__(self, *a, **k):
+            pass
+
+        def dump(self, obj):
+            out = {}
+            for name, field in self._declared_fields:
+                value = obj[name] if isinstance(obj, dict) else getattr(obj, name)
+                out[name] = field.serialize(value)
+            return out
+
+        def load(self, data):
+            if not isinstance(data, dict):
+                raise ValidationError("Invalid input type.")
+            known = dict(self._declared_fields)
+            unknown = [k for k in data if k not in known]
+            if unknown:
+                raise ValidationError({k: ["Unknown field."] for k in unknown})           # Meta.unknown = RAISE (default)
+            out = {name: field.deserialize(data[name]) for name, field in self._declared_fields if name in data}
+            for hook in self._post_load_hooks:
+                out = hook(self, out)
+            return out
+
+    import types as _types
+    fields = _types.SimpleNamespace(Field=Field, Int=Int, Integer=Int, Str=Str, String=Str, List=List, Nested=Nested,
+                                    Dict=Dict, Bool=Bool, Boolean=Bool, Float=Float, Raw=Raw)
+    return dict(Schema=Schema, fields=fields, post_load=post_load, RAISE="raise", ValidationError=ValidationError)
+
+
 def load():
     """Returns the reference `mcquic` package namespace (idempotent)."""
     if "mcquic.modules.compressor" in sys.modules:
@@ -87,21 +230,17 @@ def load():
     _pkg("vlutils")
     _pkg("vlutils.base", Registry=_Registry, Restorable=_Restorable, FrequecyHook=_FrequecyHook)
     _mod("vlutils.base.registry", Registry=_Registry)
-    _mod("vlutils.logger", readableSize=lambda *a, **k: "", configLogging=lambda *a, **k: None,
-         LoggerBase=object)
+    def _readable_size(size, floating=2):      # vlutils.logger.readableSize: binary units, two decimals
+        value = float(size)
+        for unit in ("B", "KiB", "MiB", "GiB", "TiB"):
+            if value < 1024.0 or unit == "TiB":
+                return f"{int(value)} {unit}" if unit == "B" else f"{value:.{floating}f} {unit}"
+            value /= 1024.0
 
-    class _Field:
-        def __init__(self, *a, **k):
-            pass
+    sys.modules["vlutils"].logger = _mod("vlutils.logger", readableSize=_readable_size,
+                                         configLogging=lambda *a, **k: None, LoggerBase=object)
 
-    class _Schema:
-        def __init__(self, *a, **k):
-            pass
-
-    fields = types.SimpleNamespace(Field=_Field, Int=_Field, Str=_Field, List=_Field, Nested=_Field,
-                                   Dict=_Field, Bool=_Field, Float=_Field, Raw=_Field)
-    _mod("marshmallow", Schema=_Schema, fields=fields, post_load=lambda f=None, **k: (f if f else (lambda g: g)),
-         RAISE="raise", ValidationError=ValueError)
+    _mod("marshmallow", **_mini_marshmallow())
 
     _pkg("fairscale")
     _pkg("fairscale.nn")

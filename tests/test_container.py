@@ -1,9 +1,10 @@
 """NEXT-2: the `.mcq` container and the CLI helpers (mcquic/utils/specification.py:136-160, mcquic/demo.py,
 mcquic/data/transforms.py:60-80, mcquic/utils/vision.py:135-146).
 
-The reference's `File.serialize` needs marshmallow (absent here), so the byte layout is pinned by a hand-decoded known
-answer: msgpack of `FileSchema().dump(file)`, a dict in field-declaration order.  The image helpers are compared with
-the reference's own classes where the reference tree is present."""
+Container bytes are pinned to the reference's OWN `File.serialize` / `File.deserialize` (specification.py:147-156), executed
+unmodified through the functional marshmallow stand-in of oracle/ref_import.py where the reference tree is present, and to
+its committed outputs (tests/golden/container_reference.json, oracle/gen_golden.py --container) elsewhere; plus a
+hand-decoded known answer.  The image helpers are compared with the reference's own classes."""
 import warnings
 
 import msgpack
@@ -35,6 +36,67 @@ def test_known_answer_bytes_and_field_order():
     assert list(d["fileHeader"]["codeSize"]) == ["m", "heights", "widths", "k"]    # CodeSizeSchema
     assert list(d["fileHeader"]["imageSize"]) == ["height", "width", "channel"]    # ImageSizeSchema
     assert all(isinstance(c, bytes) for c in d["contents"])                        # use_bin_type=True -> bin, not str
+
+
+def _cases():
+    import hashlib
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    from oracle.gen_golden import CONTAINER_CASES
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "container_reference.json")) as fp:
+        golden = json.load(fp)
+    return CONTAINER_CASES, golden, hashlib
+
+
+def test_bytes_equal_the_reference_outputs_committed_as_golden():
+    cases, golden, hashlib = _cases()
+    assert len(cases) == len(golden)
+    for (version, qp, m, hs, ws, k, (ih, iw, ic), contents), g in zip(cases, golden):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            f = File(FileHeader(version, qp, CodeSize(m, hs, ws, k), ImageSize(ih, iw, ic)), list(contents))
+            data = f.serialize()
+            assert len(data) == g["size"] and hashlib.sha256(data).hexdigest() == g["sha256"]
+            assert data[:160].hex() == g["head_hex"]
+            assert f.BPP == g["bpp"] and str(f) == g["str"]
+            assert File.deserialize(data) == f
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_bytes_equal_reference_file_serialize_and_each_reads_the_other():
+    """the reference's File / FileHeader / schemas, unmodified, next to ours: same bytes out, and each side deserialises
+    what the other wrote; malformed input is rejected by both"""
+    ref_import.load()
+    from marshmallow import ValidationError
+    from mcquic.utils import specification as R
+    cases, _, _ = _cases()
+    for version, qp, m, hs, ws, k, (ih, iw, ic), contents in cases:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mine = File(FileHeader(version, qp, CodeSize(m, hs, ws, k), ImageSize(ih, iw, ic)), list(contents))
+            ref = R.File(R.FileHeader(version, qp, R.CodeSize(m, hs, ws, k), R.ImageSize(ih, iw, ic)), list(contents))
+            a, b = mine.serialize(), ref.serialize()
+            assert a == b
+            back = R.File.deserialize(a)                      # the reference opens our file
+            assert back.fileHeader.qp == qp and back.fileHeader.codeSize.heights == hs and list(back.contents) == contents
+            assert File.deserialize(b) == mine                # we open the reference's
+            assert mine.BPP == ref.BPP and mine.size() == ref.size() and str(mine) == str(ref)
+    d = _file().to_dict()
+    d["extra"] = 1
+    bad = msgpack.packb(d, use_bin_type=True)
+    with pytest.raises(ValidationError):
+        R.File.deserialize(bad)
+    with pytest.raises(ValueError):
+        File.deserialize(bad)
+    d = _file().to_dict()
+    d["contents"] = [b""]
+    bad = msgpack.packb(d, use_bin_type=True)
+    with pytest.raises(ValidationError):
+        R.File.deserialize(bad)
+    with pytest.raises(ValueError):
+        File.deserialize(bad)
 
 
 def test_round_trip_bpp_and_size():

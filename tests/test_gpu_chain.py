@@ -17,11 +17,15 @@ def _model(channel, m, k):
 
 
 @pytest.fixture
-def per_tap_kernels_only(monkeypatch):
+def per_tap_kernels_only():
     """the chain kernel shares its tile body (and so its summation order) with the per-tap kernel conv_tc.cuh; the halo /
     CTA-pair kernels sum K in another order, so bit-exactness is checked with those switched off"""
-    monkeypatch.setenv("MCQ_HALO", "0")
-    monkeypatch.setenv("MCQ_PAIR", "0")
+    old = {name: _lib.get_option(name) for name in ("halo", "pair")}
+    _lib.set_option("halo", 0)
+    _lib.set_option("pair", 0)
+    yield
+    for name, v in old.items():
+        _lib.set_option(name, v)
 
 
 @pytest.mark.parametrize("n", [1, 3, 17, 64])

@@ -74,3 +74,19 @@ def test_cli_refuses_what_it_cannot_do(tmp_path):
     with pytest.raises(ValueError, match="Invalid input file"):
         cli.main(["-q", "--synthetic", str(bad)])
     assert cli.main(["-q", "--synthetic", str(tmp_path / "missing.png")]) == 2
+
+
+def test_speed_protocol_runs_and_round_trips(capsys):
+    """`--speed` = the reference's Validator.speed (validator.py:60-97): same tensor shape, same call sequence, same
+    formula; here with 2 repetitions.  The binaries it produced decode back to the codes it returned."""
+    import logging
+    model = cli.load_model(2, None, torch.device("cuda"), False, logging.getLogger("test"), synthetic=True)
+    (enc, dec), summary = cli.speed(model, torch.device("cuda"), reps=2)
+    assert enc > 0 and dec > 0 and summary.startswith("Coding throughput: encoder: ")
+    x = torch.rand(2, 3, 768, 512, device="cuda")
+    codes, binaries, headers = model.compress(x)
+    assert [tuple(c.shape) for c in codes] == [(2, 2, 48, 32), (2, 2, 24, 16), (2, 2, 12, 8)]
+    back = model._quantizer._entropyCoder.decompress(binaries, [h.CodeSize for h in headers])
+    assert all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(back, codes))
+    assert cli.main(["--speed", "-q", "-qp", "1", "--synthetic"]) == 0
+    assert "Coding throughput" in capsys.readouterr().out

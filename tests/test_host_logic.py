@@ -26,8 +26,17 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.load().__dict__.get("_name", _lib.library_path()))
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().mcq_version() == 1
+    assert _lib.load().mcq_version() == 2
     assert b"bad argument" in _lib.load().mcq_error_string(-1)
+    # explicit options (no environment reads on the launch path): round trip, unknown names rejected
+    assert _lib.get_option("pdl") == 1
+    _lib.set_option("pdl", 0)
+    assert _lib.get_option("pdl") == 0
+    _lib.set_option("pdl", 1)
+    with pytest.raises(RuntimeError):
+        _lib.set_option("no_such_knob", 1)
+    src = open(os.path.join(ROOT, "mcquic_b200", "csrc", "mcq_api.cu")).read()
+    assert "getenv" not in src
 
 
 def test_conv_params_struct_matches_header_field_order():

@@ -245,12 +245,14 @@ def g_timing():
 
 
 def g_halo():
-    """halo kernel variants; configuration comes from MCQ_HALO_* environment variables"""
+    """halo kernel variants; configuration = library options given as MCQ_OPTIONS="halo=1,halo_cl=2,..." (applied by this
+    script through mcq_set_option; the library itself never reads the environment)"""
     import torch
     from convcase import make_planes
     from mcquic_b200 import _lib
     from mcquic_b200.engine import Act, Engine, pack_conv
-    print("  env", {k: v for k, v in os.environ.items() if k.startswith("MCQ_")}, flush=True)
+    print("  options", os.environ.get("MCQ_OPTIONS", ""), flush=True)
+    _lib.apply_options(os.environ.get("MCQ_OPTIONS", ""))
     eng = Engine("tcgen05")
     for passes in (1, 3):
         _case(eng, f"halo 16x16 n1 p{passes}", n=1, h=16, w=16, cin=128, cout=128, passes=passes)
@@ -295,7 +297,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "halo_sweep":
         combos = [("0", "10", "0", "1", "0"), ("1", "10", "0", "1", "0"), ("1", "10", "0", "2", "0"), ("1", "10", "0", "2", "1"), ("0", "10", "0", "1", "1")]
         for (on, pitch, base, cl, skip) in combos:
-            env = dict(os.environ, MCQ_HALO=on, MCQ_HALO_PITCH=pitch, MCQ_HALO_BASE=base, MCQ_HALO_CL=cl, MCQ_EPI_SKIP=skip)
+            env = dict(os.environ, MCQ_OPTIONS=f"halo={on},halo_pitch={pitch},halo_base={base},halo_cl={cl},epi_skip={skip}")
             print(f"==== halo={on} pitch={pitch} base={base} cl={cl} epi_skip={skip}", flush=True)
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "halo"], timeout=300, capture_output=True, text=True, env=env)
