@@ -88,6 +88,11 @@ typedef struct mcq_conv_params {
    * Every entry is written exactly once (no atomics, no clearing needed). */
   void* gn_partials;
   int32_t gn_groups; /* group count of the GroupNorm that follows */
+  /* MCQ_STORE_SHUFFLE_NCHW only: when != NULL the pixels are written here as uint8 [n, c, 2y+i, 2x+j] through the
+   * reference's DeTransform (mcquic/utils/vision.py:135-146: ((x + 1) / 2 * 255.999).clamp(0, 255).byte()) instead of as
+   * fp32 to out_f32 (which may then be NULL): what demo.decompressImage returns (demo.py:124-134), 1 byte per sample
+   * over PCIe instead of 4. */
+  void* out_u8;
 } mcq_conv_params;
 
 /* Replaces nn.Conv2d 3x3 / 1x1 (+ the elementwise ops around it) as used by mcquic/nn/blocks.py:62-288,
@@ -113,13 +118,23 @@ int32_t mcq_conv_chain_max_layers(void);
  * issues [0,1024), MMA stage arrivals [1024,2048) and epilogue tile begin/end pairs [2048,3072).  NULL = off. */
 void mcq_debug_timeline(void* device_i64_3072);
 
-/* First layer: conv3x3 stride 2, 3 -> cout, on the fp32 NCHW image, with AlignedPadding's reflect pad folded
+/* First layer: conv3x3 stride 2, 3 -> cout, on the NCHW image, with AlignedPadding's reflect pad folded
  * into the gather (mcquic/data/transforms.py:86-99, mcquic/modules/compressor.py:124).
- * x: [n, 3, h, w] fp32; pad_top/pad_left: reflect padding already split as the reference does; hp, wp: padded size.
- * w: [cout, 27] fp32 (cin, r, s order = nn.Conv2d layout), bias [cout]. Output grid is hp/2 x wp/2, NHWC. */
-int mcq_stem_conv(const float* x, int32_t n, int32_t h, int32_t w, int32_t pad_top, int32_t pad_left, int32_t hp,
-                  int32_t wp, const float* wgt, const float* bias, int32_t cout, float* out_f32, void* out_hi,
-                  void* out_lo, int32_t out_act, mcq_stream_t stream);
+ * x: [n, 3, h, w], fp32 in [-1, 1] (x_is_u8 = 0) or uint8 (x_is_u8 = 1: the reference's input transform
+ * convert_image_dtype + (x - 0.5) * 2, mcquic/demo.py:110-118, is applied on the fly with the same fp32 operations);
+ * pad_top/pad_left: reflect padding already split as the reference does; hp, wp: padded size.  Output grid is
+ * hp/2 x wp/2, NHWC.
+ * mcq_stem_conv: FP32 FFMA kernel (cross-check / fallback); w: [cout, 27] fp32 (cin, r, s order = nn.Conv2d layout).
+ * mcq_stem_conv_tc: tcgen05 kernel, fp32-grade 3-pass split like every encode-side layer; w_lohi: fp16
+ * [cout_pad, 64], row = [w_lo (27 values, 5 zeros) | w_hi (27 values, 5 zeros)] of w * 2^e, w_scale = 2^-e;
+ * cout <= cout_pad <= 128, cout % 8 == 0, cout_pad % 16 == 0 (MCQ_ERR_UNSUPPORTED otherwise: use mcq_stem_conv). */
+int mcq_stem_conv(const void* x, int32_t x_is_u8, int32_t n, int32_t h, int32_t w, int32_t pad_top, int32_t pad_left,
+                  int32_t hp, int32_t wp, const float* wgt, const float* bias, int32_t cout, float* out_f32,
+                  void* out_hi, void* out_lo, int32_t out_act, mcq_stream_t stream);
+int mcq_stem_conv_tc(const void* x, int32_t x_is_u8, int32_t n, int32_t h, int32_t w, int32_t pad_top,
+                     int32_t pad_left, int32_t hp, int32_t wp, const void* w_lohi, float w_scale, const float* bias,
+                     int32_t cout, int32_t cout_pad, float* out_f32, void* out_hi, void* out_lo, int32_t out_act,
+                     mcq_stream_t stream);
 
 /* Replaces _multiCodebookQuantization._distance + .encode (mcquic/modules/quantizer.py:144-179):
  * code[n,m,h,w] = argmin_k (|x|^2 + |c_k|^2) - 2 x.c_k, first index on ties.

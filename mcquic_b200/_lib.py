@@ -27,6 +27,7 @@ class ConvParams(_c.Structure):
         ("passes", _c.c_int32), ("impl", _c.c_int32),
         ("ev_start", _c.c_void_p), ("ev_stop", _c.c_void_p),
         ("gn_partials", _c.c_void_p), ("gn_groups", _c.c_int32),
+        ("out_u8", _c.c_void_p),
     ]
 
 
@@ -44,7 +45,9 @@ SYMBOLS = {
     "mcq_conv_chain": (_c.c_int, [_c.POINTER(ConvParams), _i32, _p]),
     "mcq_conv_chain_max_layers": (_i32, []),
     "mcq_debug_timeline": (None, [_p]),
-    "mcq_stem_conv": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _i32, _p]),
+    "mcq_stem_conv": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _i32, _p]),
+    "mcq_stem_conv_tc": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _f, _p, _i32, _i32, _p, _p, _p,
+                                    _i32, _p]),
     "mcq_vq_assign": (_c.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mcq_vq_assign_tc": (_c.c_int, [_p, _p, _p, _f, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i64, _p]),
     "mcq_vq_assign_fused": (_c.c_int, [_p, _p, _f, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),

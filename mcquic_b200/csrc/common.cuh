@@ -29,6 +29,7 @@ struct ConvArgs {
   const float* res2;
   const float* aux;
   float* out_f32;
+  unsigned char* out_u8;          // MCQ_STORE_SHUFFLE_NCHW only: uint8 pixels (DeTransform, utils/vision.py:135-146) instead of fp32
   __half* o0_hi;
   __half* o0_lo;
   __half* o1_hi;
@@ -179,6 +180,14 @@ __device__ __forceinline__ void load_f32v(const float* p, size_t off, float (&r)
   }
 }
 
+// DeTransform of the reference (mcquic/utils/vision.py:135-146): [-1, 1] -> uint8, the same fp32 operations in the same
+// order: ((x + 1) / 2 * 255.999).clamp(0, 255).byte()  (.byte() truncates)
+__device__ __forceinline__ unsigned char detransform_u8(float x) {
+  float t = __fdiv_rn(x - (-1.0f), 2.0f) * 255.999f;
+  t = fminf(fmaxf(t, 0.0f), 255.0f);
+  return (unsigned char)(int)t;
+}
+
 // Output element offset of GEMM columns [c0, ..) of conv pixel (n, oy, ox) for the NHWC stores
 // (PixelShuffle convs: column (2i+j)*C/4 + c of pixel (oy, ox) is channel c of pixel (2oy+i, 2ox+j)).
 __device__ __forceinline__ size_t epilogue_offset(const ConvArgs& p, int n, int oy, int ox, int c0) {
@@ -212,7 +221,10 @@ __device__ __forceinline__ void epilogue_store(const ConvArgs& p, int n, int oy,
       const int col = c0 + j;
       if (col < p.cout) {
         const int c = col >> 2, i = (col >> 1) & 1, jj = col & 1;
-        p.out_f32[(((size_t)n * cq + c) * H2 + (2 * oy + i)) * W2 + (2 * ox + jj)] = fmaf(v[j], scale, bias_src[col]);
+        const size_t o = (((size_t)n * cq + c) * H2 + (2 * oy + i)) * W2 + (2 * ox + jj);
+        const float y = fmaf(v[j], scale, bias_src[col]);
+        if (p.out_u8) p.out_u8[o] = detransform_u8(y);
+        else p.out_f32[o] = y;
       }
     }
     return;

@@ -19,6 +19,7 @@
 #include "misc.cuh"
 #include "vq.cuh"
 #include "vq_fused.cuh"
+#include "stem_tc.cuh"
 
 using namespace mcq;
 
@@ -192,19 +193,21 @@ int fill_args(const mcq_conv_params* p, ConvArgs& a) {
   if (p->mode == MCQ_EPI_GATE) MCQ_CHECK_ARG(p->res1 && p->aux);
   if (p->mode == MCQ_EPI_GDN || p->mode == MCQ_EPI_IGDN) MCQ_CHECK_ARG(p->aux);
   if (p->store == MCQ_STORE_SHUFFLE_NCHW) {
-    MCQ_CHECK_ARG(p->out_f32 && p->cout % 4 == 0 && p->mode == MCQ_EPI_LINEAR && !p->res1 && !p->res2);
+    MCQ_CHECK_ARG((p->out_f32 || p->out_u8) && p->cout % 4 == 0 && p->mode == MCQ_EPI_LINEAR && !p->res1 && !p->res2);
     MCQ_CHECK_ARG(!p->out0_hi && !p->out1_hi);
   } else if (p->store == MCQ_STORE_SHUFFLE_NHWC) {
     MCQ_CHECK_ARG(p->cout % 4 == 0 && (p->cout / 4) % 8 == 0);
   } else {
     MCQ_CHECK_ARG(p->cout % 8 == 0);
   }
-  MCQ_CHECK_ARG(p->out_f32 || p->out0_hi || p->out1_hi);
+  MCQ_CHECK_ARG(p->out_f32 || p->out0_hi || p->out1_hi || (p->out_u8 && p->store == MCQ_STORE_SHUFFLE_NCHW));
+  if (p->out_u8) MCQ_CHECK_ARG(p->store == MCQ_STORE_SHUFFLE_NCHW);
   std::memset(&a, 0, sizeof(a));
   a.a_hi = (const __half*)p->a_hi; a.a_lo = (const __half*)p->a_lo;
   a.w_hi = (const __half*)p->w_hi; a.w_lo = (const __half*)p->w_lo;
   a.bias = p->bias; a.res1 = p->res1; a.res2 = p->res2; a.aux = p->aux;
   a.out_f32 = p->out_f32;
+  a.out_u8 = (unsigned char*)p->out_u8;
   a.o0_hi = (__half*)p->out0_hi; a.o0_lo = (__half*)p->out0_lo;
   a.o1_hi = (__half*)p->out1_hi; a.o1_lo = (__half*)p->out1_lo;
   a.w_scale = p->w_scale; a.res1_scale = p->res1_scale;
@@ -733,16 +736,18 @@ int32_t mcq_conv_chain_max_layers(void) { return CHAIN_MAX_LAYERS; }
 
 void mcq_debug_timeline(void* device_i64_3072) { g_chain_dbg = (long long*)device_i64_3072; }
 
-int mcq_stem_conv(const float* x, int32_t n, int32_t h, int32_t w, int32_t pad_top, int32_t pad_left, int32_t hp,
-                  int32_t wp, const float* wgt, const float* bias, int32_t cout, float* out_f32, void* out_hi,
-                  void* out_lo, int32_t out_act, mcq_stream_t stream) {
+int mcq_stem_conv(const void* x, int32_t x_is_u8, int32_t n, int32_t h, int32_t w, int32_t pad_top, int32_t pad_left,
+                  int32_t hp, int32_t wp, const float* wgt, const float* bias, int32_t cout, float* out_f32,
+                  void* out_hi, void* out_lo, int32_t out_act, mcq_stream_t stream) {
   MCQ_CHECK_ARG(x && wgt && bias && (out_f32 || out_hi));
   MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && hp >= h && wp >= w && hp % 2 == 0 && wp % 2 == 0);
   MCQ_CHECK_ARG(pad_top >= 0 && pad_left >= 0 && pad_top <= hp - h && pad_left <= wp - w);
   MCQ_CHECK_ARG(pad_top < h && (hp - h - pad_top) < h && pad_left < w && (wp - w - pad_left) < w);  // reflect pad limit
   MCQ_CHECK_ARG(cout % 4 == 0 && (27 * cout + 9 * (2 * STEM_PIX + 1)) * 4 <= 48 * 1024);
   StemArgs a;
-  a.x = x; a.w = wgt; a.bias = bias; a.out_f32 = out_f32; a.o_hi = (__half*)out_hi; a.o_lo = (__half*)out_lo;
+  a.x = x_is_u8 ? nullptr : (const float*)x;
+  a.x_u8 = x_is_u8 ? (const unsigned char*)x : nullptr;
+  a.w = wgt; a.bias = bias; a.out_f32 = out_f32; a.o_hi = (__half*)out_hi; a.o_lo = (__half*)out_lo;
   a.o_act = out_act; a.n = n; a.h = h; a.w_ = w; a.pad_top = pad_top; a.pad_left = pad_left; a.hp = hp; a.wp = wp;
   a.cout = cout; a.hout = hp / 2; a.wout = wp / 2;
   const int strips = (a.wout + STEM_PIX - 1) / STEM_PIX;
@@ -751,6 +756,51 @@ int mcq_stem_conv(const float* x, int32_t n, int32_t h, int32_t w, int32_t pad_t
   stem_conv_kernel<<<(unsigned)blocks, STEM_THREADS, smem, (cudaStream_t)stream>>>(a);
   g_launches++;
   return cuda_status();
+}
+
+int mcq_stem_conv_tc(const void* x, int32_t x_is_u8, int32_t n, int32_t h, int32_t w, int32_t pad_top,
+                     int32_t pad_left, int32_t hp, int32_t wp, const void* w_lohi, float w_scale, const float* bias,
+                     int32_t cout, int32_t cout_pad, float* out_f32, void* out_hi, void* out_lo, int32_t out_act,
+                     mcq_stream_t stream) {
+  MCQ_CHECK_ARG(x && w_lohi && bias && (out_f32 || out_hi));
+  MCQ_CHECK_ARG(n > 0 && h > 0 && w > 0 && hp >= h && wp >= w && hp % 2 == 0 && wp % 2 == 0);
+  MCQ_CHECK_ARG(pad_top >= 0 && pad_left >= 0 && pad_top <= hp - h && pad_left <= wp - w);
+  MCQ_CHECK_ARG(pad_top < h && (hp - h - pad_top) < h && pad_left < w && (wp - w - pad_left) < w);  // reflect pad limit
+  MCQ_CHECK_ARG(cout > 0 && cout_pad >= cout && ((uintptr_t)w_lohi & 15) == 0);
+  if (cout % 8 != 0 || cout_pad % 16 != 0 || cout_pad > 128) return MCQ_ERR_UNSUPPORTED;
+  if ((long long)n * (hp / 2) * (wp / 2) > 0x7fffffffLL * 64) return MCQ_ERR_UNSUPPORTED;
+  ConvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.bias = bias; a.out_f32 = out_f32; a.o0_hi = (__half*)out_hi; a.o0_lo = (__half*)out_lo; a.o0_act = out_act;
+  a.w_scale = w_scale; a.res1_scale = 1.f;
+  a.n = n; a.hin = hp; a.win = wp; a.cin = 3; a.hout = hp / 2; a.wout = wp / 2;
+  a.cout = cout; a.cout_pad = cout_pad; a.ksize = 3; a.stride = 2; a.ktotal = 27;
+  a.mode = MCQ_EPI_LINEAR; a.store = MCQ_STORE_NHWC; a.passes = 3; a.bn = cout_pad; a.tiles_c = 1;
+  a.direct_epilogue = opt("direct_epi");
+  a.debug_skip_store = opt("epi_skip");
+  StemTcArgs s;
+  s.x_f32 = x_is_u8 ? nullptr : (const float*)x;
+  s.x_u8 = x_is_u8 ? (const unsigned char*)x : nullptr;
+  s.w_lohi = (const __half*)w_lohi;
+  s.h = h; s.w = w; s.pad_top = pad_top; s.pad_left = pad_left; s.hp = hp; s.wp = wp; s.cout_pad = cout_pad;
+  const long long total_pix = (long long)n * a.hout * a.wout;
+  const long long tiles = (total_pix + STC_BM - 1) / STC_BM;
+  const size_t smem = 1024 + 2 * STC_A_BYTES + 16384 + 128 + (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 * 4 + 64;
+  cudaError_t e = ensure_dyn_smem<KTag<800>>(stem_tc_kernel, smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()));
+  cfg.blockDim = dim3(STC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = opt("pdl") ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, stem_tc_kernel, a, s);
+  g_launches++;
+  return e == cudaSuccess ? cuda_status() : (int)e;
 }
 
 int mcq_vq_assign(const float* x, const float* codebook, const float* c2, int64_t* codes, float* logits,

@@ -6,7 +6,8 @@
 namespace mcq {
 
 struct StemArgs {
-  const float* x;   // [n, 3, h, w]
+  const float* x;   // [n, 3, h, w] fp32, or
+  const unsigned char* x_u8;   // uint8: value = (u / 255 - 0.5) * 2 (mcquic/demo.py:110-118)
   const float* w;   // [cout, 27]
   const float* bias;
   float* out_f32;
@@ -49,7 +50,8 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const StemArgs 
     float v = 0.f;
     if (Y >= 0 && Y < a.hp && X >= 0 && X < a.wp) {
       const int sy = reflect_idx(Y - a.pad_top, a.h), sx = reflect_idx(X - a.pad_left, a.w_);
-      v = a.x[(((size_t)n * 3 + ci) * a.h + sy) * a.w_ + sx];
+      const size_t idx = (((size_t)n * 3 + ci) * a.h + sy) * a.w_ + sx;
+      v = a.x_u8 ? (__fdiv_rn((float)a.x_u8[idx], 255.0f) - 0.5f) * 2.0f : a.x[idx];
     }
     patch[i] = v;
   }

@@ -157,6 +157,7 @@ class Engine:
         self._rec_depth = 0
         # stride-1 convs with cin % 8 == 0 run on the tensor cores with a partly zero-filled last K chunk (A/B knob)
         self.partial_chunk = True
+        self.stem_tc = True      # the stem on the tensor cores (csrc/stem_tc.cuh); False: FFMA kernel (A/B knob)
 
     # ------------------------------------------------------------------ plumbing
     @contextlib.contextmanager
@@ -379,11 +380,16 @@ class Engine:
             return t
 
         if pc.store == _lib.STORE_SHUFFLE_NCHW:
-            if into is not None:
-                out.f32 = given(into.f32, (x.n, co, ho, wo), torch.float32)
+            if into is not None and into.f32 is not None and into.f32.dtype == torch.uint8:
+                # uint8 pixels through the reference's DeTransform (vision.py:135-146) in the epilogue
+                out.f32 = given(into.f32, (x.n, co, ho, wo), torch.uint8)
+                p.out_u8 = _ptr(out.f32)
             else:
-                out.f32 = torch.empty((x.n, co, ho, wo), dtype=torch.float32, device=dev)  # NCHW pixels
-            p.out_f32 = _ptr(out.f32)
+                if into is not None:
+                    out.f32 = given(into.f32, (x.n, co, ho, wo), torch.float32)
+                else:
+                    out.f32 = torch.empty((x.n, co, ho, wo), dtype=torch.float32, device=dev)  # NCHW pixels
+                p.out_f32 = _ptr(out.f32)
         else:
             if "f32" in want:
                 if into is not None:
@@ -569,31 +575,71 @@ class Engine:
         return x
 
     # ------------------------------------------------------------------ boundary ops
-    def stem(self, conv: nn.Conv2d, x: torch.Tensor, pad: Tuple[int, int, int, int], want: Set[str]) -> Act:
-        """conv3x3 s2 on the fp32 NCHW image; pad = (top, left, padded_h, padded_w) (AlignedPadding folded in).
-        (Chunked execution calls this on batch slices of the image tensor; the outputs are chunk-local.)"""
+    def _packed_stem(self, conv: nn.Conv2d):
+        """tcgen05 operand of the stem: fp16 [cout_pad, 64], row = [w_lo (27 + 5 zeros) | w_hi (27 + 5 zeros)] of
+        w * 2^e (csrc/stem_tc.cuh), plus (2^-e, bias, cout_pad); cached per weight version"""
+        key = (id(conv), "stem")
+        try:
+            ver = (conv.weight._version, conv.bias._version, conv.weight.data_ptr(), conv.bias.data_ptr())
+        except RuntimeError:
+            ver = (0, 0, conv.weight.data_ptr(), conv.bias.data_ptr())
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        cout = conv.out_channels
+        hi, lo, scale = split_weight(conv.weight.detach().float().reshape(cout, 27))
+        cout_pad = (cout + 15) // 16 * 16
+        rows = torch.zeros((cout_pad, 64), dtype=torch.float16, device=conv.weight.device)
+        rows[:cout, 0:27] = lo
+        rows[:cout, 32:59] = hi
+        packed = (rows.contiguous(), scale, conv.bias.detach().contiguous().float(), cout_pad)
+        self._packed[key] = (ver, packed)
+        return packed
+
+    def stem(self, conv: nn.Conv2d, x: torch.Tensor, pad: Tuple[int, int, int, int], want: Set[str],
+             into: Optional[Act] = None) -> Act:
+        """conv3x3 s2 on the NCHW image; pad = (top, left, padded_h, padded_w) (AlignedPadding folded in).
+        x: fp32 in [-1, 1], or uint8 (the reference's input transform convert_image_dtype + (x - 0.5) * 2, demo.py:110-118,
+        is then applied inside the kernel).  tcgen05 kernel (fp32-grade 3-pass) for cout <= 128, FFMA kernel otherwise /
+        for impl='simt'.  (Chunked execution calls this on batch slices of the image tensor.)"""
         self.flush()
         n, c, h, w = x.shape
         if c != 3 or conv.in_channels != 3 or conv.stride[0] != 2:
             raise RuntimeError("mcquic_b200: the stem expects [n, 3, h, w] input and conv3x3(3, C, stride=2)")
+        if x.dtype not in (torch.float32, torch.uint8):
+            raise RuntimeError(f"mcquic_b200: images must be float32 in [-1, 1] or uint8, got {x.dtype}")
         top, left, hp, wp = pad
         cout = conv.out_channels
-        out = Act(n, hp // 2, wp // 2, cout)
         dev = x.device
-        if "f32" in want:
-            out.f32 = torch.empty((n, out.h, out.w, cout), dtype=torch.float32, device=dev)
+        out = into if into is not None else Act(n, hp // 2, wp // 2, cout)
+        if into is None:
+            if "f32" in want:
+                out.f32 = torch.empty((n, out.h, out.w, cout), dtype=torch.float32, device=dev)
+            if "silu" in want:
+                out.silu = self._planes(n, out.h, out.w, cout, dev)
+            elif "raw" in want:
+                out.raw = self._planes(n, out.h, out.w, cout, dev)
         pl, act = (None, None), _lib.ACT_NONE
         if "silu" in want:
-            out.silu = pl = self._planes(n, out.h, out.w, cout, dev)
-            act = _lib.ACT_SILU
+            pl, act = out.silu, _lib.ACT_SILU
         elif "raw" in want:
-            out.raw = pl = self._planes(n, out.h, out.w, cout, dev)
+            pl = out.raw
+        xc = x.contiguous()
+        u8 = 1 if x.dtype == torch.uint8 else 0
+        f32 = out.f32 if "f32" in want else None
+        if self.impl == _lib.IMPL_TCGEN05 and not self.emulated and cout <= 128 and cout % 8 == 0 and self.passes == 3 \
+                and self.stem_tc:
+            rows, scale, bias, cout_pad = self._packed_stem(conv)
+            with self._prof("mcq_stem_conv_tc"):
+                _lib.check(self.lib.mcq_stem_conv_tc(_ptr(xc), u8, n, h, w, top, left, hp, wp, _ptr(rows), scale,
+                                                     _ptr(bias), cout, cout_pad, _ptr(f32), _ptr(pl[0]), _ptr(pl[1]),
+                                                     act, self._stream()), "mcq_stem_conv_tc")
+            return out
         wgt = conv.weight.detach().reshape(cout, 27).contiguous().float()
         bias = conv.bias.detach().contiguous().float()
-        xc = x.contiguous().float()
         with self._prof("mcq_stem_conv"):
-            _lib.check(self.lib.mcq_stem_conv(_ptr(xc), n, h, w, top, left, hp, wp, _ptr(wgt), _ptr(bias), cout,
-                                              _ptr(out.f32), _ptr(pl[0]), _ptr(pl[1]), act, self._stream()),
+            _lib.check(self.lib.mcq_stem_conv(_ptr(xc), u8, n, h, w, top, left, hp, wp, _ptr(wgt), _ptr(bias), cout,
+                                              _ptr(f32), _ptr(pl[0]), _ptr(pl[1]), act, self._stream()),
                        "mcq_stem_conv")
         return out
 

@@ -152,8 +152,10 @@ class BaseCompressor(nn.Module):
         return self._encoder[0].weight.device
 
     def _host_batch_ok(self, t: torch.Tensor) -> bool:
-        """A pinned, contiguous fp32 host batch that the chunked copy/compute pipeline can stream."""
-        return (not t.is_cuda and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4
+        """A pinned, contiguous host batch (fp32 in [-1, 1], or uint8 images as demo.compressImage / decompressImage
+        take and return them) that the chunked copy/compute pipeline can stream."""
+        return (not t.is_cuda and t.is_pinned() and t.dtype in (torch.float32, torch.uint8) and t.is_contiguous()
+                and t.dim() == 4
                 and self.use_graphs and not self.engine.emulated and self._device().type == "cuda"
                 and isinstance(self._encoder[1], ResidualBlock) and isinstance(self._decoder[5], ResidualBlock))
 
@@ -292,7 +294,7 @@ class BaseCompressor(nn.Module):
         dev = self._device()
         n, _, h, w = x.shape
         bounds = self.host_slices(n, small_first=True)
-        key = ("enc", tuple(x.shape), self.encode_passes, dev)
+        key = ("enc", tuple(x.shape), x.dtype, self.encode_passes, dev)
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
             if pipe is None:
@@ -300,7 +302,7 @@ class BaseCompressor(nn.Module):
                 eng = self.engine
                 eng.passes = self.encode_passes
                 total = self._quantizer.hist_size()
-                sx = torch.empty(tuple(x.shape), dtype=torch.float32, device=dev)
+                sx = torch.empty(tuple(x.shape), dtype=x.dtype, device=dev)
                 sh = torch.zeros(total, dtype=torch.int32, device=dev)
                 _, _, hp, wp = aligned_pad_amounts(h, w)
                 y1 = eng.alloc_act(n, hp // 2, wp // 2, self._encoder[0].out_channels, eng.needs_of(self._encoder[2]), dev)
@@ -346,14 +348,14 @@ class BaseCompressor(nn.Module):
         dev = codes[0].device
         n = codes[0].shape[0]
         bounds = self.host_slices(n, small_first=False)
-        key = ("dec", tuple(tuple(c.shape) for c in codes), tuple(out.shape), self.decode_passes, dev)
+        key = ("dec", tuple(tuple(c.shape) for c in codes), tuple(out.shape), out.dtype, self.decode_passes, dev)
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
             if pipe is None:
                 mem0 = torch.cuda.memory_allocated()
                 sc = [torch.zeros_like(c) for c in codes]
                 status = torch.zeros(1, dtype=torch.int32, device=dev)
-                sout = torch.empty(tuple(out.shape), dtype=torch.float32, device=dev)
+                sout = torch.empty(tuple(out.shape), dtype=out.dtype, device=dev)
 
                 def main_body():
                     status.zero_()
@@ -392,15 +394,17 @@ class BaseCompressor(nn.Module):
     @torch.no_grad()
     def encode(self, x: torch.Tensor, hist: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         """compressor.py:79-88.  `hist`: optional flat int32 [sum_l m*k_l] code histogram, accumulated in place.
-        x may also be a pinned fp32 host batch: it is then streamed to the GPU in chunks that overlap the first layers
-        (codes are returned on the model's device)."""
+        x may also be a pinned host batch: it is then streamed to the GPU in chunks that overlap the first layers
+        (codes are returned on the model's device), and / or uint8 RGB images (host or device) as `demo.compressImage`
+        receives them (demo.py:109-118): `convert_image_dtype` + `(x - 0.5) * 2` then happen inside the first kernel
+        with the reference's fp32 operations, so a host batch crosses PCIe as bytes."""
         self._check_image(x)
         self._check_weights()
         if not x.is_cuda and self._host_batch_ok(x):
             return self._encode_pipelined(x, hist)
         if not (self.use_graphs and x.is_cuda):
             return self._encode_eager(x, hist)
-        x = x.contiguous().float()
+        x = x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
         total = self._quantizer.hist_size()
 
         def make_static():
@@ -410,7 +414,8 @@ class BaseCompressor(nn.Module):
             sh.zero_()
             return self._encode_eager(sx, sh)
 
-        graph, (sx, sh), codes, launches = self._graph(("enc", tuple(x.shape), self.encode_passes, x.device), make_static, body)
+        graph, (sx, sh), codes, launches = self._graph(("enc", tuple(x.shape), x.dtype, self.encode_passes, x.device),
+                                                       make_static, body)
         sx.copy_(x)
         graph.replay()
         self.graph_launches += launches
@@ -421,8 +426,10 @@ class BaseCompressor(nn.Module):
     @torch.no_grad()
     def decode(self, codes: List[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """compressor.py:114-117 (no crop; `decompress` crops upstream).
-        out (extension): a pinned fp32 host tensor [n, 3, H_pad, W_pad]; the pixels are then streamed into it in chunks
-        that overlap the last layers, and `out` is returned (complete when the call returns)."""
+        out (extension): a pinned host tensor [n, 3, H_pad, W_pad]; the pixels are then streamed into it in chunks
+        that overlap the last layers, and `out` is returned (complete when the call returns).  fp32: the pixels as upstream;
+        uint8: the pixels through the reference's DeTransform (utils/vision.py:135-146, what demo.decompressImage returns),
+        applied in the last kernel's epilogue."""
         if len(codes) == 0:
             raise RuntimeError("Length of codes is 0.")
         self._check_weights()
@@ -430,7 +437,7 @@ class BaseCompressor(nn.Module):
         if out is not None:
             ok = all(c.is_cuda and c.dtype == torch.int64 and c.dim() == 4 and c.is_contiguous() for c in codes)
             if not (ok and self._host_batch_ok(out) and out.shape[0] == codes[0].shape[0]):
-                raise RuntimeError("decode(out=): needs CUDA int64 codes and a pinned contiguous fp32 host tensor "
+                raise RuntimeError("decode(out=): needs CUDA int64 codes and a pinned contiguous fp32 / uint8 host tensor "
                                    "[n, 3, H_pad, W_pad]")
             if len(codes) != len(self._quantizer._k):
                 raise RuntimeError(f"expected {len(self._quantizer._k)} code levels, got {len(codes)}")
@@ -570,6 +577,8 @@ class Neon(BaseCompressor):
         return False        # the host I/O pipeline is built around Compressor's strided stem / pixel-shuffle tail
 
     def _encode_eager(self, x: torch.Tensor, hist: Optional[torch.Tensor]) -> List[torch.Tensor]:
+        if x.dtype == torch.uint8:
+            raise RuntimeError("Neon.encode takes float images in [-1, 1] (uint8 input is a Compressor extension)")
         eng = self.engine
         eng.passes = self.encode_passes
         n, _, h, w = x.shape

@@ -74,7 +74,13 @@ class EmulatedLib:
         v = (acc * p.w_scale).float() + bias[None, :, None, None]
         ho, wo = hin // s, win // s
         if p.store == _lib.STORE_SHUFFLE_NCHW:
-            _arr(p.out_f32, (n, p.cout // 4, 2 * ho, 2 * wo), np.float32)[...] = F.pixel_shuffle(v, 2).numpy()
+            pix = F.pixel_shuffle(v, 2)
+            if p.out_u8:
+                u8 = (((pix - (-1.0)) / 2.0) * 255.999).clamp(0.0, 255.0).byte()      # DeTransform, vision.py:135-146
+                buf = (ctypes.c_uint8 * u8.numel()).from_address(p.out_u8)
+                np.ctypeslib.as_array(buf).reshape(tuple(u8.shape))[...] = u8.numpy()
+            else:
+                _arr(p.out_f32, (n, p.cout // 4, 2 * ho, 2 * wo), np.float32)[...] = pix.numpy()
             self.launches += 1
             return 0
         y = v.permute(0, 2, 3, 1)  # NHWC, GEMM-column order
@@ -122,8 +128,13 @@ class EmulatedLib:
     def mcq_conv_chain_max_layers(self):
         return 28
 
-    def mcq_stem_conv(self, x, n, h, w, top, left, hp, wp, wgt, bias, cout, out_f32, out_hi, out_lo, act, stream):
-        xi = torch.from_numpy(_arr(x.value, (n, 3, h, w), np.float32).copy())
+    def mcq_stem_conv(self, x, x_is_u8, n, h, w, top, left, hp, wp, wgt, bias, cout, out_f32, out_hi, out_lo, act, stream):
+        if x_is_u8:
+            buf = (ctypes.c_uint8 * (n * 3 * h * w)).from_address(x.value)
+            xi = torch.from_numpy(np.ctypeslib.as_array(buf).reshape(n, 3, h, w).copy())
+            xi = (xi.float() / 255.0 - 0.5) * 2          # demo.py:110-118
+        else:
+            xi = torch.from_numpy(_arr(x.value, (n, 3, h, w), np.float32).copy())
         if hp != h or wp != w:
             xi = F.pad(xi, (left, wp - w - left, top, hp - h - top), "reflect")
         wt = torch.from_numpy(_arr(wgt.value, (cout, 3, 3, 3), np.float32).copy())

@@ -226,12 +226,14 @@ def test_reencode_after_codebook_reassignment(graphs, via):
     assert float((model.decode(codes).cpu() - O.decode(new_sd, ref)).abs().max()) <= PIXEL_TOL
 
 
-@pytest.mark.parametrize("case", ["x*2^10", "x*2^-10", "stem*2^10,x*2^-10", "codebooks*2^8"])
+@pytest.mark.parametrize("case", ["x*2^10", "x*2^-10", "stem*2^10,x*2^-10", "codebooks*2^2", "codebooks*2^-8"])
 def test_fp16_range_stress(case):
     """Activations travel as split-fp16 planes without a per-tensor scale (include/mcquic_b200.h): check the path against
     the fp32 oracle where activations are 2^10 times larger / smaller than with [-1, 1] images and reference-scale weights
     (squares of the GDN operand would leave fp16's range without MCQ_SQUARE_SCALE), with pre-scaled weights, and on the
-    decode side with codebooks 2^8 times larger.  Codes: 0 flips; pixels: 1e-3 of the oracle's output range."""
+    decode side with codebooks 4 times larger (the IGDN stages amplify quadratically: pixels reach ~1e3; at 2^8 the
+    reference's own fp32 output is 3.5e8 and the fp16 planes saturate -- activations beyond 6.5e4 are outside the format,
+    include/mcquic_b200.h) and 2^-8 times smaller.  Codes: 0 flips; pixels: 1e-3 of the oracle's output range."""
     cfg = dict(channel=128, m=1, k=[8192, 2048, 512])
     sd = synthetic_state_dict(128, 1, cfg["k"], seed=0)
     x = uniform((2, 3, 256, 256), "range.image", 9)
@@ -243,9 +245,10 @@ def test_fp16_range_stress(case):
         sd["_encoder.0.weight"] = sd["_encoder.0.weight"] * 1024.0
         x = x / 1024.0
     else:
+        factor = 4.0 if case == "codebooks*2^2" else 2.0 ** -8
         for key in sd:
             if key.endswith("._codebook"):
-                sd[key] = sd[key] * 256.0
+                sd[key] = sd[key] * factor
     model = _model(cfg, sd)
     codes = model.encode(x.cuda())
     ref, marg = O.encode(sd, x, with_margin=True)
@@ -291,3 +294,33 @@ def test_host_pipeline_matches_device_path(hw, n):
         model.decode(codes, out=torch.empty(tuple(ref_x.shape)))           # not pinned
     with pytest.raises(RuntimeError):
         model.encode(uniform((2, 3) + hw, "pipe.unpinned", 0))             # plain CPU tensor: no CPU fallback
+
+
+def test_uint8_images_in_and_out_like_the_reference_cli_flow():
+    """demo.compressImage / decompressImage (demo.py:109-134) hold images as uint8: `convert_image_dtype` + `(x - 0.5) * 2`
+    before `compress`, `DeTransform` after `decompress`.  encode(uint8) / decode(out=uint8) apply both inside the first / last
+    kernel: the codes must equal those of the float path fed with the reference's transform of the same bytes (and the
+    oracle's), the uint8 pixels must equal DeTransform of the float pixels exactly -- device-resident and through the host
+    pipeline."""
+    cfg = dict(channel=128, m=1, k=[8192, 2048, 512])
+    sd = synthetic_state_dict(128, 1, cfg["k"], seed=0)
+    model = _model(cfg, sd)
+    for (n, h, w) in ((16, 256, 256), (3, 200, 328)):
+        u8 = ((uniform((n, 3, h, w), "u8.image", 6) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+        xf = (u8.float() / 255.0 - 0.5) * 2
+        ref_codes = model.encode(xf.cuda())
+        for src in (u8.cuda(), u8.pin_memory()):
+            codes = model.encode(src)
+            assert all(torch.equal(a, b) for a, b in zip(codes, ref_codes))
+        oc, marg = O.encode(sd, xf[:2], with_margin=True)
+        flips, total, at = code_report([c[:2] for c in codes], oc, marg)
+        log_parity(f"oracle uint8 input {n}x{h}x{w}", flips, total, at, min(float(mg.min()) for mg in marg))
+        assert flips == 0, (flips, at)
+        xhat = model.decode(codes)
+        exp = O.to_uint8(xhat.cpu())
+        out = torch.empty(tuple(xhat.shape), dtype=torch.uint8).pin_memory()
+        got = model.decode(codes, out=out)
+        assert got is out and torch.equal(out, exp)
+        outf = torch.empty(tuple(xhat.shape), dtype=torch.float32).pin_memory()
+        assert torch.equal(model.decode(codes, out=outf), xhat.cpu())
+    assert model.engine.lib.mcq_device_error_flag() == 0

@@ -241,3 +241,31 @@ def test_compressor_forward_values_through_emulated_abi():
     assert torch.equal(model(xa)[2][0], model.encode(xa)[0])
     with pytest.raises(RuntimeError):
         model(x[:, :, :60])
+
+
+def test_uint8_images_take_the_reference_input_transform():
+    """encode(uint8) == encode((u8 / 255 - 0.5) * 2) (demo.py:110-118) -- host logic on the CPU model of the C ABI; the
+    last layer's uint8 store is the reference's DeTransform (vision.py:135-146)."""
+    from mcquic_b200.engine import Act
+    from mcquic_b200.utils.synthetic import synthetic_state_dict, uniform
+    from oracle import mcquic_oracle as O
+    model = Compressor(32, 2, [16, 8]).eval()
+    model.load_state_dict(synthetic_state_dict(32, 2, [16, 8], seed=0))
+    model._engine = Engine(lib=EmulatedLib())
+    u8 = ((uniform((2, 3, 100, 130), "u8.host", 0) + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8)
+    xf = (u8.float() / 255.0 - 0.5) * 2
+    a, b = model.encode(u8), model.encode(xf)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+    assert all(torch.equal(p, q) for p, q in zip(a, O.encode(model.state_dict(), xf)))
+    eng = model.engine
+    eng.passes = 1
+    status = torch.zeros(1, dtype=torch.int32)
+    y = model._quantizer.decode_act(eng, a, eng.needs_of(model._decoder[0]), status)
+    y5 = eng.run_seq(list(model._decoder)[:6], y, eng.needs_of(model._decoder[6]))
+    xf32 = eng.run(model._decoder[6], y5, set()).f32
+    out8 = torch.empty(tuple(xf32.shape), dtype=torch.uint8)
+    n, c, h, w = out8.shape
+    eng.run(model._decoder[6], y5, set(), into=Act(n, h, w, c, f32=out8))
+    assert torch.equal(out8, O.to_uint8(xf32))
+    with pytest.raises(RuntimeError):
+        model.encode(torch.zeros(1, 3, 64, 64, dtype=torch.int32))
