@@ -93,6 +93,9 @@ typedef struct mcq_conv_params {
    * fp32 to out_f32 (which may then be NULL): what demo.decompressImage returns (demo.py:124-134), 1 byte per sample
    * over PCIe instead of 4. */
   void* out_u8;
+  /* optional DEVICE scalar multiplied into w_scale by the epilogue (bias should then be zero): the backward convolutions
+   * run on gradients pre-scaled into fp16's range by a factor that lives on the device (no host sync), and remove it here */
+  const float* dev_scale;
 } mcq_conv_params;
 
 /* Replaces nn.Conv2d 3x3 / 1x1 (+ the elementwise ops around it) as used by mcquic/nn/blocks.py:62-288,
@@ -213,8 +216,11 @@ int mcq_groupnorm_apply(const float* x, const void* partials, int32_t rowblocks_
 int mcq_add_scaled(const float* x, const float* y, float alpha, int64_t count, float* out_f32, void* out_hi,
                    void* out_lo, int32_t out_act, mcq_stream_t stream);
 
-/* fp32 [count] -> split-fp16 planes, act applied first (boundary helper; also NCHW->NHWC when c,h,w given). */
-int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, mcq_stream_t stream);
+/* fp32 [count] -> split-fp16 planes of act(x * s), s = *dev_scale (optional DEVICE scalar, NULL = 1): the operand planes
+ * of the training-step convolutions (gradients are brought into fp16's range by a power of two computed on the device).
+ * out_lo may be NULL (1-pass consumers). */
+int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, const float* dev_scale,
+                     mcq_stream_t stream);
 int mcq_nchw_to_nhwc(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, float* out_f32, void* out0_hi,
                      void* out0_lo, int32_t out0_act, void* out1_hi, void* out1_lo, int32_t out1_act,
                      mcq_stream_t stream);
@@ -222,6 +228,33 @@ int mcq_nhwc_to_nchw(const float* x, int32_t n, int32_t c, int32_t h, int32_t w,
 
 /* Introspection */
 const char* mcq_error_string(int code);
+/* ---- training step (SURVEY.md section 8f NEXT-3): weight gradient of a convolution, replaces what autograd computes for
+ * nn.Conv2d.weight in the reference's training forward/backward (mcquic/modules/compressor.py:35-43 under
+ * mcquic/train/trainer.py:273-283).  dW[co, ci, r, s] = scale * (*dev_scale) * sum_p dY[p, co] * X[p @ (r, s), ci] on
+ * tcgen05 with MN-major operands (csrc/conv_wgrad.cuh): x_hi = the forward convolution's A operand plane
+ * [n, hin, win, cin] fp16 NHWC, dy_hi = the plane of the output gradient [n, hin/stride, win/stride, cout] fp16 NHWC
+ * (one fp16 pass, fp32 accumulation: TF32-grade, as the reference trains).  dw: fp32 [cout, cin, ksize, ksize]
+ * (nn.Conv2d layout), overwritten or (accumulate != 0) added to.  cin % 8 == 0, cout % 8 == 0; stride 2 needs
+ * cin % 64 == 0 (MCQ_ERR_UNSUPPORTED otherwise).  workspace: device scratch of mcq_conv_wgrad_workspace_bytes(p), 256 B
+ * aligned.  The dgrad (input gradient) needs no entry point of its own: it is mcq_conv2d with flipped / transposed
+ * weights (stride 2: the sub-pixel form with MCQ_STORE_SHUFFLE_NHWC), see mcquic_b200/autograd.py. */
+typedef struct mcq_wgrad_params {
+  const void* x_hi;
+  int32_t n, hin, win, cin;
+  const void* dy_hi;
+  int32_t cout;
+  int32_t ksize;  /* 1 or 3 */
+  int32_t stride; /* 1 or 2 */
+  float* dw;
+  float scale;
+  const float* dev_scale; /* optional device scalar */
+  int32_t accumulate;
+  void* workspace;
+  int64_t workspace_bytes;
+} mcq_wgrad_params;
+int64_t mcq_conv_wgrad_workspace_bytes(const mcq_wgrad_params* p);
+int mcq_conv_wgrad(const mcq_wgrad_params* p, mcq_stream_t stream);
+
 int mcq_version(void);            /* ABI version */
 /* Tuning / A-B knobs (kernel selection, grid caps, profiling aids -- the table at the top of csrc/mcq_api.cu).  They are
  * explicit process-wide settings with fixed defaults: nothing on the launch path reads the environment.

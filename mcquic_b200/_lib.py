@@ -28,6 +28,17 @@ class ConvParams(_c.Structure):
         ("ev_start", _c.c_void_p), ("ev_stop", _c.c_void_p),
         ("gn_partials", _c.c_void_p), ("gn_groups", _c.c_int32),
         ("out_u8", _c.c_void_p),
+        ("dev_scale", _c.c_void_p),
+    ]
+
+
+class WgradParams(_c.Structure):
+    """mirror of `mcq_wgrad_params` (include/mcquic_b200.h)"""
+    _fields_ = [
+        ("x_hi", _c.c_void_p), ("n", _c.c_int32), ("hin", _c.c_int32), ("win", _c.c_int32), ("cin", _c.c_int32),
+        ("dy_hi", _c.c_void_p), ("cout", _c.c_int32), ("ksize", _c.c_int32), ("stride", _c.c_int32),
+        ("dw", _c.c_void_p), ("scale", _c.c_float), ("dev_scale", _c.c_void_p), ("accumulate", _c.c_int32),
+        ("workspace", _c.c_void_p), ("workspace_bytes", _c.c_int64),
     ]
 
 
@@ -59,7 +70,9 @@ SYMBOLS = {
     "mcq_conv_gn_layout": (_c.c_int, [_c.POINTER(ConvParams), _c.POINTER(_i32), _c.POINTER(_i32)]),
     "mcq_groupnorm_apply": (_c.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _p, _p, _p, _i32, _p]),
     "mcq_add_scaled": (_c.c_int, [_p, _p, _f, _i64, _p, _p, _p, _i32, _p]),
-    "mcq_split_planes": (_c.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "mcq_split_planes": (_c.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
+    "mcq_conv_wgrad_workspace_bytes": (_i64, [_c.POINTER(WgradParams)]),
+    "mcq_conv_wgrad": (_c.c_int, [_c.POINTER(WgradParams), _p]),
     "mcq_nchw_to_nhwc": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _i32, _p]),
     "mcq_nhwc_to_nchw": (_c.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "mcq_error_string": (_c.c_char_p, [_c.c_int]),

@@ -36,6 +36,7 @@ struct ConvArgs {
   __half* o1_lo;
   float w_scale;
   float res1_scale;
+  const float* dev_scale;        // optional device scalar multiplied into w_scale (loss-scale removal of the backward convs)
   int n, hin, win, cin;
   int hout, wout;  // conv output grid (before any pixel shuffle)
   int cout, cout_pad, ksize, stride, ktotal;
@@ -59,6 +60,10 @@ struct ConvArgs {
   // per-tap TMA coordinate offsets in the 5-D view of A (see conv_tc.cuh)
   int tap_c[9], tap_dx[9], tap_py[9], tap_dy[9];
 };
+
+__device__ __forceinline__ float effective_w_scale(const ConvArgs& p) {
+  return p.dev_scale ? p.w_scale * __ldg(p.dev_scale) : p.w_scale;
+}
 
 // Activation math.  Both variants use the SFU (ex2.approx, rcp.approx); the exact variant adds one Newton step to the
 // reciprocal so that sigmoid/SiLU carry <= ~2 ulp error (the exponential's 2^-22), i.e. fp32-grade like the rest of

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(const ConvArgs 
     const int n = (int)(t / p.hout);
     float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] * p.w_scale;
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] * effective_w_scale(p);
     epilogue_store<4>(p, n, oy, ox, n0 + tx * 4, v);
   }
 }

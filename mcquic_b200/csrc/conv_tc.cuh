@@ -197,7 +197,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // pix(row, n, oy, ox) -> valid maps a tile row to its output pixel.
 template <int PASSES, bool GN = false, class PixFn>
 __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, int bn, int ct, int cg, int q, int lane,
-                                           uint32_t stage, PixFn pix, const float* bias_src) {
+                                           uint32_t stage, PixFn pix, const float* bias_src, const float wscale) {
   int n_[2], oy_[2], ox_[2];
   bool ok_[2];
 #pragma unroll
@@ -228,7 +228,7 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
           const int col = ct * bn + col0 + j;
           float v = __uint_as_float(r[j]);
           if (PASSES == 3) v = fmaf(__uint_as_float(l[j]), kLoInv, v);
-          v *= p.w_scale;
+          v *= wscale;
           if (col < p.cout) {
             const float dist = (x2 + p.bias[col]) - 2.0f * v;
             if (dist < best) { best = dist; best_k = col; }
@@ -291,7 +291,7 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
           float b[16];
           load_f32v<16>(bias_src, c0, b);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], p.w_scale, b[j]);
+          for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], wscale, b[j]);
         }
         if (p.mode == MCQ_EPI_LINEAR) {
           if (src1) {
@@ -429,7 +429,7 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
                        : "memory");
         }
         if (ok_[it] && !p.debug_skip_store)
-          epilogue_store<8, PASSES == 1>(p, n_[it], oy_[it], ox_[it], ct * bn + col0 + col8, vv, bias_src, p.w_scale);
+          epilogue_store<8, PASSES == 1>(p, n_[it], oy_[it], ox_[it], ct * bn + col0 + col8, vv, bias_src, wscale);
       }
       __syncwarp();
     }
@@ -645,6 +645,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       };
     };
     int it = 0;
+    const float wscale = effective_w_scale(p);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int ct;
       auto pix = tile_pix(t, ct);
@@ -654,7 +655,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(tfull_bar(buf), use & 1u, 4, p.wait_sleep_ns);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias);
+      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, wscale);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));

@@ -20,6 +20,7 @@
 #include "vq.cuh"
 #include "vq_fused.cuh"
 #include "stem_tc.cuh"
+#include "conv_wgrad.cuh"
 
 using namespace mcq;
 
@@ -211,6 +212,7 @@ int fill_args(const mcq_conv_params* p, ConvArgs& a) {
   a.o0_hi = (__half*)p->out0_hi; a.o0_lo = (__half*)p->out0_lo;
   a.o1_hi = (__half*)p->out1_hi; a.o1_lo = (__half*)p->out1_lo;
   a.w_scale = p->w_scale; a.res1_scale = p->res1_scale;
+  a.dev_scale = p->dev_scale;
   a.n = p->n; a.hin = p->hin; a.win = p->win; a.cin = p->cin;
   a.hout = p->hin / p->stride; a.wout = p->win / p->stride;
   a.cout = p->cout; a.cout_pad = p->cout_pad; a.ksize = p->ksize; a.stride = p->stride;
@@ -785,7 +787,7 @@ int mcq_stem_conv_tc(const void* x, int32_t x_is_u8, int32_t n, int32_t h, int32
   s.h = h; s.w = w; s.pad_top = pad_top; s.pad_left = pad_left; s.hp = hp; s.wp = wp; s.cout_pad = cout_pad;
   const long long total_pix = (long long)n * a.hout * a.wout;
   const long long tiles = (total_pix + STC_BM - 1) / STC_BM;
-  const size_t smem = 1024 + 2 * STC_A_BYTES + 16384 + 128 + (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 * 4 + 64;
+  const size_t smem = 1024 + 2 * STC_A_BYTES + 16384 + 128 + (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 * 4 + 256 * 4 + 64;
   cudaError_t e = ensure_dyn_smem<KTag<800>>(stem_tc_kernel, smem);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};
@@ -1076,11 +1078,12 @@ int mcq_add_scaled(const float* x, const float* y, float alpha, int64_t count, f
   return cuda_status();
 }
 
-int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, mcq_stream_t stream) {
+int mcq_split_planes(const float* x, int64_t count, int32_t act, void* out_hi, void* out_lo, const float* dev_scale,
+                     mcq_stream_t stream) {
   MCQ_CHECK_ARG(x && out_hi && count > 0 && count % 4 == 0);
   const long long c4 = count / 4;
   split_planes_kernel<<<(unsigned)((c4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, c4, act, (__half*)out_hi,
-                                                                                      (__half*)out_lo);
+                                                                                      (__half*)out_lo, dev_scale);
   g_launches++;
   return cuda_status();
 }
@@ -1102,6 +1105,82 @@ int mcq_nhwc_to_nchw(const float* x, int32_t n, int32_t c, int32_t h, int32_t w,
   MCQ_CHECK_ARG(x && out && n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535);
   dim3 grid((unsigned)((h * w + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
   nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, c, h * w, out);
+  g_launches++;
+  return cuda_status();
+}
+
+// ---- weight gradient (conv_wgrad.cuh)
+namespace {
+int plan_wgrad(const mcq_wgrad_params* p, WgradArgs& w) {
+  MCQ_CHECK_ARG(p && p->n > 0 && p->hin > 0 && p->win > 0 && p->cin > 0 && p->cout > 0);
+  MCQ_CHECK_ARG(p->ksize == 1 || p->ksize == 3);
+  MCQ_CHECK_ARG(p->stride == 1 || p->stride == 2);
+  if (p->cin % 8 != 0 || p->cout % 8 != 0) return MCQ_ERR_UNSUPPORTED;
+  if (p->stride == 2 && (p->cin % TC_BK != 0 || p->hin % 2 != 0 || p->win % 2 != 0)) return MCQ_ERR_UNSUPPORTED;
+  std::memset(&w, 0, sizeof(w));
+  ConvArgs g;
+  std::memset(&g, 0, sizeof(g));
+  g.n = p->n; g.hin = p->hin; g.win = p->win; g.cin = p->cin;
+  g.hout = p->hin / p->stride; g.wout = p->win / p->stride;
+  g.ksize = p->ksize; g.stride = p->stride;
+  fill_mtile(g);
+  fill_taps(g);
+  w.n = p->n; w.hout = g.hout; w.wout = g.wout; w.cin = p->cin; w.cout = p->cout;
+  w.ksize = p->ksize; w.ntaps = p->ksize * p->ksize;
+  w.tw = g.tw; w.th = g.th; w.tn = g.tn; w.tiles_x = g.tiles_x; w.tiles_y = g.tiles_y; w.tiles_n = g.tiles_n;
+  w.tiles_ci = (p->cin + 127) / 128; w.tiles_co = (p->cout + 127) / 128;
+  w.taps_per_group = w.ntaps < WG_MAX_TAPS ? w.ntaps : WG_MAX_TAPS;
+  w.tap_groups = (w.ntaps + w.taps_per_group - 1) / w.taps_per_group;
+  const int items = w.tiles_ci * w.tiles_co * w.tap_groups;
+  const int tiles_pix = w.tiles_x * w.tiles_y * w.tiles_n;
+  int splits = num_sms() / items;
+  if (splits < 1) splits = 1;
+  if (splits > tiles_pix) splits = tiles_pix;
+  w.splits = splits;
+  for (int t = 0; t < 9; ++t) { w.tap_c[t] = g.tap_c[t]; w.tap_dx[t] = g.tap_dx[t]; w.tap_py[t] = g.tap_py[t]; w.tap_dy[t] = g.tap_dy[t]; }
+  return 0;
+}
+}  // namespace
+
+int64_t mcq_conv_wgrad_workspace_bytes(const mcq_wgrad_params* p) {
+  WgradArgs w;
+  if (plan_wgrad(p, w)) return -1;
+  return (int64_t)w.tiles_ci * w.tiles_co * w.tap_groups * w.splits * WG_MAX_TAPS * 128 * 128 * 4;
+}
+
+int mcq_conv_wgrad(const mcq_wgrad_params* p, mcq_stream_t stream) {
+  WgradArgs w;
+  int rc = plan_wgrad(p, w);
+  if (rc) return rc;
+  MCQ_CHECK_ARG(p->x_hi && p->dy_hi && p->dw && p->workspace && ((uintptr_t)p->workspace & 255) == 0);
+  const int64_t need = mcq_conv_wgrad_workspace_bytes(p);
+  MCQ_CHECK_ARG(p->workspace_bytes >= need);
+  w.partial = (float*)p->workspace;
+  CUtensorMap tmDY, tmX;
+  rc = encode_act_map(&tmDY, p->dy_hi, p->n, w.hout, w.wout, p->cout, 1, w.tw, w.th, w.tn);
+  if (rc) return rc;
+  rc = encode_act_map(&tmX, p->x_hi, p->n, p->hin, p->win, p->cin, p->stride, w.tw, w.th, w.tn);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)WG_NA * WG_A_BYTES + (size_t)WG_NB * WG_B_BYTES + 8 * (2 * WG_NA + 2 * WG_NB + 2) + 64;
+  cudaError_t e = ensure_dyn_smem<KTag<900>>(conv_wgrad_kernel, smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(w.tiles_ci * w.tiles_co * w.tap_groups * w.splits));
+  cfg.blockDim = dim3(WG_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = opt("pdl") ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tmDY, tmX, w);
+  g_launches++;
+  if (e != cudaSuccess) return (int)e;
+  const long long total = (long long)p->cout * p->cin * w.ntaps;
+  wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.partial, p->dw, w, p->scale, p->dev_scale,
+                                                                        p->accumulate);
   g_launches++;
   return cuda_status();
 }

@@ -84,11 +84,17 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const StemArgs 
   }
 }
 
-__global__ void split_planes_kernel(const float* x, long long count4, int act, __half* hi, __half* lo) {
+__global__ void split_planes_kernel(const float* x, long long count4, int act, __half* hi, __half* lo,
+                                    const float* dev_scale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count4) return;
   float y[4];
   load_f32v<4>(x, (size_t)i * 4, y);
+  if (dev_scale) {
+    const float s = __ldg(dev_scale);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] *= s;
+  }
   store_planes<4>(hi, lo, (size_t)i * 4, y, act);
 }
 

@@ -21,7 +21,8 @@
 
 namespace mcq {
 
-constexpr int STC_PROD_WARPS = 2;                                   // 64 producer threads, two rows each
+constexpr int STC_PROD_WARPS = 2;                                   // 64 producer threads, two tile rows each (19 warps
+                                                                    // -> 96 registers per thread; 21 warps would get 80)
 constexpr int STC_FIRST_EPI = 1 + STC_PROD_WARPS;                  // warp 0 = TMEM owner + MMA issuer
 constexpr int STC_THREADS = 32 * (STC_FIRST_EPI + TC_EPI_WARPS);   // 608
 constexpr int STC_BM = 128;
@@ -61,7 +62,10 @@ __global__ void __launch_bounds__(STC_THREADS, 1) stem_tc_kernel(const ConvArgs 
   const uint32_t epi_base = bar_base + 128u;                                          // 16 x 2 KB drain staging
   float* bias_smem = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + TC_EPI_WARPS * TC_EPI_STAGE_BYTES);
 
+  float* u8_lut = bias_smem + 128;                                                    // 256 floats
   for (int i = threadIdx.x; i < p.cout; i += STC_THREADS) bias_smem[i] = p.bias[i];
+  if (s.x_u8)
+    for (int i = threadIdx.x; i < 256; i += STC_THREADS) u8_lut[i] = u8_to_unit((unsigned char)i);
   // weights -> shared memory in the swizzled K-major layout (16 B chunk j of row r at chunk j ^ (r & 7))
   for (int i = threadIdx.x; i < bn * 8; i += STC_THREADS) {
     const int r = i >> 3, j = i & 7;
@@ -128,47 +132,69 @@ __global__ void __launch_bounds__(STC_THREADS, 1) stem_tc_kernel(const ConvArgs 
       const int ab = i & 1;
       mbar_wait_sleep(a_empty(ab), (((uint32_t)(i >> 1)) & 1u) ^ 1u, 43, 200);
       const uint32_t abuf = a_base + (uint32_t)ab * STC_A_BYTES;
-#pragma unroll 1
-      for (int rr = 0; rr < STC_BM / (STC_PROD_WARPS * 32); ++rr) {
+      // both rows of this thread: all 54 tap loads are issued before any is consumed (one memory round trip per tile
+      // instead of two -- the producers' latency, not the tensor pipe, paces this kernel's mainloop)
+      float v[2][27];
+      bool ok[2][9];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
         const int row = rr * (STC_PROD_WARPS * 32) + ptid;
         const long long f = (long long)t * STC_BM + row;
-        float v[27];
-        if (f < total_pix) {
-          const int n = (int)(f / hw_out);
-          const int rem = (int)(f - (long long)n * hw_out);
-          const int oy = rem / p.wout, ox = rem - oy * p.wout;
-          int sy[3], sx[3];
-          bool vy[3], vx[3];
+        const bool live = f < total_pix;
+        const long long fc = live ? f : 0;
+        const int n = (int)(fc / hw_out);
+        const int rem = (int)(fc - (long long)n * hw_out);
+        const int oy = rem / p.wout, ox = rem - oy * p.wout;
+        // the 3 source rows / columns of this pixel's taps: always in-range indices (the loads are unconditional --
+        // predicated loads were serialised by the compiler: 27 dependent L2 round trips per row); zero padding is
+        // applied to the loaded values
+        int sy[3], sx[3];
+        bool vy[3], vx[3];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const int Y = 2 * oy + k - 1, X = 2 * ox + k - 1;     // coordinates in the padded image (zeros outside it)
-            vy[k] = Y >= 0 && Y < s.hp;
-            vx[k] = X >= 0 && X < s.wp;
-            sy[k] = stem_reflect(Y - s.pad_top, s.h);
-            sx[k] = stem_reflect(X - s.pad_left, s.w);
-          }
-          const size_t img = (size_t)n * 3 * s.h * s.w;
+        for (int k = 0; k < 3; ++k) {
+          const int Y = 2 * oy + k - 1, X = 2 * ox + k - 1;       // coordinates in the padded image (zeros outside it)
+          vy[k] = live && Y >= 0 && Y < s.hp;
+          vx[k] = X >= 0 && X < s.wp;
+          sy[k] = min(max(stem_reflect(Y - s.pad_top, s.h), 0), s.h - 1);
+          sx[k] = min(max(stem_reflect(X - s.pad_left, s.w), 0), s.w - 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ok[rr][k] = vy[k / 3] && vx[k % 3];
+        const size_t img = (size_t)n * 3 * s.h * s.w;
+        if (s.x_u8) {
 #pragma unroll
           for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                float val = 0.f;
-                if (vy[r] && vx[c]) {
-                  const size_t idx = img + ((size_t)ci * s.h + sy[r]) * s.w + sx[c];
-                  val = s.x_u8 ? u8_to_unit(s.x_u8[idx]) : s.x_f32[idx];
-                }
-                v[ci * 9 + r * 3 + c] = val;
-              }
+              for (int c = 0; c < 3; ++c)
+                v[rr][ci * 9 + r * 3 + c] =
+                    __uint_as_float((uint32_t)__ldg(s.x_u8 + img + ((size_t)ci * s.h + sy[r]) * s.w + sx[c]));
         } else {
 #pragma unroll
-          for (int k = 0; k < 27; ++k) v[k] = 0.f;
+          for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                v[rr][ci * 9 + r * 3 + c] = __ldg(s.x_f32 + img + ((size_t)ci * s.h + sy[r]) * s.w + sx[c]);
         }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = rr * (STC_PROD_WARPS * 32) + ptid;
+        if (s.x_u8) {
+          // uint8 -> [-1, 1] through a 256-entry table of the reference's transform (filled with the same fp32 operations)
+#pragma unroll
+          for (int k = 0; k < 27; ++k) v[rr][k] = u8_lut[__float_as_uint(v[rr][k])];
+        }
+#pragma unroll
+        for (int k = 0; k < 27; ++k)
+          if (!ok[rr][k % 9]) v[rr][k] = 0.f;
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int e = 0; e < 13; ++e) split_f32x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-        split_f32x2(v[26], 0.f, hi[13], lo[13]);
+        for (int e = 0; e < 13; ++e) split_f32x2(v[rr][2 * e], v[rr][2 * e + 1], hi[e], lo[e]);
+        split_f32x2(v[rr][26], 0.f, hi[13], lo[13]);
         hi[14] = hi[15] = lo[14] = lo[15] = 0u;
         const uint32_t rbase = abuf + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
         const uint32_t sw = (uint32_t)(row & 7);
@@ -206,7 +232,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) stem_tc_kernel(const ConvArgs 
       mbar_wait(tfull(ab), ((uint32_t)(i >> 1)) & 1u, 44);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
-      drain_tile<3>(p, t_acc, bn, 0, cg, q, lane, stage, pix, bias_smem);
+      drain_tile<3>(p, t_acc, bn, 0, cg, q, lane, stage, pix, bias_smem, effective_w_scale(p));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(ab));

@@ -351,8 +351,9 @@ class Engine:
     def conv(self, pc: PackedConv, a: Planes, x: Act, want: Set[str], *, mode: int = _lib.EPI_LINEAR,
              res1: Optional[torch.Tensor] = None, res1_scale: float = 1.0, res2: Optional[torch.Tensor] = None,
              aux: Optional[torch.Tensor] = None, into: Optional[Act] = None, gn_groups: int = 0,
-             a_scale: float = 1.0) -> Act:
+             a_scale: float = 1.0, dev_scale: Optional[torch.Tensor] = None) -> Act:
         """a_scale: power-of-two factor the A planes carry (x^2 planes: _lib.SQUARE_SCALE); undone through w_scale.
+        dev_scale: optional device scalar (fp32 [1]) the epilogue multiplies into w_scale (training-step dgrad).
         gn_groups > 0: a nn.GroupNorm(gn_groups, cout) follows; where the kernel can (mcq_conv_gn_layout) its
         epilogue also writes the per-row-block (sum, sum^2) partials of the fp32 output -> `out.gn`.
         into: write the outputs into these caller-owned tensors (same shapes / representations as `want`) instead
@@ -370,10 +371,11 @@ class Engine:
         p.w_hi, p.w_lo = _ptr(pc.w_hi), _ptr(pc.w_lo)
         p.cout, p.cout_pad, p.ksize, p.stride = pc.cout, pc.cout_pad, pc.ksize, pc.stride
         p.w_scale = pc.w_scale / a_scale
+        p.dev_scale = _ptr(dev_scale)
         p.bias = _ptr(pc.bias)
         p.mode, p.store = mode, pc.store
         p.res1, p.res1_scale, p.res2, p.aux = _ptr(res1), res1_scale, _ptr(res2), _ptr(aux)
-        keep = [a, res1, res2, aux]
+        keep = [a, res1, res2, aux, dev_scale]
         def given(t, shape, dtype):
             if t is None or tuple(t.shape) != shape or t.dtype != dtype or not t.is_contiguous():
                 raise RuntimeError("mcquic_b200: `into` buffers do not match the convolution's outputs")

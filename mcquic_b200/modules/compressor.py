@@ -79,6 +79,12 @@ class BaseCompressor(nn.Module):
         # (decode) full-resolution layers so that the PCIe copies overlap the convolutions
         self._pipes = _ShapeCache()
         self._copy_stream = None
+        # L2-resident sub-batches: the full-resolution part of the analysis / synthesis transform is run per slice of this
+        # many images (0 = whole batch at once), so that a layer's output is still in the 126 MB L2 when the next layer of
+        # the same slice reads it (at batch 64 one 64x64x128 activation is 134 MB fp32 + 67 MB planes: every layer streams
+        # through HBM).  Results are bit-identical (images are independent).
+        self.encode_slice = 0
+        self.decode_slice = 32      # measured at batch 64 (tools/exp_slices.py): decode 5.51 -> 5.37 ms; encode loses
 
     @property
     def QuantizationParameter(self) -> str:
@@ -133,11 +139,19 @@ class BaseCompressor(nn.Module):
                                "streams in); there is no CPU fallback")
 
     @staticmethod
-    def host_slices(n: int, small_first: bool) -> List[Tuple[int, int]]:
+    def host_slices(n: int, small_first: bool, itemsize: int = 4) -> List[Tuple[int, int]]:
         """Batch slices [(n0, n1), ...] a host batch of n images is streamed in.  Up to four slices of >= 8 images keep
         the per-slice layers efficient (measured: eight equal slices cost in extra dependent launches what the shorter
         exposed copy saves); the slice whose PCIe copy cannot overlap anything -- the first one going in, the last one
         coming out -- is split once more into a quarter and the rest, so only ~n/16 images' worth of copy stays exposed."""
+        if itemsize == 1:
+            # uint8 images: a quarter of the bytes -- the copy of half a batch (6 MB at 64 x 3 x 256 x 256, ~0.12 ms) is all
+            # that stays exposed with two slices, and every further slice costs more in launches / tile quantisation of the
+            # per-slice layers than it hides (measured: the 5-slice schedule left e2e 1.0 ms above the device-resident step
+            # even with the bytes cut by 4)
+            if n % 2 == 0 and n // 2 >= 8:
+                return [(0, n // 2), (n // 2, n)]
+            return [(0, n)]
         ch = next((c for c in (4, 2) if n % c == 0 and n // c >= 8), 1)
         nc = n // ch
         bounds = [(c * nc, (c + 1) * nc) for c in range(ch)]
@@ -211,8 +225,19 @@ class BaseCompressor(nn.Module):
         eng = self.engine
         eng.passes = self.encode_passes
         n, _, h, w = x.shape
-        y0 = eng.stem(self._encoder[0], x, aligned_pad_amounts(h, w), eng.needs_of(self._encoder[1]))
-        y = eng.run_seq(list(self._encoder)[1:], y0, self._quantizer.first_needs(eng))
+        sl = self.encode_slice
+        if sl and n > sl and isinstance(self._encoder[-1], ResidualBlock):
+            _, _, hp, wp = aligned_pad_amounts(h, w)
+            y = eng.alloc_act(n, hp // 8, wp // 8, self._encoder[0].out_channels, self._quantizer.first_needs(eng), x.device)
+            mods = list(self._encoder)
+            for n0 in range(0, n, sl):
+                n1 = min(n, n0 + sl)
+                y0 = eng.stem(mods[0], x[n0:n1], aligned_pad_amounts(h, w), eng.needs_of(mods[1]))
+                t = eng.run_seq(mods[1:-1], y0, eng.needs_of(mods[-1]))
+                eng.run(mods[-1], t, self._quantizer.first_needs(eng), into=y.batch_slice(n0, n1))
+        else:
+            y0 = eng.stem(self._encoder[0], x, aligned_pad_amounts(h, w), eng.needs_of(self._encoder[1]))
+            y = eng.run_seq(list(self._encoder)[1:], y0, self._quantizer.first_needs(eng))
         codes = self._quantizer.encode_act(eng, y, hist)
         eng.flush()
         return codes
@@ -221,7 +246,19 @@ class BaseCompressor(nn.Module):
         eng = self.engine
         eng.passes = self.decode_passes
         yHat = self._quantizer.decode_act(eng, codes, eng.needs_of(self._decoder[0]), status)
-        out = eng.run_seq(list(self._decoder), yHat, set()).f32
+        sl = self.decode_slice
+        n = yHat.n
+        if sl and n > sl:
+            mods = list(self._decoder)
+            y0 = eng.run(mods[0], yHat, eng.needs_of(mods[1]))
+            out = torch.empty((n, 3, yHat.h * 8, yHat.w * 8), dtype=torch.float32, device=yHat.f32.device
+                              if yHat.f32 is not None else codes[0].device)
+            for n0 in range(0, n, sl):
+                n1 = min(n, n0 + sl)
+                t = eng.run_seq(mods[1:-1], y0.batch_slice(n0, n1), eng.needs_of(mods[-1]))
+                eng.run(mods[-1], t, set(), into=Act(n1 - n0, out.shape[2], out.shape[3], 3, f32=out[n0:n1]))
+        else:
+            out = eng.run_seq(list(self._decoder), yHat, set()).f32
         eng.flush()
         return out
 
@@ -293,7 +330,7 @@ class BaseCompressor(nn.Module):
         """x: pinned host batch.  Chunk c is copied on the copy stream while chunk c-1 runs stem + first block."""
         dev = self._device()
         n, _, h, w = x.shape
-        bounds = self.host_slices(n, small_first=True)
+        bounds = self.host_slices(n, small_first=True, itemsize=x.element_size())
         key = ("enc", tuple(x.shape), x.dtype, self.encode_passes, dev)
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
@@ -347,7 +384,7 @@ class BaseCompressor(nn.Module):
         """out: pinned host batch.  The pixels of chunk c travel to the host while chunk c+1 runs the last layers."""
         dev = codes[0].device
         n = codes[0].shape[0]
-        bounds = self.host_slices(n, small_first=False)
+        bounds = self.host_slices(n, small_first=False, itemsize=out.element_size())
         key = ("dec", tuple(tuple(c.shape) for c in codes), tuple(out.shape), out.dtype, self.decode_passes, dev)
         pipe = self._pipes.get(key)
         with torch.cuda.device(dev):
@@ -414,8 +451,8 @@ class BaseCompressor(nn.Module):
             sh.zero_()
             return self._encode_eager(sx, sh)
 
-        graph, (sx, sh), codes, launches = self._graph(("enc", tuple(x.shape), x.dtype, self.encode_passes, x.device),
-                                                       make_static, body)
+        graph, (sx, sh), codes, launches = self._graph(("enc", tuple(x.shape), x.dtype, self.encode_passes, x.device,
+                                                        self.encode_slice), make_static, body)
         sx.copy_(x)
         graph.replay()
         self.graph_launches += launches
@@ -458,7 +495,7 @@ class BaseCompressor(nn.Module):
                 st.zero_()
                 return self._decode_eager(sc, st)
 
-            key = ("dec", tuple(tuple(c.shape) for c in codes), self.decode_passes, dev)
+            key = ("dec", tuple(tuple(c.shape) for c in codes), self.decode_passes, dev, self.decode_slice)
             graph, (sc, status), sout, launches = self._graph(key, make_static, body)
             for dst, src in zip(sc, codes):
                 dst.copy_(src)

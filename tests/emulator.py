@@ -252,7 +252,7 @@ class EmulatedLib:
         self.launches += 1
         return 0
 
-    def mcq_split_planes(self, x, count, act, out_hi, out_lo, stream):
+    def mcq_split_planes(self, x, count, act, out_hi, out_lo, dev_scale, stream):
         y = torch.from_numpy(_arr(x.value, (count,), np.float32).copy())
         _store_planes(out_hi.value, out_lo.value if out_lo is not None and out_lo.value else 0, (count,), y, act)
         self.launches += 1

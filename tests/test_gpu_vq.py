@@ -15,6 +15,10 @@ def _strict(what, shape, codes, ref, x, cb):
     """bit-exact indices: 0 flips, reported to the parity log (printed at the end of the run)"""
     mism = codes.cpu() != ref
     flips = int(mism.sum())
+    if cb.shape[1] < 2:                      # a single codeword: no second-best distance
+        log_parity(f"oracle vq {what} {shape}", flips, ref.numel())
+        assert flips == 0
+        return
     marg = O.vq_margin(x, cb)
     log_parity(f"oracle vq {what} {shape}", flips, ref.numel(), marg[mism].tolist(), float(marg.min()))
     assert flips == 0, (flips, marg[mism].tolist()[:8])
