@@ -828,7 +828,8 @@ int mcq_vq_assign(const float* x, const float* codebook, const float* c2, int64_
 
 int mcq_vq_fused_supported(int32_t h, int32_t w, int32_t k, int32_t d) {
   const int hw = h * w;
-  return (d == 32 || d == 64) && k > 0 && k % VQF_BN == 0 && hw > 0 && (hw % 32 == 0 || 32 % hw == 0);
+  return (d == 32 || d == 64 || (d == 128 && opt("vq128_fused"))) && k > 0 && k % VQF_BN == 0 && hw > 0 &&
+         (hw % 32 == 0 || 32 % hw == 0);
 }
 
 int mcq_vq_assign_fused(const float* x, const void* cb_lohi, float cb_scale, const float* c2, int64_t* codes,
@@ -853,20 +854,25 @@ int mcq_vq_assign_fused(const float* x, const void* cb_lohi, float cb_scale, con
   a.inv_sqrt_k = 1.0f / sqrtf((float)k);
   const int kch = 2 * d / TC_BK;
   const size_t op_bytes = (size_t)kch * VQF_CHUNK_BYTES;
+  // d = 128: 64 KB operand rows -> one latent buffer, codebook streamed in half rows (32 KB stages), see vq_fused.cuh
+  const int na = d == 128 ? 1 : 2, halves = d == 128 ? 2 : 1;
+  const size_t bst_bytes = op_bytes / halves;
   const size_t smem_max = 227 * 1024;
   int nst = 2, nb = 0;
   size_t fixed = 0;
-  for (; nst >= 1; --nst) {   // prefer double-buffered logits staging; d=64 only has room for one buffer per warp
+  for (; nst >= 1; --nst) {   // prefer double-buffered logits staging; d >= 64 only has room for one buffer per warp
     const size_t st_bytes = logits ? (size_t)VQF_EPI_WARPS * nst * VQF_STAGE_BYTES : 0;
-    fixed = 1024 + 2 * op_bytes + st_bytes + 2 * VQF_BM * 4 + 6 * VQF_BM * 8 + VQF_C2_SLOTS * VQF_BN * 4 + 64;
-    nb = fixed + 8 * 16 < smem_max ? (int)((smem_max - fixed - 8 * 16) / op_bytes) : 0;
+    fixed = 1024 + na * op_bytes + st_bytes + 2 * VQF_BM * 4 + 6 * VQF_BM * 8 + VQF_C2_SLOTS * VQF_BN * 4 + 64;
+    nb = fixed + 8 * 16 < smem_max ? (int)((smem_max - fixed - 8 * 16) / bst_bytes) : 0;
     if (nb >= 2) break;
   }
   if (nb < 2) return MCQ_ERR_UNSUPPORTED;
   if (nb > 4) nb = 4;
   a.nb = nb;
   a.nst = nst;
-  const size_t smem = fixed + nb * op_bytes + 8 * (8 + 2 * nb);
+  a.na = na;
+  a.halves = halves;
+  const size_t smem = fixed + nb * bst_bytes + 8 * (8 + 2 * nb);
 
   CUtensorMap tmB, tmL;
   {

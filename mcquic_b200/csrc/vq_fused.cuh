@@ -18,7 +18,13 @@
 //   |c|^2   = 512 B per chunk, bulk-copied (cp.async.bulk) into an 8-slot shared-memory ring with the codebook stage
 //   finish  = the four column quarters are merged through shared memory; int64 codes and the histogram are written.
 //
-// Supported: d in {32, 64}, k % 128 == 0, (h*w) % 32 == 0 or 32 % (h*w) == 0; everything else -> vq_assign_kernel.
+// d = 128 (qp = 1: one codebook over all 128 channels): an operand row is 256 fp16 = four 64-element chunks, 64 KB per
+// 128-row buffer -- two A buffers and two such codebook stages would not fit.  There the latents are single-buffered
+// (a tile lasts k / 128 = 4..64 chunks, the refill bubble is small) and the codebook is streamed in HALF rows: stage
+// 2c holds the c_lo halves of chunk c (K-steps [0, d/16): the x_hi.c_lo part of D_lo), stage 2c+1 the c_hi halves
+// (D_hh = x_hi.c_hi and the x_lo.c_hi part of D_lo) -- 32 KB stages like d = 64's.
+//
+// Supported: d in {32, 64, 128}, k % 128 == 0, (h*w) % 32 == 0 or 32 % (h*w) == 0; everything else -> vq_assign_kernel.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -49,6 +55,8 @@ struct VqFusedArgs {
   float inv_sqrt_k;
   int hist_on;
   int nst;                   // logits staging buffers per drain warp (2, or 1 when shared memory is short)
+  int na;                    // latent (A) buffers: 2, or 1 for d = 128
+  int halves;                // codebook stages per 128-codeword chunk: 1, or 2 (half rows) for d = 128
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -96,10 +104,13 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.d, nb = a.nb;
   const int kch = (2 * d) / TC_BK;                       // 64-element K chunks per operand row (1 or 2)
-  const uint32_t op_bytes = (uint32_t)kch * VQF_CHUNK_BYTES;   // one A buffer == one B stage
+  const uint32_t op_bytes = (uint32_t)kch * VQF_CHUNK_BYTES;   // one A buffer (= one B stage when halves == 1)
+  const int na = a.na, halves = a.halves;
+  const int kch_st = kch / halves;                             // 64-element chunks per codebook stage
+  const uint32_t bst_bytes = op_bytes / (uint32_t)halves;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + 2u * op_bytes;
-  const uint32_t st_base = b_base + (uint32_t)nb * op_bytes;                       // logits staging (1024-aligned)
+  const uint32_t b_base = a_base + (uint32_t)na * op_bytes;
+  const uint32_t st_base = b_base + (uint32_t)nb * bst_bytes;                      // logits staging (1024-aligned)
   const uint32_t st_bytes = LOGITS ? (uint32_t)(VQF_EPI_WARPS * a.nst * VQF_STAGE_BYTES) : 0u;
   const uint32_t x2_off = (st_base - smem_base) + st_bytes;                        // float [2][128]
   const uint32_t red_off = x2_off + 2u * VQF_BM * 4u;                              // u64 [2][3][128]
@@ -149,53 +160,71 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
 
   if (warp == 0) {
     // ===================== codebook stream (TMA) =====================
-    int gc = 0;
+    int gc = 0, gs = 0;                                     // chunk / stage counters
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mi = t / a.tiles_p;
       for (int c = 0; c < chunks; ++c, ++gc) {
-        // |c_k|^2 of the chunk rides on the codebook stage's barrier but lives in its own ring: the drain warps read it
-        // after the MMA has released the stage.  Slot gc % 8 was last read by the drain of chunk gc - 8; this point is
-        // only reached after MMA(gc - nb) completed, hence after drain(gc - nb - 2) handed its accumulator back (its
-        // |c|^2 reads precede that hand-over), and nb + 2 <= 6 < 8.
-        const int s = gc % nb, cs = gc % VQF_C2_SLOTS;
-        mbar_wait_sleep(b_empty(s), (((uint32_t)(gc / nb)) & 1u) ^ 1u, 31, 200);
-        if (elect_one()) {
-          mbar_expect_tx(b_full(s), op_bytes + VQF_BN * 4u);
-          for (int kc = 0; kc < kch; ++kc)
-            tma_load_2d(&tmB, b_base + (uint32_t)s * op_bytes + (uint32_t)kc * VQF_CHUNK_BYTES, b_full(s), kc * TC_BK,
-                        mi * a.k + c * VQF_BN);
-          bulk_load_1d(c2_base + (uint32_t)cs * VQF_BN * 4u, a.c2 + (size_t)mi * a.k + c * VQF_BN, VQF_BN * 4u, b_full(s));
+        // |c_k|^2 of the chunk rides on the barrier of the chunk's first codebook stage but lives in its own ring: the
+        // drain warps read it after the MMA has released the stage.  Slot gc % 8 was last read by the drain of chunk
+        // gc - 8; this point is only reached after the MMAs of stage gs - nb completed (chunk gc - nb / halves at the
+        // latest), hence after drain(gc - nb - 2) handed its accumulator back (its |c|^2 reads precede that hand-over),
+        // and nb + 2 <= 6 < 8.
+        const int cs = gc % VQF_C2_SLOTS;
+        for (int hf = 0; hf < halves; ++hf, ++gs) {
+          const int s = gs % nb;
+          mbar_wait_sleep(b_empty(s), (((uint32_t)(gs / nb)) & 1u) ^ 1u, 31, 200);
+          if (elect_one()) {
+            mbar_expect_tx(b_full(s), bst_bytes + (hf == 0 ? VQF_BN * 4u : 0u));
+            for (int kc = 0; kc < kch_st; ++kc)
+              tma_load_2d(&tmB, b_base + (uint32_t)s * bst_bytes + (uint32_t)kc * VQF_CHUNK_BYTES, b_full(s),
+                          (hf * kch_st + kc) * TC_BK, mi * a.k + c * VQF_BN);
+            if (hf == 0)
+              bulk_load_1d(c2_base + (uint32_t)cs * VQF_BN * 4u, a.c2 + (size_t)mi * a.k + c * VQF_BN, VQF_BN * 4u,
+                           b_full(s));
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = (1u << 4) | ((uint32_t)(VQF_BN >> 3) << 17) | ((uint32_t)(VQF_BM >> 4) << 24);
     const int ks = d / 16;                                 // K-steps per half row
-    int gc = 0, i = 0;
+    int gc = 0, gs = 0, i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
-      const int ab = i & 1;
-      mbar_wait_sleep(a_full(ab), ((uint32_t)(i >> 1)) & 1u, 32, 100);
+      const int ab = i % na;
+      mbar_wait_sleep(a_full(ab), ((uint32_t)(i / na)) & 1u, 32, 100);
       const uint64_t a0 = make_sdesc(a_base + (uint32_t)ab * op_bytes);
       for (int c = 0; c < chunks; ++c, ++gc) {
-        const int s = gc % nb, buf = gc & 1;
+        const int buf = gc & 1;
         mbar_wait_sleep(tempty(buf), (((uint32_t)(gc >> 1)) & 1u) ^ 1u, 33, 60);
-        mbar_wait_sleep(b_full(s), ((uint32_t)(gc / nb)) & 1u, 34, 60);
-        tc_fence_after();
-        const uint64_t b0 = make_sdesc(b_base + (uint32_t)s * op_bytes);
         const uint32_t d_hh = tmem_base + (uint32_t)(buf * 2 * VQF_BN);
         const uint32_t d_lo = d_hh + (uint32_t)VQF_BN;
-        if (elect_one()) {
-          // K-step j of a row lives in chunk j/4 at +32 B * (j%4); descriptor addresses are in 16 B units
-          auto off = [](int j) { return (uint64_t)((j >> 2) * (VQF_CHUNK_BYTES >> 4) + (j & 3) * 2); };
-          for (int j = 0; j < ks; ++j) umma_f16(d_hh, a0 + off(j), b0 + off(ks + j), idesc, j > 0 ? 1u : 0u);
-          for (int j = 0; j < 2 * ks; ++j) umma_f16(d_lo, a0 + off(j), b0 + off(j), idesc, j > 0 ? 1u : 0u);
-          umma_commit(b_empty(s));
-          umma_commit(tfull(buf));
-          if (c == chunks - 1) umma_commit(a_empty(ab));
+        // K-step j of a row lives in chunk j/4 at +32 B * (j%4); descriptor addresses are in 16 B units
+        auto off = [](int j) { return (uint64_t)((j >> 2) * (VQF_CHUNK_BYTES >> 4) + (j & 3) * 2); };
+        for (int hf = 0; hf < halves; ++hf, ++gs) {
+          const int s = gs % nb;
+          mbar_wait_sleep(b_full(s), ((uint32_t)(gs / nb)) & 1u, 34, 60);
+          tc_fence_after();
+          const uint64_t b0 = make_sdesc(b_base + (uint32_t)s * bst_bytes);
+          if (elect_one()) {
+            if (halves == 1) {
+              for (int j = 0; j < ks; ++j) umma_f16(d_hh, a0 + off(j), b0 + off(ks + j), idesc, j > 0 ? 1u : 0u);
+              for (int j = 0; j < 2 * ks; ++j) umma_f16(d_lo, a0 + off(j), b0 + off(j), idesc, j > 0 ? 1u : 0u);
+            } else if (hf == 0) {       // stage = [c_lo] of the chunk: D_lo = x_hi . c_lo
+              for (int j = 0; j < ks; ++j) umma_f16(d_lo, a0 + off(j), b0 + off(j), idesc, j > 0 ? 1u : 0u);
+            } else {                    // stage = [c_hi]: D_hh = x_hi . c_hi, D_lo += x_lo . c_hi
+              for (int j = 0; j < ks; ++j) umma_f16(d_hh, a0 + off(j), b0 + off(j), idesc, j > 0 ? 1u : 0u);
+              for (int j = 0; j < ks; ++j) umma_f16(d_lo, a0 + off(ks + j), b0 + off(j), idesc, 1u);
+            }
+            umma_commit(b_empty(s));
+            if (hf == halves - 1) {
+              umma_commit(tfull(buf));
+              if (c == chunks - 1) umma_commit(a_empty(ab));
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (warp < VQF_FIRST_EPI) {
@@ -206,9 +235,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
     const int C = a.m * d;
     int i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
-      const int ab = i & 1;
+      const int ab = i % na;
       const int mi = t / a.tiles_p, p0 = (t - mi * a.tiles_p) * VQF_BM;
-      mbar_wait_sleep(a_empty(ab), (((uint32_t)(i >> 1)) & 1u) ^ 1u, 35, 1000);
+      mbar_wait_sleep(a_empty(ab), (((uint32_t)(i / na)) & 1u) ^ 1u, 35, 1000);
       const uint32_t abuf = a_base + (uint32_t)ab * op_bytes;
       for (int r0 = 0; r0 < VQF_BM; r0 += rows_per_pass) {
         const int row = r0 + ptid / g, j = ptid % g;
@@ -265,9 +294,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
     uint32_t gc = 0;
     int i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
-      const int ab = i & 1;
+      const int ab = i % na;
       const int mi = t / a.tiles_p, p0 = (t - mi * a.tiles_p) * VQF_BM;
-      mbar_wait(a_full(ab), ((uint32_t)(i >> 1)) & 1u, 36);
+      mbar_wait(a_full(ab), ((uint32_t)(i / na)) & 1u, 36);
       const float x2 = x2buf[ab * VQF_BM + row];
       __syncwarp();
       if (lane == 0) mbar_arrive(a_empty(ab));

@@ -545,15 +545,24 @@ class BaseCompressor(nn.Module):
         act = eng.from_nchw(yHat, eng.needs_of(self._decoder[0]))
         return eng.run_seq(list(self._decoder), act, set()).f32        # the final pixel-shuffle conv stores NCHW
 
-    @torch.no_grad()
     def forward(self, x: torch.Tensor):
-        """compressor.py:35-43, FORWARD VALUES ONLY: (xHat, yHat, codes, logits) of the training-time path (soft
-        quantizer: Gumbel sample with PyTorch's RNG, frequency EMA updated) -- no autograd graph is built, so this is
-        for monitoring / validation of a training run, not for back-propagation (SURVEY 8f NEXT-3 is not built).
-        Upstream returns this tuple in training mode only; here the mode is not consulted."""
+        """compressor.py:35-43: (xHat, yHat, codes, logits) of the training-time path (soft quantizer: Gumbel sample with
+        PyTorch's RNG, frequency EMA updated).
+        * module in training mode and autograd enabled: the TRAINING STEP (SURVEY 8f NEXT-3) -- an autograd graph is built,
+          every convolution runs forward / dgrad / wgrad on the tcgen05 kernels (mcquic_b200/autograd.py);
+          `loss(xHat, x).backward()` fills the parameters' `.grad` like upstream.
+        * otherwise (eval mode or torch.no_grad()): FORWARD VALUES ONLY on the inference engine, for monitoring /
+          validation of a training run.  (Upstream returns nothing in eval mode; here the values are returned.)"""
         self._check_image(x)
         if x.shape[2] % 16 or x.shape[3] % 16:
             raise RuntimeError("forward() takes training crops whose sides the strided stages divide (multiples of 16)")
+        if self.training and torch.is_grad_enabled():
+            from ..autograd import compressor_forward
+            return compressor_forward(self, x)
+        with torch.no_grad():
+            return self._forward_values(x)
+
+    def _forward_values(self, x: torch.Tensor):
         from .. import engine as E
         old, E._DEFAULT = E._DEFAULT, self.engine       # the quantizer's values path runs on this model's engine
         try:

@@ -200,6 +200,56 @@ def baseline_configs():
     print("vq_cfg3_full", code.numel(), "codes, min margin", float(margin.min()))
 
 
+def train():
+    """tests/golden/train_*.npz: ONE training step of the reference's own `Neon` (BaseCompressor.forward in training mode,
+    compressor.py:35-43 -> ResidualBackwardQuantizer.forward, quantizer.py:727-765) with an MSE loss, on CPU in fp32:
+    loss, xHat, codes, the updated frequency EMA and, for every parameter, the gradient's L2 norm plus a strided sample.
+    The Gumbel / drop uniforms come from tests/common.py:DeterministicRand so the CUDA path can draw the same ones."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import TRAIN_CASES, DeterministicRand, grad_sample, train_inputs
+    import torch.distributed as dist
+    ref_import.load()
+    from mcquic.modules.compressor import Neon
+    torch.set_num_threads(8)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    if not dist.is_initialized():      # EntropyCoder.forward all-reduces unconditionally (entropyCoder.py:314)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    for name in TRAIN_CASES:
+        model, x = train_inputs(name, Neon)
+        model.train()
+        with DeterministicRand(name) as rnd:
+            xHat, yHat, codes, logits = model(x.clone())
+            loss = torch.nn.functional.mse_loss(xHat, x)
+            loss.backward()
+            calls = rnd.calls
+        rec = {"loss": np.array(float(loss)), "xhat": xHat.detach().numpy().astype(np.float32),
+               "yhat": yHat.detach().numpy().astype(np.float32), "rand_calls": np.array(calls)}
+        for j, (c, lg) in enumerate(zip(codes, logits)):
+            rec[f"codes_{j}"] = c.numpy().astype(np.int32)
+            top2 = torch.topk(lg.detach(), 2, dim=-1).values
+            rec[f"logit_margin_{j}"] = np.array(float((top2[..., 0] - top2[..., 1]).min()))
+        for j, f in enumerate(model._quantizer._entropyCoder._freqEMA):
+            rec[f"freq_{j}"] = f.detach().numpy().astype(np.float32)
+        seen = set()
+        missing = []
+        for key, p in model.named_parameters():
+            if p.data_ptr() in seen:
+                continue
+            seen.add(p.data_ptr())
+            if p.grad is None:
+                missing.append(key)
+                continue
+            rec["gnorm." + key] = np.array(float(p.grad.norm()))
+            rec["gsample." + key] = grad_sample(p.grad).numpy().astype(np.float32)
+        rec["no_grad_params"] = np.array(";".join(missing))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, "loss", float(loss), "params with grad", sum(1 for k_ in rec if k_.startswith("gnorm.")),
+              "without", len(missing), "rand calls", calls, [tuple(c.shape) for c in codes])
+
+
 CONTAINER_CASES = [
     # (version, qp, m, heights, widths, k, (height, width, channel), contents)
     ("0.1.40", "qp_1_msssim", [1, 1, 1], [16, 8, 4], [16, 8, 4], [8192, 2048, 512], (256, 256, 3),
@@ -235,6 +285,9 @@ if __name__ == "__main__":
     if "--container" in sys.argv:
         container()
         sys.exit(0)
+    if "--train" in sys.argv:
+        train()
+        sys.exit(0)
     if "--blocks" in sys.argv:
         blocks()
     elif "--neon" in sys.argv:
@@ -247,3 +300,4 @@ if __name__ == "__main__":
         neon()
         baseline_configs()
         container()
+        train()

@@ -104,3 +104,51 @@ def neon_inputs(name, cls):
     model = cls(c, k, list(size), dense).eval()
     model.load_state_dict(synthetic_block_state(model.state_dict(), name, seed=0))
     return model, uniform((n, 3, h, w), name + ".image", 1)
+
+
+# ---- training step (NEXT-3): tiny models the reference can run forward + backward on CPU in seconds
+# name -> (channel, k, size, denseNorm, n, h, w)
+TRAIN_CASES = {
+    # (`size` = latent grids per level, first = image / 16; it must end in two equal entries: the last level's up-projection
+    #  is the identity upstream, quantizer.py:616,641)
+    "train_neon_c32_gn": (32, 64, [8, 4, 4], True, 2, 128, 128),     # GroupNorm everywhere, 32 / 64 / 8-channel nets
+    "train_neon_c64_plain": (64, 128, [4, 4], False, 2, 64, 64),     # SiLU blocks, 64 / 128-channel trunk
+}
+
+
+class DeterministicRand:
+    """context manager: torch.rand_like -> counter-hash uniforms in [0, 1) that depend only on (shape, call number), so the
+    reference on CPU and the CUDA path draw the SAME Gumbel noise / drop masks (consume given uniforms
+    rather than reproduce Philox offsets)"""
+
+    def __init__(self, tag: str):
+        self.tag, self.calls, self._orig = tag, 0, None
+
+    def __enter__(self):
+        self._orig = torch.rand_like
+
+        def rand_like(t, *a, **k):
+            u = (uniform(tuple(t.shape), f"{self.tag}.rand.{self.calls}", 9) + 1.0) * 0.5
+            self.calls += 1
+            return u.to(device=t.device, dtype=t.dtype)
+
+        torch.rand_like = rand_like
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand_like = self._orig
+
+
+def train_inputs(name, cls):
+    from mcquic_b200.utils.synthetic import synthetic_block_state
+    c, k, size, dense, n, h, w = TRAIN_CASES[name]
+    model = cls(c, k, list(size), dense)
+    model.load_state_dict(synthetic_block_state(model.state_dict(), name, seed=0))
+    return model, uniform((n, 3, h, w), name + ".image", 1)
+
+
+def grad_sample(g: torch.Tensor, count: int = 64) -> torch.Tensor:
+    """a deterministic strided sample of a gradient tensor (what the golden files store next to its norm)"""
+    flat = g.detach().flatten()
+    step = max(1, flat.numel() // count)
+    return flat[::step][:count].clone()

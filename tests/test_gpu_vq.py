@@ -68,8 +68,11 @@ def test_assign_matches_oracle(n, h, w, m, k, d):
     (1, 5, 7, 1, 96, 64),        # ragged point count, k = 96 (N tile 96)
 ])
 def test_tensor_core_assign_matches_oracle(n, h, w, m, k, d):
-    """mcq_vq_assign_tc: x.c_k on tcgen05 (3-pass split fp16), distance + argmin in the GEMM epilogue."""
+    """mcq_vq_assign_tc: x.c_k on tcgen05 (3-pass split fp16), distance + argmin in the GEMM epilogue (the path d = 128 took
+    before the one-launch kernel covered it; still the route for d % 64 == 0 shapes the fused kernel does not tile)."""
+    from mcquic_b200 import _lib
     from mcquic_b200.engine import split_weight
+    _lib.set_option("vq128_fused", 0)
     x = uniform((n, m * d, h, w), "vqtc.x", 7) * 0.26
     cb = uniform((m, k, d), "vqtc.cb", 7) * 0.19
     eng = Engine()
@@ -88,9 +91,13 @@ def test_tensor_core_assign_matches_oracle(n, h, w, m, k, d):
     exp = torch.cat([h_.flatten() for h_ in O.code_histogram([codes.cpu()], [k])]).int()
     assert torch.equal(hist.cpu(), exp)
     assert eng.lib.mcq_device_error_flag() == 0
+    _lib.set_option("vq128_fused", 1)
 
 
 @pytest.mark.parametrize("n,h,w,m,k,d", [
+    (2, 16, 16, 1, 8192, 128),   # qp=1 level 0 (d = 128: single latent buffer, codebook in half-row stages)
+    (64, 4, 4, 1, 512, 128),     # qp=1 level 2 at the benchmark batch
+    (3, 8, 8, 2, 2048, 128),     # two codebooks of d = 128
     (2, 32, 32, 6, 2048, 32),    # BASELINE configs[2] shape (qp=3-like: M=6, K=2048, d=32), 2 images
     (2, 8, 8, 2, 2048, 64),      # qp=2-like: d=64 (two 64-element K chunks per operand row)
     (3, 4, 4, 6, 256, 32),       # 16-point images: a 32-row store box spans two images; ragged last tile (48 points)
