@@ -83,7 +83,7 @@ def _split(eng: Engine, x_nhwc_mem: torch.Tensor, n: int, h: int, w: int, c: int
 def _grad_scale(g: torch.Tensor):
     """(S, 1/S) as device scalars: S = the power of two that brings max |g| to [256, 512) -- fp16 planes then keep ~2^-23
     of the largest gradient before flushing.  A handful of tiny launches, no host synchronisation."""
-    amax = g.detach().abs().amax().float()
+    amax = torch.linalg.vector_norm(g.detach(), float("inf")).float()       # one reduction launch, no |g| temporary
     s = torch.exp2(torch.floor(torch.log2(256.0 / amax.clamp_min(1e-37))).clamp(-100.0, 100.0))
     s = torch.where(torch.isfinite(s) & (amax > 0), s, torch.ones_like(s)).reshape(1).contiguous()
     return s, (1.0 / s).contiguous()
@@ -108,23 +108,43 @@ def _dgrad_weight(weight: torch.Tensor, stride: int) -> torch.Tensor:
 
 
 class _Packed:
-    """per-convolution cache of the forward / dgrad operand packings, keyed on the weight's version counter"""
+    """per-layer cache of the forward / dgrad operand packings.  The packings are valid for one weight version; the
+    power-of-two exponents they were scaled with are kept for the life of the layer: re-packing after an optimizer step
+    is then a handful of device operations without any host read, so a whole training step (forward, backward, optimizer)
+    can be captured in ONE CUDA graph.  (fp16 operands scaled to max |w| = 256..512 have a factor 128 of head-room and 2^-22
+    of resolution below that, far more than weights drift between re-scalings; `reset_weight_scales()` re-derives them.)"""
 
     def __init__(self):
         self.key = None
         self.fwd = None
         self.dgrad = None
+        self.exp_fwd = None
+        self.exp_dgrad = None
 
 
 _PACKS = {}
 
 
-def _packs_for(conv: nn.Conv2d) -> _Packed:
-    pk = _PACKS.get(id(conv))
-    key = (_version(conv.weight), conv.weight.data_ptr(), None if conv.bias is None else _version(conv.bias))
-    if pk is None or pk.key != key:
-        pk = _PACKS[id(conv)] = _Packed()
-        pk.key = key
+def reset_weight_scales():
+    """forget the cached packings and exponents (call outside a captured step, e.g. every few thousand steps)"""
+    _PACKS.clear()
+
+
+def _exp_of(pc) -> int:
+    import math
+    return int(round(-math.log2(pc.w_scale)))
+
+
+def _packs_for(owner: nn.Module, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> _Packed:
+    pk = _PACKS.get(id(owner))
+    key = (_version(weight), weight.data_ptr(), None if bias is None else _version(bias))
+    capturing = weight.is_cuda and torch.cuda.is_current_stream_capturing()
+    if pk is None:
+        pk = _PACKS[id(owner)] = _Packed()
+    if pk.key != key or capturing or weight.grad_fn is not None:
+        # new weight values (or a graph capture, whose replays must re-pack, or weights that are themselves computed each
+        # step like GDN's reparametrised gamma): drop the packings, keep the exponents
+        pk.key, pk.fwd, pk.dgrad = key, None, None
     return pk
 
 
@@ -153,9 +173,10 @@ class _ConvFn(torch.autograd.Function):
         hi, lo = _split(eng, xm, n, h, w, cin)
         pc = cache.fwd if cache is not None else None
         if pc is None:
-            pc = pack_conv(weight, bias, stride, _lib.STORE_NHWC, weight.device)
+            pc = pack_conv(weight, bias, stride, _lib.STORE_NHWC, weight.device,
+                           exp=None if cache is None else cache.exp_fwd)
             if cache is not None:
-                cache.fwd = pc
+                cache.fwd, cache.exp_fwd = pc, _exp_of(pc)
         out = eng.conv(pc, (hi, lo), Act(n, h, w, pc.cin), {"f32"})
         y = out.f32                                         # [n, ho, wo, cout_pad8]
         ctx.cache, ctx.stride = cache, stride
@@ -181,9 +202,10 @@ class _ConvFn(torch.autograd.Function):
             pd = cache.dgrad if cache is not None else None
             if pd is None:
                 wd = _dgrad_weight(weight, stride)
-                pd = pack_conv(wd, None, 1, _lib.STORE_SHUFFLE_NHWC if stride == 2 else _lib.STORE_NHWC, weight.device)
+                pd = pack_conv(wd, None, 1, _lib.STORE_SHUFFLE_NHWC if stride == 2 else _lib.STORE_NHWC, weight.device,
+                               exp=None if cache is None else cache.exp_dgrad)
                 if cache is not None:
-                    cache.dgrad = pd
+                    cache.dgrad, cache.exp_dgrad = pd, _exp_of(pd)
             out = eng.conv(pd, (gp, gl), Act(n, ho, wo, cop), {"f32"}, dev_scale=inv_s)
             d = out.f32                                     # [n, h, w, cin_pad8]
             dx = d.permute(0, 3, 1, 2)
@@ -209,9 +231,11 @@ class _ConvFn(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
-def conv2d_weights(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1) -> torch.Tensor:
-    """convolution with explicitly given weights [cout, cin, k, k] (k in {1, 3}, padding k // 2) on the tcgen05 kernels"""
-    return _ConvFn.apply(x, weight, bias, stride, None)
+def conv2d_weights(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1,
+                   owner: Optional[nn.Module] = None) -> torch.Tensor:
+    """convolution with explicitly given weights [cout, cin, k, k] (k in {1, 3}, padding k // 2) on the tcgen05 kernels;
+    owner: the module the weights are derived from (its operand exponents are cached, see _Packed)"""
+    return _ConvFn.apply(x, weight, bias, stride, None if owner is None else _packs_for(owner, weight, bias))
 
 
 def conv2d(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
@@ -219,7 +243,7 @@ def conv2d(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         raise RuntimeError("mcquic_b200 runs on CUDA tensors only (no CPU fallback)")
     if conv_supported(conv):
-        return _ConvFn.apply(x, conv.weight, conv.bias, conv.stride[0], _packs_for(conv))
+        return _ConvFn.apply(x, conv.weight, conv.bias, conv.stride[0], _packs_for(conv, conv.weight, conv.bias))
     return F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding)
 
 
@@ -249,7 +273,8 @@ def gdn(mod, x: torch.Tensor) -> torch.Tensor:
     beta = _reparam(mod.beta_reparam, mod.beta)
     gamma = _reparam(mod.gamma_reparam, mod.gamma)[..., None, None]
     # the operand plane holds x^2 * 2^-6 like the inference path's MCQ_ACT_SQUARE planes (|x| up to 2047 stays in fp16 range)
-    std = conv2d_weights(x ** 2 * _lib.SQUARE_SCALE, gamma, None) * (1.0 / _lib.SQUARE_SCALE) + beta.reshape(1, -1, 1, 1)
+    std = conv2d_weights(x ** 2 * _lib.SQUARE_SCALE, gamma, None, owner=mod) * (1.0 / _lib.SQUARE_SCALE) \
+        + beta.reshape(1, -1, 1, 1)
     return x * torch.sqrt(std) if mod.inverse else x * torch.rsqrt(std)
 
 
@@ -344,8 +369,7 @@ def quantize_soft(q, x: torch.Tensor):
     t = _LowerBoundFn.apply(q._temperature, q._bound.bound)                   # quantizer.py:204
     logit = _LogitsFn.apply(x, q._codebook, t)
     if isinstance(getattr(q, "_freqEMA", None), torch.Tensor):
-        # upstream masks in place (quantizer.py:199); the un-masked logits are kept for the temperature gradient
-        logit = q._randomDrop(logit.clone())
+        logit = q._randomDrop(logit)        # quantizer.py:194-200 (out of place: the un-masked logits feed dL/dtemperature)
     sample = _gumbel_softmax_hard(logit)
     code = logit.argmax(-1, keepdim=True)
     one_hot = torch.zeros_like(logit).scatter_(-1, code, 1).contiguous()

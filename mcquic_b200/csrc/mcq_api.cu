@@ -716,7 +716,10 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
                                opt("pair_resident");
     if (a.gn_ws) rc = halo_supported(a) ? launch_pair(a, st) : MCQ_ERR_UNSUPPORTED;   // only the pair kernel has it
     else
-    if (halo_supported(a) && (opt("pair") >= 0 ? opt("pair") : ((a.passes == 3 || pair_resident) ? 1 : 0))) rc = launch_pair(a, st);
+    // (streaming-weight 1-pass pairs pay off once K is long enough to amortise the epilogue: cin >= 256, measured on the
+    //  a800_16 training step: 696 -> 666 ms)
+    if (halo_supported(a) && (opt("pair") >= 0 ? opt("pair") : ((a.passes == 3 || pair_resident || a.cin >= 256) ? 1 : 0)))
+      rc = launch_pair(a, st);
     if (rc == MCQ_ERR_UNSUPPORTED && !a.gn_ws && halo_supported(a) && opt("halo")) rc = launch_halo(a, st);
     if (rc == MCQ_ERR_UNSUPPORTED && !a.gn_ws) rc = launch_tc(a, st);
   }

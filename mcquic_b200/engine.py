@@ -76,17 +76,22 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def split_weight(w2d: torch.Tensor, amax: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor, float]:
+def split_weight(w2d: torch.Tensor, amax: Optional[float] = None, exp: Optional[int] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor, float]:
     """fp32 [rows, K] -> (hi, lo) fp16 with  w * 2^e ~= hi + lo / 2048  and the accumulator scale 2^-e.
     amax: max |w| when the caller already knows it (Engine.prepare computes it for ALL layers with one device
-    reduction and one host read instead of a device-to-host sync per layer)."""
-    if amax is None:
-        amax = float(w2d.abs().max())
-    e = 0 if amax == 0.0 or not math.isfinite(amax) else int(max(-14, min(14, math.floor(math.log2(256.0 / amax)))))
-    ws = w2d.double() * (2.0 ** e)
+    reduction and one host read instead of a device-to-host sync per layer).
+    exp: the exponent e itself (training step: chosen when a layer is first packed and kept while its weights drift, so
+    that re-packing after every optimizer step needs no host synchronisation and can be captured in a CUDA graph).
+    The arithmetic is exact in fp32 (power-of-two scaling; w * 2^e - hi has at most 13 significant bits)."""
+    if exp is None:
+        if amax is None:
+            amax = float(w2d.abs().max())
+        exp = 0 if amax == 0.0 or not math.isfinite(amax) else int(max(-14, min(14, math.floor(math.log2(256.0 / amax)))))
+    ws = w2d.float() * (2.0 ** exp)
     hi = ws.to(torch.float16)
-    lo = ((ws - hi.double()) * LO_SCALE).to(torch.float16)
-    return hi.contiguous(), lo.contiguous(), float(2.0 ** (-e))
+    lo = ((ws - hi.float()) * LO_SCALE).to(torch.float16)
+    return hi.contiguous(), lo.contiguous(), float(2.0 ** (-exp))
 
 
 def pack_codebook(codebook: torch.Tensor):
@@ -98,7 +103,7 @@ def pack_codebook(codebook: torch.Tensor):
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, store: int, device,
-              amax: Optional[float] = None) -> PackedConv:
+              amax: Optional[float] = None, exp: Optional[int] = None) -> PackedConv:
     """nn.Conv2d weight [cout, cin, k, k] -> K-major GEMM matrix [cout_pad, (r, s, cin)] (split fp16).
     bias=None (conv1x1(..., bias=False) of the Neon quantizer) packs a zero bias.  Channel counts the kernels' vector
     accesses cannot address are zero-padded: cin to a multiple of 8 (RGB input of Neon's first conv: the caller pads
@@ -125,7 +130,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, s
     cout_pad = cout if cout % 128 == 0 or (cout <= 256 and cout % 32 == 0) else ((cout + 15) // 16) * 16
     if cout_pad != cout:
         w = torch.cat([w, torch.zeros(cout_pad - cout, w.shape[1], device=device)], 0)
-    hi, lo, scale = split_weight(w, amax)        # zero padding and row permutation leave max |w| unchanged
+    hi, lo, scale = split_weight(w, amax, exp)   # zero padding and row permutation leave max |w| unchanged
     return PackedConv(hi, lo, b.contiguous(), cin, cout, cout_pad, k, stride, scale, store)
 
 

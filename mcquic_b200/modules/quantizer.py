@@ -244,8 +244,10 @@ class _multiCodebookQuantization(nn.Module):
         freq = self._freqEMA.detach().to(logit.device)
         usage = (freq > _EPS).float().mean().clamp(0.0, 1.0)
         mask = (torch.rand_like(logit) ** (-(bits - 1) * (usage ** 2) + bits)) < freq[:, None, None, ...]
-        logit[mask] += -1e9
-        return logit
+        # upstream: `logit[randomMask] += -1e9` (quantizer.py:199).  Same values, but as a select instead of a boolean-mask
+        # scatter: the latter needs the number of set bits on the host, i.e. a device synchronisation per level, which also
+        # keeps a training step from being captured in a CUDA graph
+        return torch.where(mask, logit + (-1e9), logit)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor):

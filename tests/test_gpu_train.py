@@ -185,7 +185,7 @@ def test_compressor_training_step_equals_a_library_evaluation_of_the_same_graph(
         model = model.cuda().train()
         if patched:
             monkeypatch.setattr(A, "conv2d", lambda conv, t: F.conv2d(t, conv.weight, conv.bias, conv.stride, conv.padding))
-            monkeypatch.setattr(A, "conv2d_weights", lambda t, w, b, stride=1: F.conv2d(t, w, b, stride, w.shape[-1] // 2))
+            monkeypatch.setattr(A, "conv2d_weights", lambda t, w, b, stride=1, owner=None: F.conv2d(t, w, b, stride, w.shape[-1] // 2))
 
             class Logits:
                 @staticmethod
