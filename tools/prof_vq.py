@@ -16,6 +16,8 @@ from mcquic_b200.utils.synthetic import uniform  # noqa: E402
 
 once = "--once" in sys.argv
 n, h, w, m, k, d = 32, 32, 32, 6, 2048, 32
+if "--qp1" in sys.argv:      # the headline model's level-0 VQ: one codebook over all 128 channels, K = 8192, batch 64 of 256x256
+    n, h, w, m, k, d = 64, 16, 16, 1, 8192, 128
 eng = Engine()
 x = (uniform((n, m * d, h, w), "vq.big", 5) * 0.26).cuda()
 cb = (uniform((m, k, d), "vq.bigcb", 5) * 0.19).cuda().contiguous()
@@ -50,4 +52,5 @@ for logits in (False, True):
     b = bytes_soft if logits else bytes_hard
     out["soft" if logits else "hard"] = {"ms": ms, "alg_bytes": b, "GBps": b / ms / 1e6, "frac_hbm": b / ms / 1e6 / peaks["hbm_gbs"],
                                         "TFLOPs": flops / ms / 1e9}
+out["shape"] = dict(n=n, h=h, w=w, m=m, k=k, d=d)
 print(json.dumps(out))

@@ -43,6 +43,16 @@ def main(path, steps, out_json=None):
     out["conv_dram_bytes_per_step"] = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"] for v in conv.values())
     out["conv_share"] = sum(v["share"] for v in conv.values())
     print(f"# tcgen05 conv kernels: {100*out['conv_share']:.1f}% of the step, DRAM traffic {out['conv_dram_bytes_per_step']/1e9:.2f} GB per step")
+    dom = [v for k, v in ours.items() if "conv_pair_kernel<3" in k.replace(" ", "") and "true" not in k and ", 1>" not in k]
+    if dom:
+        n_l = sum(v["launches_per_step"] for v in dom)
+        out["dominant_kernel_dram_bytes_per_launch"] = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"]
+                                                           for v in dom) / n_l
+        out["dominant_kernel_launches_per_step"] = n_l
+        out["dominant_kernel_ms_per_step"] = sum(v["ms_per_step"] for v in dom)
+        out["dominant_kernel_share"] = sum(v["share"] for v in dom)
+        print(f"# dominant kernel conv_pair_kernel<3>: {n_l:.0f} launches/step, {out['dominant_kernel_ms_per_step']:.3f} ms/step "
+              f"({100*out['dominant_kernel_share']:.1f}% of the serialised step), DRAM {out['dominant_kernel_dram_bytes_per_launch']/1e6:.1f} MB per launch")
     if out_json:
         json.dump(out, open(out_json, "w"), indent=1)
 
