@@ -265,6 +265,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    _lib.apply_options(args.opt)      # A/B knobs (mcq_set_option), e.g. --opt direct_epi=1; empty = the library defaults
     model = Compressor(CHANNEL, M, K).eval()
     model.load_state_dict(synthetic_state_dict(CHANNEL, M, K, seed=0))
     model = model.to(dev)
@@ -345,7 +346,7 @@ def run_ours(args):
 
     out = None
     roofline = None
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
         # ---- roofline leg: one eager step with every conv launch bracketed by events (single stream)
         peaks, peak_src = _peaks()
         model.use_graphs = False
@@ -368,7 +369,7 @@ def run_ours(args):
         t_all = t_other + sum(p["ev"][0].elapsed_time(p["ev"][1]) for p in prof) * 1e-3
         if args.dump_profile:
             with open(args.dump_profile, "w") as fp:
-                json.dump([{"shape": p["shape"], "passes": p["passes"], "flops": p["flops"],
+                json.dump([{"shape": p["shape"], "passes": p["passes"], "flops": p["flops"], "epi": p.get("epi"),
                             "us": 1e3 * p["ev"][0].elapsed_time(p["ev"][1])} for p in prof] +
                           [{"other": p["other"], "us": 1e3 * p["ev"][0].elapsed_time(p["ev"][1])} for p in others], fp)
         tc = [p for p in prof if p["impl"] == _lib.IMPL_TCGEN05]
@@ -457,11 +458,12 @@ def run_ours(args):
                 gpu_base["what"] = ("the reference algorithm as eager PyTorch (ATen / cuDNN / cuBLAS) on this GPU in this "
                                     "run, batch 64x3x256x256, encode+decode, device-resident input: PyTorch's default "
                                     "(TF32 convolutions) and true fp32 (the setting whose code indices are comparable)")
-            cpu_val, cpu_s, cores = _cpu_oracle_throughput(sample_images=CPU_SAMPLE, repeats=5)
-            cpu = {"value": cpu_val, "unit": "MPix/s", "cores": cores, "kind": "port",
-                   "sample": f"{CPU_SAMPLE} of the 64 images of a step, encode+decode, best of 5 ({cpu_s:.2f} s each), "
-                             f"oracle/mcquic_oracle.py (CPU PyTorch fp32), {cores} threads = physical cores "
-                             f"({os.cpu_count()} logical CPUs)"}
+            if not args.no_cpu_baseline:
+                cpu_val, cpu_s, cores = _cpu_oracle_throughput(sample_images=CPU_SAMPLE, repeats=5)
+                cpu = {"value": cpu_val, "unit": "MPix/s", "cores": cores, "kind": "port",
+                       "sample": f"{CPU_SAMPLE} of the 64 images of a step, encode+decode, best of 5 ({cpu_s:.2f} s each), "
+                                 f"oracle/mcquic_oracle.py (CPU PyTorch fp32), {cores} threads = physical cores "
+                                 f"({os.cpu_count()} logical CPUs)"}
         out = {
             "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -479,6 +481,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": roofline,
+            "options": args.opt or None,
             "cpu_baseline": cpu,
             "gpu_baseline": gpu_base,
             "strong_scaling": None if not strong_ms else {
@@ -508,6 +511,9 @@ def main():
     ap.add_argument("--dump-profile", default=None, help="write the per-conv-launch timing list of the roofline leg here")
     ap.add_argument("--no-strong", action="store_true", help="skip the 512-image strong-scaling leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-PyTorch-on-this-GPU baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-oracle leg (A/B runs of tools/)")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-launch roofline leg (A/B runs of tools/)")
+    ap.add_argument("--opt", default="", help="library options name=value,... (mcq_set_option); default: none")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -68,7 +68,7 @@ __device__ __forceinline__ uint64_t make_sdesc_halo(uint32_t saddr, uint32_t sbo
   return ((uint64_t)hi << 32) | lo;
 }
 
-template <int PASSES, int CL>
+template <int PASSES, int CL, int DRAIN = DRAIN_ROWS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -311,7 +311,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       mbar_wait(tfull_bar(buf), use & 1u, 16, p.wait_sleep_ns);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, effective_w_scale(p));
+      drain_tile<PASSES, false, DRAIN>(p, nullptr, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, effective_w_scale(p));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));

@@ -72,11 +72,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
       : "memory");
 }
 
-template <int PASSES, bool GN = false>
+template <int PASSES, bool GN = false, int DRAIN = DRAIN_ROWS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi_full, const __grid_constant__ CUtensorMap tmB_lo_full,
-                 const __grid_constant__ CUtensorMap tmB_hi_half, const ConvArgs p, const HaloArgs hp) {
+                 const __grid_constant__ CUtensorMap tmB_hi_half, const ConvArgs p, const HaloArgs hp,
+                 const __grid_constant__ OutMaps om) {
   // tmB_{hi,lo}_full: weight planes with box {64, bn} (3-pass only); tmB_hi_half: hi plane with box {64, bn / 2}
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -106,7 +107,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * na + 2 * nbs + 2 + b); };
   uint32_t* tmem_slot =
       reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8u * (2 * na + 2 * nbs + 4));
-  const uint32_t epi_base = (bar_base + 8u * (2 * na + 2 * nbs + 4) + 16u + 127u) & ~127u;
+  const uint32_t epi_base = (bar_base + 8u * (2 * na + 2 * nbs + 4) + 16u + 511u) & ~511u;   // 512 B: swizzle period of the staging
   float* bias_smem = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + TC_EPI_WARPS * TC_EPI_STAGE_BYTES);
   const bool bias_staged = p.cout <= TC_BIAS_SMEM_FLOATS;
   if (bias_staged)
@@ -315,13 +316,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       mbar_wait(tfull_bar(buf), use & 1u, 26, p.wait_sleep_ns);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES, GN>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, effective_w_scale(p));
+      drain_tile<PASSES, GN, DRAIN>(p, &om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, effective_w_scale(p));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(tempty_bar(buf));
         else mbar_arrive_remote(tempty_bar(buf), 0);
       }
+    }
+    if constexpr (DRAIN == DRAIN_TMA) {
+      if (lane == 0) bulk_wait_all();          // this lane's bulk stores have left shared memory and are complete
     }
   }
 

@@ -188,16 +188,336 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
 __device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ void st_global_128(void* ptr, const uint32_t (&w)[4]) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+               : "memory");
+}
+
+// ---- bulk-tensor stores (shared -> global) of the drain; bulk groups belong to the issuing thread
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// TMA-store views of a launch's outputs (DRAIN_TMA instantiations only): 5-D {channels, W, 1 | sub-pixel row, H, N} with a
+// box of 16 channels x the 32 pixels one drain warp owns; fp32: SWIZZLE_64B, fp16 planes: SWIZZLE_32B
+struct OutMaps {
+  CUtensorMap f32, o0_hi, o0_lo, o1_hi, o1_lo;
+};
+
+constexpr int DRAIN_ROWS = 0;   // row per lane: direct / smem-transposed global stores (any shape)
+constexpr int DRAIN_QUAD = 1;   // quad layout: full-line global accesses
+constexpr int DRAIN_TMA = 2;    // row per lane, outputs staged in shared memory and written by bulk-tensor stores
+
 // ---------------------------------------------------------------- epilogue
-// Drain this warp's share (TMEM lanes 32q.., 32-column chunks cg, cg+4, ...) of one accumulator tile.
-// tcgen05.ld hands every thread one GEMM row (= pixel); storing from that layout would touch 32 cache lines per
-// warp instruction.  So each 32x16 block goes through a per-warp, XOR-swizzled (conflict-free) smem transpose and
-// the fused epilogue runs with 2 lanes per pixel x 8 consecutive channels each: residual / aux loads and all stores
-// are 64 B-contiguous per pixel (16 lines per instruction -> full sectors).
-// pix(row, n, oy, ox) -> valid maps a tile row to its output pixel.
-template <int PASSES, bool GN = false, class PixFn>
-__device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, int bn, int ct, int cg, int q, int lane,
-                                           uint32_t stage, PixFn pix, const float* bias_src, const float wscale) {
+// Quad drain: full-line global accesses.
+//
+// tcgen05.ld hands every lane one GEMM row (= pixel).  Storing from that layout (the "direct" drain below) makes every
+// 256-bit access of a warp touch 32 different 128 B lines, 32 B each -- and the L1TEX data pipe, which also feeds the
+// tensor core its shared-memory operands, pays per LINE visited, not per byte (ncu, 3-pass 64x64 layer: LSU wavefronts
+// 41 % + tensor-core operand wavefronts 30 % of the pipe's peak; ~10 k LSU wavefronts per 128 x 128 tile against ~4.6 k
+// cycles of MMA).  Here a warp's 32 pixels x 32 channels block is re-distributed through its 2 KB staging buffer so that
+// the four lanes of a quad hold the four 32 B pieces of ONE pixel's 128 B line: lane 4g+j owns channels [c0 + 8j, +8) of
+// pixels 4g .. 4g+3.  Every global instruction then covers 8 complete lines (fp32; 8 half lines for fp16 planes) instead
+// of 32 quarter lines: a quarter of the line visits for the residual read, the fp32 store and the plane stores.  All
+// epilogue math is element-wise, so it runs unchanged in the new layout.
+template <int PASSES, class PixFn>
+__device__ __forceinline__ void drain_tile_quad(const ConvArgs& p, uint32_t t_acc, int bn, int ct, int cg, int q, int lane,
+                                                uint32_t stage, PixFn pix, const float* bias_src, const float wscale) {
+  constexpr bool FAST = PASSES == 1;
+  const int g = lane >> 2, j = lane & 3;
+  const bool shuffled = p.store == MCQ_STORE_SHUFFLE_NHWC;
+  // operand roles: `pre` is requested one pixel ahead of its use, `sec` (second residual / gate operand: rare) at its use
+  const float* pre = p.mode == MCQ_EPI_LINEAR ? (p.res1 ? p.res1 : p.res2) : (p.mode == MCQ_EPI_GATE ? p.res1 : p.aux);
+  const float* sec = p.mode == MCQ_EPI_LINEAR ? (p.res1 ? p.res2 : nullptr) : (p.mode == MCQ_EPI_GATE ? p.aux : nullptr);
+  const uint32_t wbase = stage + (uint32_t)lane * 64u;   // staging: row per lane, 64 B; 16 B chunk c at c ^ ((row >> 1) & 3)
+  const uint32_t wsw = (uint32_t)((lane >> 1) & 3);
+  for (int cc = cg * 32; cc < bn; cc += 128) {
+    const int c0 = ct * bn + cc;
+    if (c0 >= p.cout) break;
+    size_t off[4];
+    bool ok_[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int n, oy, ox;
+      ok_[k] = pix(q * 32 + 4 * g + k, n, oy, ox) && !p.debug_skip_store;
+      off[k] = (shuffled ? epilogue_offset(p, n, oy, ox, c0)
+                         : (((size_t)n * p.hout + oy) * p.wout + ox) * (size_t)p.cout + c0) + (size_t)(8 * j);
+    }
+    float o1[2][8];
+    if (pre && ok_[0]) ld_global_256(pre + off[0], o1[0]);
+    // accumulator block [32 pixels x 32 columns]: TMEM -> registers (row per lane) -> staging -> registers (quad layout:
+    // v[8 k + e] = channel c0 + 8 j + e of pixel 4g + k)
+    float v[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[16];
+      float w[16];
+      tmem_ld16(t_acc + (uint32_t)(cc + half * 16), r);
+      if (PASSES == 3) {
+        uint32_t l[16];
+        tmem_ld16(t_acc + (uint32_t)(bn + cc + half * 16), l);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = fmaf(__uint_as_float(l[i]), kLoInv, __uint_as_float(r[i]));
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = __uint_as_float(r[i]);
+      }
+      __syncwarp();                                          // the previous round's reads of the staging buffer are done
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wbase + ((((uint32_t)c) ^ wsw) << 4)),
+                     "f"(w[4 * c]), "f"(w[4 * c + 1]), "f"(w[4 * c + 2]), "f"(w[4 * c + 3])
+                     : "memory");
+      __syncwarp();
+      if ((j >> 1) == half) {                                // this round carries channels [16 half, 16 half + 16)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t row = (uint32_t)(4 * g + k);
+          const uint32_t rbase = stage + row * 64u;
+          const uint32_t rsw = (row >> 1) & 3u;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const uint32_t chunk = (uint32_t)((j & 1) * 2 + e);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v[8 * k + 4 * e]), "=f"(v[8 * k + 4 * e + 1]), "=f"(v[8 * k + 4 * e + 2]),
+                           "=f"(v[8 * k + 4 * e + 3])
+                         : "r"(rbase + ((chunk ^ rsw) << 4))
+                         : "memory");
+          }
+        }
+      }
+    }
+    float b[8];
+    load_f32v<8>(bias_src, c0 + 8 * j, b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k + 1 < 4) {
+        if (pre && ok_[(k + 1) & 3]) ld_global_256(pre + off[(k + 1) & 3], o1[(k + 1) & 1]);
+      }
+      if (!ok_[k]) continue;
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = fmaf(v[8 * k + e], wscale, b[e]);
+      if (p.mode == MCQ_EPI_LINEAR) {
+        if (p.res1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = y[e] + p.res1_scale * o1[k & 1][e];
+          if (sec) {
+            float o2[8];
+            ld_global_256(sec + off[k], o2);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = y[e] + o2[e];
+          }
+        } else if (pre) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = y[e] + o1[k & 1][e];
+        }
+      } else if (p.mode == MCQ_EPI_GATE) {
+        float o2[8];
+        ld_global_256(sec + off[k], o2);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = o2[e] * sigmoid_f<FAST>(y[e]) + o1[k & 1][e];
+      } else if (p.mode == MCQ_EPI_GDN) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if constexpr (FAST) y[e] = o1[k & 1][e] * rsqrtf(y[e]);
+          else y[e] = o1[k & 1][e] * (1.0f / sqrtf(y[e]));
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if constexpr (FAST) y[e] = o1[k & 1][e] * (y[e] * rsqrtf(y[e]));
+          else y[e] = o1[k & 1][e] * sqrtf(y[e]);
+        }
+      }
+      if (p.out_f32) st_global_256(p.out_f32 + off[k], reinterpret_cast<const uint32_t(&)[8]>(y[0]));
+#pragma unroll
+      for (int slot = 0; slot < 2; ++slot) {
+        __half* hi_p = slot == 0 ? p.o0_hi : p.o1_hi;
+        __half* lo_p = slot == 0 ? p.o0_lo : p.o1_lo;
+        if (!hi_p) continue;
+        float t[8];
+        act_group<8, FAST>(y, t, slot == 0 ? p.o0_act : p.o1_act);
+        uint32_t h[4], lw[4];
+        if (lo_p) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_f32x2(t[2 * e], t[2 * e + 1], h[e], lw[e]);
+          st_global_128(hi_p + off[k], h);
+          st_global_128(lo_p + off[k], lw);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = f2h2_sat(t[2 * e], t[2 * e + 1]);
+          st_global_128(hi_p + off[k], h);
+        }
+      }
+    }
+  }
+}
+
+// TMA-store drain.
+//
+// ncu (profiles/r2_ncu_drain_variants.txt) shows what bounds the layers with fp32 outputs: the L1TEX data pipe, which also
+// feeds the tensor core its shared-memory operands, is ~75 % busy, and a global STORE costs it one wavefront per 32 B
+// sector (two in the row-per-lane layout) however well it coalesces: 8-11 k wavefronts per 128 x 128 tile beside the MMA's
+// 8 k (3-pass).  A shared-memory store moves 128 B per wavefront.  So the drain keeps its row-per-lane layout, writes every
+// 16-column batch of every output into the warp's 2 KB staging buffer (the same XOR pattern as the transposed drain =
+// SWIZZLE_64B for fp32 rows of 64 B, SWIZZLE_32B for fp16 rows of 32 B) and one lane issues a bulk-tensor store of the
+// 16 channels x 32 pixels box.  The buffer is single: a store must have been read out (wait_group.read) before the next
+// batch is staged -- by then the warp has spent a batch's worth of math.  Image borders and phantom tiles need no
+// masking: the TMA clips the box.
+template <int PASSES, class PixFn>
+__device__ __forceinline__ void drain_tile_tma(const ConvArgs& p, const OutMaps* om, uint32_t t_acc, int bn, int ct, int cg,
+                                               int q, int lane, uint32_t stage, PixFn pix, const float* bias_src,
+                                               const float wscale) {
+  constexpr bool FAST = PASSES == 1;
+  const bool shuffled = p.store == MCQ_STORE_SHUFFLE_NHWC;
+  int n, oy, ox;
+  const bool ok = pix(q * 32 + lane, n, oy, ox);
+  const size_t pixoff = (((size_t)n * p.hout + oy) * p.wout + ox) * (size_t)p.cout;
+  // box origin = the warp's first row (lane 0); the box covers the 32 rows in tile order (x, then y, then n)
+  const int bx0 = __shfl_sync(0xffffffffu, ox, 0), by0 = __shfl_sync(0xffffffffu, oy, 0);
+  const int bn0 = __shfl_sync(0xffffffffu, n, 0);
+  const uint32_t row64 = stage + (uint32_t)lane * 64u;               // fp32: 64 B per row, chunk c at c ^ ((row >> 1) & 3)
+  const uint32_t sw64 = (uint32_t)((lane >> 1) & 3);
+  const uint32_t row32 = stage + (uint32_t)lane * 32u;               // fp16: 32 B per row, chunk c at c ^ ((row >> 2) & 1)
+  const uint32_t sw32 = (uint32_t)((lane >> 2) & 1);
+  const bool skip = p.debug_skip_store != 0;
+  for (int cc = cg * 32; cc < bn; cc += 128) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int col0 = cc + half * 16;
+      if (col0 >= bn) break;
+      const int c0 = ct * bn + col0;
+      if (c0 >= p.cout) break;                                       // warp-uniform
+      const size_t off = shuffled ? epilogue_offset(p, n, oy, ox, c0) : pixoff + c0;
+      int cx = c0, cz = 0;                                           // channel / sub-pixel-row coordinates of the box
+      if (shuffled) {
+        const int cq = p.cout >> 2, sub = c0 / cq;
+        cx = (sub & 1) * cq + (c0 - sub * cq);
+        cz = sub >> 1;
+      }
+      uint32_t r[16];
+      float y[16];
+      tmem_ld16(t_acc + (uint32_t)col0, r);
+      float o1[16], o2[16];
+      const float* src1 = (p.mode == MCQ_EPI_LINEAR || p.mode == MCQ_EPI_GATE) ? p.res1 : nullptr;
+      const float* src2 = (p.mode == MCQ_EPI_LINEAR) ? p.res2 : p.aux;
+      if (ok && src1) { ld_global_256(src1 + off, o1); ld_global_256(src1 + off + 8, o1 + 8); }
+      if (ok && src2) { ld_global_256(src2 + off, o2); ld_global_256(src2 + off + 8, o2 + 8); }
+      if (PASSES == 3) {
+        uint32_t l[16];
+        tmem_ld16(t_acc + (uint32_t)(bn + col0), l);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] = fmaf(__uint_as_float(l[j]), kLoInv, __uint_as_float(r[j]));
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
+      }
+      {
+        float b[16];
+        load_f32v<16>(bias_src, c0, b);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], wscale, b[j]);
+      }
+      if (ok) {                                                      // rows outside the image: values unused (clipped)
+        if (p.mode == MCQ_EPI_LINEAR) {
+          if (src1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = y[j] + p.res1_scale * o1[j];
+          }
+          if (src2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = y[j] + o2[j];
+          }
+        } else if (p.mode == MCQ_EPI_GATE) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = o2[j] * sigmoid_f<FAST>(y[j]) + o1[j];
+        } else if (p.mode == MCQ_EPI_GDN) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if constexpr (FAST) y[j] = o2[j] * rsqrtf(y[j]);
+            else y[j] = o2[j] * (1.0f / sqrtf(y[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if constexpr (FAST) y[j] = o2[j] * (y[j] * rsqrtf(y[j]));
+            else y[j] = o2[j] * sqrtf(y[j]);
+          }
+        }
+      }
+      if (p.out_f32) {
+        if (lane == 0) bulk_wait_read<0>();                          // the store that last read the staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row64 + ((((uint32_t)c) ^ sw64) << 4)),
+                       "f"(y[4 * c]), "f"(y[4 * c + 1]), "f"(y[4 * c + 2]), "f"(y[4 * c + 3])
+                       : "memory");
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (!skip) tma_store_5d(&om->f32, stage, cx, bx0, cz, by0, bn0);
+          bulk_commit();
+        }
+      }
+#pragma unroll
+      for (int slot = 0; slot < 2; ++slot) {
+        const bool on = slot == 0 ? p.o0_hi != nullptr : p.o1_hi != nullptr;
+        const bool with_lo = slot == 0 ? p.o0_lo != nullptr : p.o1_lo != nullptr;
+        if (!on) continue;
+        float t[16];
+        act_group<16, FAST>(y, t, slot == 0 ? p.o0_act : p.o1_act);
+        uint32_t h[8], lw[8];
+        if (with_lo) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_f32x2(t[2 * j], t[2 * j + 1], h[j], lw[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = f2h2_sat(t[2 * j], t[2 * j + 1]);
+        }
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t a = row32 + ((((uint32_t)c) ^ sw32) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[4 * c]), "r"(h[4 * c + 1]),
+                       "r"(h[4 * c + 2]), "r"(h[4 * c + 3])
+                       : "memory");
+          if (with_lo)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 1024u), "r"(lw[4 * c]), "r"(lw[4 * c + 1]),
+                         "r"(lw[4 * c + 2]), "r"(lw[4 * c + 3])
+                         : "memory");
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (!skip) {
+            tma_store_5d(slot == 0 ? &om->o0_hi : &om->o1_hi, stage, cx, bx0, cz, by0, bn0);
+            if (with_lo) tma_store_5d(slot == 0 ? &om->o0_lo : &om->o1_lo, stage + 1024u, cx, bx0, cz, by0, bn0);
+          }
+          bulk_commit();
+        }
+      }
+    }
+  }
+}
+
+// Row-per-lane drain with global stores (DRAIN_ROWS; any shape, argmin epilogue, GroupNorm statistics).
+template <int PASSES, bool GN, class PixFn>
+__device__ __forceinline__ void drain_tile_rows(const ConvArgs& p, uint32_t t_acc, int bn, int ct, int cg, int q, int lane,
+                                                uint32_t stage, PixFn pix, const float* bias_src, const float wscale) {
   int n_[2], oy_[2], ox_[2];
   bool ok_[2];
 #pragma unroll
@@ -249,9 +569,9 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
   // operand reads) -- and, measured, everywhere else too.  At 64x64: 1-pass plane->plane 64 -> 60 us (mainloop alone
   // 45), 3-pass 164 -> 157 us; whole step -2 %.
   const bool plane_only = p.mode == MCQ_EPI_LINEAR && !p.res1 && !p.res2 && !p.out_f32 && p.o0_hi && !p.o1_hi;
-  // direct_epilogue (A/B knob MCQ_DIRECT_EPI): 1 = every NHWC / PixelShuffle-NHWC store (default; measured best also for
-  // the 1-pass layers with fp32 residual + output), 2 = plane-only outputs only, 0 = never
-  const bool direct_ok = p.direct_epilogue == 1 || (p.direct_epilogue == 2 && plane_only);
+  // direct_epilogue (A/B knob, mcq_set_option("direct_epi")): 3 / 4 = quad drain (another kernel instantiation) where the host chose it, else as 1;
+  // 1 = direct drain for every NHWC / PixelShuffle-NHWC store, 2 = plane-only outputs only, 0 = never
+  const bool direct_ok = p.direct_epilogue == 1 || p.direct_epilogue >= 3 || (p.direct_epilogue == 2 && plane_only);
   const bool shuffled = p.store == MCQ_STORE_SHUFFLE_NHWC;
   if (direct_ok && ((p.store == MCQ_STORE_NHWC && p.cout % 16 == 0) || (shuffled && (p.cout >> 2) % 16 == 0))) {
     int n, oy, ox;
@@ -436,6 +756,23 @@ __device__ __forceinline__ void drain_tile(const ConvArgs& p, uint32_t t_acc, in
   }
 }
 
+// DRAIN (chosen by the host, drain_kind() in mcq_api.cu): each variant is a separate kernel instantiation -- two drains in
+// one kernel do not fit its 96 registers per thread.
+template <int PASSES, bool GN = false, int DRAIN = DRAIN_ROWS, class PixFn>
+__device__ __forceinline__ void drain_tile(const ConvArgs& p, const OutMaps* om, uint32_t t_acc, int bn, int ct, int cg,
+                                           int q, int lane, uint32_t stage, PixFn pix, const float* bias_src,
+                                           const float wscale) {
+  if constexpr (DRAIN == DRAIN_QUAD) {
+    static_assert(!GN, "the GroupNorm-statistics drain is row-per-lane");
+    drain_tile_quad<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, wscale);
+  } else if constexpr (DRAIN == DRAIN_TMA) {
+    static_assert(!GN, "the GroupNorm-statistics drain stores from registers");
+    drain_tile_tma<PASSES>(p, om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, wscale);
+  } else {
+    drain_tile_rows<PASSES, GN>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, wscale);
+  }
+}
+
 // The fp32 operands of the fused epilogue (residuals, GDN/gate operand) were written two or more launches ago and
 // have left L2 at batch 64.  A drain warp reads them 32 B per lane with the loads right in front of their use, so one
 // SM has ~16 KB in flight against ~1 us of DRAM latency: 16 GB/s per SM, a third of its HBM share.  Requesting the
@@ -461,11 +798,11 @@ __device__ __forceinline__ void prefetch_epilogue_operands(const ConvArgs& p, in
 }
 
 // ---------------------------------------------------------------- kernel
-template <int PASSES>
+template <int PASSES, int DRAIN = DRAIN_ROWS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const ConvArgs p) {
+               const ConvArgs p, const __grid_constant__ OutMaps om) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16 B aligned: round up to the 1024 B the 128B swizzle needs
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -484,7 +821,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * stages + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * stages + 2 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + stage_bytes * stages + 8u * (2 * stages + 4));
-  const uint32_t epi_base = (bar_base + 8u * (2 * stages + 4) + 16u + 127u) & ~127u;   // 16 x 2 KB transpose buffers
+  const uint32_t epi_base = (bar_base + 8u * (2 * stages + 4) + 16u + 511u) & ~511u;   // 16 x 2 KB staging buffers (512 B: swizzle period)
   float* bias_smem = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + TC_EPI_WARPS * TC_EPI_STAGE_BYTES);
   const bool bias_staged = (p.mode != EPI_ARGMIN) && (p.cout <= TC_BIAS_SMEM_FLOATS);
   if (bias_staged)
@@ -655,10 +992,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(tfull_bar(buf), use & 1u, 4, p.wait_sleep_ns);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, wscale);
+      drain_tile<PASSES, false, DRAIN>(p, &om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, wscale);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+    if constexpr (DRAIN == DRAIN_TMA) {
+      if (lane == 0) bulk_wait_all();          // this lane's bulk stores have left shared memory and are complete
     }
   }
 

@@ -68,7 +68,9 @@ EncodeTiledFn get_encode_fn() {
 // mcq_set_option() call (tools/ and tests use it for A/B measurements); nothing on the launch path reads the environment.
 struct Option { const char* name; int value; };
 Option g_options[] = {
-    {"direct_epi", 1},        // transpose-free drain: 1 = every NHWC / PixelShuffle store, 2 = plane-only outputs, 0 = never
+    {"direct_epi", 3},        // drain (drain_kind()): 3 = bulk-tensor stores for large launches, else direct; 5 = bulk-tensor
+                              // stores wherever they apply; 4 = quad layout wherever it applies; 1 = direct (row per lane)
+                              // for every NHWC / PixelShuffle store, 2 = direct for plane-only outputs, 0 = smem-transposed
     {"wait_sleep_ns", 0},     // nanosleep between mbarrier polls of the producer / drain warps
     {"tc_spread", 33},        // conv_tc: narrow the N tile until this % of the SMs have a tile
     {"pdl", 1},               // programmatic dependent launch
@@ -96,6 +98,59 @@ int pow2_ceil(int v) {
   int r = 1;
   while (r < v) r <<= 1;
   return r;
+}
+
+// Which drain a tensor-core convolution launch runs (conv_tc.cuh; one kernel instantiation per kind).  `work_per_cta`:
+// tiles each CTA walks -- a launch with less than two is latency-bound (small maps) and keeps the plain drain, whose
+// stores need no staging round trip and no bulk-group wait before the kernel can end.
+//   direct_epi = 3 (default): DRAIN_TMA for large launches that can take it;  5: DRAIN_TMA wherever it applies;
+//   4: DRAIN_QUAD wherever it applies;  0 / 1 / 2: DRAIN_ROWS (see the option table)
+int drain_kind(const ConvArgs& a, long long work_per_cta) {
+  if (a.direct_epilogue < 3 || a.mode == EPI_ARGMIN || a.gn_ws) return DRAIN_ROWS;
+  const int cper = a.store == MCQ_STORE_NHWC ? a.cout : (a.store == MCQ_STORE_SHUFFLE_NHWC ? a.cout >> 2 : 0);
+  if (cper == 0) return DRAIN_ROWS;
+  if (a.direct_epilogue == 4) return (a.bn % 32 == 0 && cper % 32 == 0) ? DRAIN_QUAD : DRAIN_ROWS;
+  if (a.bn % 16 != 0 || cper % 16 != 0) return DRAIN_ROWS;
+  if (a.direct_epilogue == 3 && work_per_cta < 2) return DRAIN_ROWS;
+  return DRAIN_TMA;
+}
+
+// TMA-store view of one output tensor for DRAIN_TMA: 5-D {channels, W, 1 | sub-pixel row, H, N} over the conv's output
+// grid, box = 16 channels x the 32 consecutive tile rows of one drain warp (tile rows run x, then y, then n)
+int encode_out_map(CUtensorMap* map, const void* ptr, bool f32, const ConvArgs& a) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MCQ_ERR_DRIVER;
+  const cuuint64_t es = f32 ? 4 : 2;
+  const int bw = a.tw < 32 ? a.tw : 32;
+  const int bh = a.th < 32 / bw ? a.th : 32 / bw;
+  const int bnn = 32 / (bw * bh);
+  cuuint64_t dims[5], strides[4];
+  if (a.store == MCQ_STORE_NHWC) {
+    const cuuint64_t c = (cuuint64_t)a.cout, w = (cuuint64_t)a.wout, h = (cuuint64_t)a.hout;
+    dims[0] = c; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = (cuuint64_t)a.n;
+    strides[0] = c * es; strides[1] = w * c * es; strides[2] = w * c * es; strides[3] = h * w * c * es;
+  } else {
+    // PixelShuffle: GEMM column (2i + j) * cq + c of conv pixel (oy, ox) is channel c of output pixel (2 oy + i, 2 ox + j)
+    const cuuint64_t cq = (cuuint64_t)(a.cout >> 2), w = (cuuint64_t)a.wout, h = (cuuint64_t)a.hout, w2 = 2 * w;
+    dims[0] = 2 * cq; dims[1] = w; dims[2] = 2; dims[3] = h; dims[4] = (cuuint64_t)a.n;
+    strides[0] = 2 * cq * es; strides[1] = w2 * cq * es; strides[2] = 2 * w2 * cq * es; strides[3] = 2 * h * w2 * cq * es;
+  }
+  cuuint32_t box[5] = {16u, (cuuint32_t)bw, 1u, (cuuint32_t)bh, (cuuint32_t)bnn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MCQ_ERR_DRIVER;
+}
+int encode_out_maps(OutMaps& om, const ConvArgs& a) {
+  int rc = 0;
+  if (a.out_f32) rc = encode_out_map(&om.f32, a.out_f32, true, a);
+  if (!rc && a.o0_hi) rc = encode_out_map(&om.o0_hi, a.o0_hi, false, a);
+  if (!rc && a.o0_lo) rc = encode_out_map(&om.o0_lo, a.o0_lo, false, a);
+  if (!rc && a.o1_hi) rc = encode_out_map(&om.o1_hi, a.o1_hi, false, a);
+  if (!rc && a.o1_lo) rc = encode_out_map(&om.o1_lo, a.o1_lo, false, a);
+  return rc;
 }
 
 struct TcPlan {
@@ -302,7 +357,7 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   fill_taps(a);
   // ---- pipeline depth
   const size_t stage_bytes = (size_t)(TC_A_BYTES + bn * TC_BK * 2) * (a.passes == 3 ? 2 : 1);
-  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + TC_BIAS_SMEM_FLOATS * 4;
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 512 + TC_BIAS_SMEM_FLOATS * 4;
   // 227 KB of dynamic smem per CTA: 1 KB alignment slack, 256 B barriers, epilogue staging, the rest = pipeline
   int stages = (int)((227 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
@@ -339,15 +394,29 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   cfg.attrs = at;
   cfg.numAttrs = opt("pdl") ? 1 : 0;
   EvScope ev(st);
-  if (a.passes == 3) {
-    e = ensure_dyn_smem<KTag<103>>(conv_tc_kernel<3>, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
-  } else {
-    e = ensure_dyn_smem<KTag<101>>(conv_tc_kernel<1>, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, a);
+  OutMaps om;
+  std::memset(&om, 0, sizeof(om));
+  const int drain = drain_kind(a, total_tiles / grid);
+  if (drain == DRAIN_TMA) {
+    rc = encode_out_maps(om, a);
+    if (rc) return rc;
   }
+#define MCQ_LAUNCH_TC(P, D, TAG)                                                                    \
+  do {                                                                                              \
+    e = ensure_dyn_smem<KTag<TAG>>(conv_tc_kernel<P, D>, 227 * 1024);                                \
+    if (e != cudaSuccess) return (int)e;                                                            \
+    e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<P, D>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, a, om);       \
+  } while (0)
+  if (a.passes == 3) {
+    if (drain == DRAIN_TMA) MCQ_LAUNCH_TC(3, DRAIN_TMA, 123);
+    else if (drain == DRAIN_QUAD) MCQ_LAUNCH_TC(3, DRAIN_QUAD, 113);
+    else MCQ_LAUNCH_TC(3, DRAIN_ROWS, 103);
+  } else {
+    if (drain == DRAIN_TMA) MCQ_LAUNCH_TC(1, DRAIN_TMA, 121);
+    else if (drain == DRAIN_QUAD) MCQ_LAUNCH_TC(1, DRAIN_QUAD, 111);
+    else MCQ_LAUNCH_TC(1, DRAIN_ROWS, 101);
+  }
+#undef MCQ_LAUNCH_TC
   g_launches++;
   return e == cudaSuccess ? cuda_status() : (int)e;
 }
@@ -359,11 +428,11 @@ bool halo_supported(const ConvArgs& a) {
          a.cout_pad % 16 == 0;
 }
 
-template <int PASSES, int CL>
+template <int PASSES, int CL, int DRAIN = DRAIN_ROWS>
 int launch_halo_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t smem, int grid, cudaStream_t st) {
-  auto kern = conv_halo_kernel<PASSES, CL>;
+  auto kern = conv_halo_kernel<PASSES, CL, DRAIN>;
   {
-    cudaError_t e = ensure_dyn_smem<KTag<200 + PASSES * 10 + CL>>(kern, 227 * 1024);
+    cudaError_t e = ensure_dyn_smem<KTag<200 + PASSES * 10 + CL + DRAIN * 50>>(kern, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
   }
   cudaLaunchConfig_t cfg{};
@@ -413,7 +482,7 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
   hp.tps = opt("halo_tps") ? opt("halo_tps") : (a.passes == 3 ? 1 : 3);
   if (hp.tps != 1 && hp.tps != 3) return MCQ_ERR_BAD_ARG;
   const size_t b_stage = (size_t)bn * TC_BK * 2 * np * hp.tps;
-  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + TC_BIAS_SMEM_FLOATS * 4;
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 512 + TC_BIAS_SMEM_FLOATS * 4;
   const size_t budget = 227 * 1024 - 1024 - 256 - epi_bytes;
   a.debug_skip_store = opt("epi_skip");
   hp.na = (a.passes == 3) ? 2 : 3;
@@ -461,21 +530,24 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
   const int grid = clusters * cl;
   if (a.passes == 3) {
     if (cl == 1) return launch_halo_t<3, 1>(a, hp, maps, smem, grid, st);
-    if (cl == 2) return launch_halo_t<3, 2>(a, hp, maps, smem, grid, st);
+    if (cl == 2) return drain_kind(a, 2) == DRAIN_QUAD ? launch_halo_t<3, 2, DRAIN_QUAD>(a, hp, maps, smem, grid, st)
+                                                       : launch_halo_t<3, 2>(a, hp, maps, smem, grid, st);
     return launch_halo_t<3, 4>(a, hp, maps, smem, grid, st);
   }
   if (cl == 1) return launch_halo_t<1, 1>(a, hp, maps, smem, grid, st);
-  if (cl == 2) return launch_halo_t<1, 2>(a, hp, maps, smem, grid, st);
+  if (cl == 2) return drain_kind(a, 2) == DRAIN_QUAD ? launch_halo_t<1, 2, DRAIN_QUAD>(a, hp, maps, smem, grid, st)
+                                                     : launch_halo_t<1, 2>(a, hp, maps, smem, grid, st);
   return launch_halo_t<1, 4>(a, hp, maps, smem, grid, st);
 }
 
 
 // ---- CTA-pair kernel (tcgen05.mma.cta_group::2): 3x3 stride-1 convs with a 128-column N tile
-template <int PASSES, bool GN = false>
-int launch_pair_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t smem, int grid, cudaStream_t st) {
-  auto kern = conv_pair_kernel<PASSES, GN>;
+template <int PASSES, bool GN = false, int DRAIN = DRAIN_ROWS>
+int launch_pair_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t smem, int grid, cudaStream_t st,
+                  const OutMaps& om) {
+  auto kern = conv_pair_kernel<PASSES, GN, DRAIN>;
   {
-    cudaError_t e = ensure_dyn_smem<KTag<300 + PASSES * 10 + (GN ? 1 : 0)>>(kern, 227 * 1024);
+    cudaError_t e = ensure_dyn_smem<KTag<300 + PASSES * 10 + (GN ? 1 : 0) + DRAIN * 2>>(kern, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
   }
   cudaLaunchConfig_t cfg{};
@@ -493,7 +565,7 @@ int launch_pair_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t sme
   cfg.attrs = at;
   cfg.numAttrs = opt("pdl") ? 2 : 1;
   EvScope ev(st);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], a, hp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], a, hp, om);
   g_launches++;
   return e == cudaSuccess ? cuda_status() : (int)e;
 }
@@ -521,7 +593,7 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
   const size_t a_buf = (size_t)hp.a_bytes * np;
   const size_t b_plane = (size_t)bn * TC_BK * 2;
   const size_t b_stage = (a.passes == 3 ? b_plane + b_plane / 2 : b_plane / 2) * hp.tps;
-  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 + TC_BIAS_SMEM_FLOATS * 4;
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 512 + TC_BIAS_SMEM_FLOATS * 4;
   const size_t budget = 227 * 1024 - 1024 - 256 - epi_bytes;
   a.debug_skip_store = opt("epi_skip");
   hp.na = (a.passes == 3) ? 2 : 3;
@@ -583,12 +655,25 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
     clusters = hp.per_ct * a.tiles_c;
   }
   const int grid = clusters * 2;
+  OutMaps om;
+  std::memset(&om, 0, sizeof(om));
   if (a.gn_ws) {   // GroupNorm partials: the instantiation whose drain also reduces (sum, sum^2) per row block
-    if (a.passes == 3) return launch_pair_t<3, true>(a, hp, maps, smem, grid, st);
-    return launch_pair_t<1, true>(a, hp, maps, smem, grid, st);
+    if (a.passes == 3) return launch_pair_t<3, true>(a, hp, maps, smem, grid, st, om);
+    return launch_pair_t<1, true>(a, hp, maps, smem, grid, st, om);
   }
-  if (a.passes == 3) return launch_pair_t<3>(a, hp, maps, smem, grid, st);
-  return launch_pair_t<1>(a, hp, maps, smem, grid, st);
+  const int drain = drain_kind(a, work / clusters);
+  if (drain == DRAIN_TMA) {
+    rc = encode_out_maps(om, a);
+    if (rc) return rc;
+    if (a.passes == 3) return launch_pair_t<3, false, DRAIN_TMA>(a, hp, maps, smem, grid, st, om);
+    return launch_pair_t<1, false, DRAIN_TMA>(a, hp, maps, smem, grid, st, om);
+  }
+  if (drain == DRAIN_QUAD) {
+    if (a.passes == 3) return launch_pair_t<3, false, DRAIN_QUAD>(a, hp, maps, smem, grid, st, om);
+    return launch_pair_t<1, false, DRAIN_QUAD>(a, hp, maps, smem, grid, st, om);
+  }
+  if (a.passes == 3) return launch_pair_t<3>(a, hp, maps, smem, grid, st, om);
+  return launch_pair_t<1>(a, hp, maps, smem, grid, st, om);
 }
 
 // ---- layer chain (conv_chain.cuh): `count` dependent convolutions on small maps in one persistent launch
@@ -790,8 +875,22 @@ int mcq_stem_conv_tc(const void* x, int32_t x_is_u8, int32_t n, int32_t h, int32
   s.h = h; s.w = w; s.pad_top = pad_top; s.pad_left = pad_left; s.hp = hp; s.wp = wp; s.cout_pad = cout_pad;
   const long long total_pix = (long long)n * a.hout * a.wout;
   const long long tiles = (total_pix + STC_BM - 1) / STC_BM;
-  const size_t smem = 1024 + 2 * STC_A_BYTES + 16384 + 128 + (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 * 4 + 256 * 4 + 64;
-  cudaError_t e = ensure_dyn_smem<KTag<800>>(stem_tc_kernel, smem);
+  const size_t smem = 1024 + 2 * STC_A_BYTES + 16384 + 512 + (size_t)TC_EPI_WARPS * TC_EPI_STAGE_BYTES + 128 * 4 + 256 * 4 + 64;
+  const long long per_cta = tiles / (tiles < num_sms() ? tiles : num_sms());
+  int drain = drain_kind(a, per_cta);
+  if (drain == DRAIN_TMA && total_pix >= 0x7fffffffLL) drain = DRAIN_ROWS;
+  OutMaps om;
+  std::memset(&om, 0, sizeof(om));
+  if (drain == DRAIN_TMA) {
+    // the stem's tile is 128 consecutive pixels of the flattened [n, y, x] grid: view the outputs as [pixels, channels]
+    ConvArgs v = a;
+    v.wout = (int)total_pix; v.hout = 1; v.n = 1; v.tw = 32; v.th = 1; v.tn = 4;
+    const int rc = encode_out_maps(om, v);
+    if (rc) return rc;
+  }
+  cudaError_t e = drain == DRAIN_TMA    ? ensure_dyn_smem<KTag<802>>(stem_tc_kernel<DRAIN_TMA>, smem)
+                  : drain == DRAIN_QUAD ? ensure_dyn_smem<KTag<801>>(stem_tc_kernel<DRAIN_QUAD>, smem)
+                                        : ensure_dyn_smem<KTag<800>>(stem_tc_kernel<DRAIN_ROWS>, smem);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()));
@@ -803,7 +902,9 @@ int mcq_stem_conv_tc(const void* x, int32_t x_is_u8, int32_t n, int32_t h, int32
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = opt("pdl") ? 1 : 0;
-  e = cudaLaunchKernelEx(&cfg, stem_tc_kernel, a, s);
+  e = drain == DRAIN_TMA    ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<DRAIN_TMA>, a, s, om)
+      : drain == DRAIN_QUAD ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<DRAIN_QUAD>, a, s, om)
+                            : cudaLaunchKernelEx(&cfg, stem_tc_kernel<DRAIN_ROWS>, a, s, om);
   g_launches++;
   return e == cudaSuccess ? cuda_status() : (int)e;
 }

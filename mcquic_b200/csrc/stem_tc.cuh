@@ -45,7 +45,9 @@ __device__ __forceinline__ int stem_reflect(int i, int n) {
   return i;
 }
 
-__global__ void __launch_bounds__(STC_THREADS, 1) stem_tc_kernel(const ConvArgs p, const StemTcArgs s) {
+template <int DRAIN>
+__global__ void __launch_bounds__(STC_THREADS, 1) stem_tc_kernel(const ConvArgs p, const StemTcArgs s,
+                                                                 const __grid_constant__ OutMaps om) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) stem_tc_kernel(const ConvArgs 
   auto tfull = [&](int i) { return bar_base + 8u * (4 + i); };
   auto tempty = [&](int i) { return bar_base + 8u * (6 + i); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 64u);
-  const uint32_t epi_base = bar_base + 128u;                                          // 16 x 2 KB drain staging
+  const uint32_t epi_base = bar_base + 512u;                                          // 16 x 2 KB drain staging (512 B aligned)
   float* bias_smem = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + TC_EPI_WARPS * TC_EPI_STAGE_BYTES);
 
   float* u8_lut = bias_smem + 128;                                                    // 256 floats
@@ -222,6 +224,11 @@ __global__ void __launch_bounds__(STC_THREADS, 1) stem_tc_kernel(const ConvArgs 
       const long long f0 = (long long)t * STC_BM;
       auto pix = [&](int row, int& n, int& oy, int& ox) {
         const long long f = f0 + row;
+        if constexpr (DRAIN == DRAIN_TMA) {
+          // bulk-store drain: the output is viewed as [pixels, channels] (host: total_pix < 2^31), "x" = flat pixel index
+          n = 0; oy = 0; ox = (int)f;
+          return f < total_pix;
+        }
         const long long fc = f < total_pix ? f : 0;
         n = (int)(fc / hw_out);
         const int rem = (int)(fc - (long long)n * hw_out);
@@ -232,10 +239,13 @@ __global__ void __launch_bounds__(STC_THREADS, 1) stem_tc_kernel(const ConvArgs 
       mbar_wait(tfull(ab), ((uint32_t)(i >> 1)) & 1u, 44);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
-      drain_tile<3>(p, t_acc, bn, 0, cg, q, lane, stage, pix, bias_smem, effective_w_scale(p));
+      drain_tile<3, false, DRAIN>(p, &om, t_acc, bn, 0, cg, q, lane, stage, pix, bias_smem, effective_w_scale(p));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(ab));
+    }
+    if constexpr (DRAIN == DRAIN_TMA) {
+      if (lane == 0) bulk_wait_all();
     }
   }
 

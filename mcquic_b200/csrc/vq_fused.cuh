@@ -59,16 +59,12 @@ struct VqFusedArgs {
   int halves;                // codebook stages per 128-codeword chunk: 1, or 2 (half rows) for d = 128
 };
 
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// (fence_async_smem, bulk_commit, bulk_wait_read, bulk_wait_all: conv_tc.cuh)
 // Wait for warps that are off the critical path (codebook stream, MMA issue, latent producer): between polls the warp
 // sleeps, so its spin loop does not take issue slots from the drain warps sharing its scheduler (ncu: 45 % of all
 // executed instructions were wait loops before this).  Same 4 s watchdog as mbar_wait.

@@ -438,7 +438,11 @@ class Engine:
                 out.gn = (part, rb.value, unit.value)
                 keep.append(part)
         info = {"flops": 2.0 * x.n * (x.h // pc.stride) * (x.w // pc.stride) * pc.cout * pc.cin * pc.ksize ** 2,
-                "passes": p.passes, "impl": p.impl, "shape": (x.n, x.h, x.w, pc.cin, pc.cout, pc.ksize, pc.stride)}
+                "passes": p.passes, "impl": p.impl, "shape": (x.n, x.h, x.w, pc.cin, pc.cout, pc.ksize, pc.stride),
+                # epilogue kind of the launch (profiling only): mode, fp32 output, residual / aux operands, plane pairs
+                "epi": f"m{mode}{'F' if out.f32 is not None else ''}{'R' if res1 is not None else ''}"
+                       f"{'r' if res2 is not None else ''}{'A' if aux is not None else ''}"
+                       f"P{sum(t is not None for t in (out.raw, out.silu, out.sq))}"}
         # everything the launch touches stays referenced until it has been issued (a freed block could otherwise be
         # handed to a later layer of the same chain, whose clusters do not run in lock step)
         item = (p, (keep, out, pc, into), info)

@@ -78,6 +78,41 @@ def test_weight_stationary_pair_kernel():
     _check("tcgen05", passes=1, want=("raw",), n=2, h=16, w=24, cin=128, cout=256)
 
 
+@pytest.fixture
+def drain_option(request):
+    old = _lib.get_option("direct_epi")
+    _lib.set_option("direct_epi", request.param)
+    yield request.param
+    _lib.set_option("direct_epi", old)
+
+
+@pytest.mark.parametrize("passes", [3, 1])
+@pytest.mark.parametrize("drain_option", [1, 4, 5], indirect=True,
+                         ids=["rows", "quad-everywhere", "bulk-store-everywhere"])
+def test_drain_variants(drain_option, passes):
+    """every drain (csrc/conv_tc.cuh: row-per-lane global stores, quad layout, bulk-tensor stores through shared memory),
+    forced onto every launch that can take it -- the default only picks the bulk-store drain for large launches: ragged
+    and tiny maps (boxes clipped at image borders, boxes spanning images), PixelShuffle stores, stride 2, every epilogue
+    mode, two plane pairs, both residual operands"""
+    base = dict(n=2, h=16, w=16, cin=128, cout=128, passes=passes)
+    _check("tcgen05", want=("f32", "silu"), use_res1=True, n=24, h=64, w=64, cin=128, cout=128, passes=passes)
+    _check("tcgen05", want=("f32", "silu"), use_res1=True, n=3, h=40, w=24, cin=128, cout=128, passes=passes)   # ragged
+    _check("tcgen05", want=("silu",), n=2, h=24, w=40, cin=128, cout=128, passes=passes)
+    _check("tcgen05", want=("f32", "raw"), use_res1=True, n=5, h=4, w=4, cin=128, cout=128, passes=passes)     # 8 images / tile
+    _check("tcgen05", want=("f32",), n=3, h=2, w=2, cin=128, cout=128, passes=passes)
+    _check("tcgen05", want=("f32", "silu"), n=3, h=6, w=12, cin=128, cout=128, passes=passes)
+    _check("tcgen05", want=("f32", "sq"), n=2, h=32, w=32, cin=128, cout=128, stride=2, passes=passes)
+    _check("tcgen05", want=("f32", "sq"), n=20, h=32, w=32, cin=128, cout=512, store=_lib.STORE_SHUFFLE_NHWC, passes=passes)
+    _check("tcgen05", want=("f32", "sq"), n=1, h=10, w=12, cin=128, cout=512, store=_lib.STORE_SHUFFLE_NHWC, passes=passes)
+    _check("tcgen05", want=("f32", "silu"), ksize=1, mode=_lib.EPI_GATE, **base)
+    _check("tcgen05", want=("raw",), ksize=1, mode=_lib.EPI_GDN, **base)
+    _check("tcgen05", want=("raw",), ksize=1, mode=_lib.EPI_IGDN, **base)
+    _check("tcgen05", want=("f32", "raw"), use_res1=True, res1_scale=-1.0, use_res2=True, **base)
+    _check("tcgen05", want=("silu", "sq"), **base)
+    _check("tcgen05", want=("f32",), n=2, h=16, w=16, cin=192, cout=192, passes=passes)        # halo kernel (rows / quad)
+    _check("tcgen05", want=("raw",), n=2, h=16, w=24, cin=128, cout=256, passes=passes)
+
+
 PARTIAL_CHUNK_SHAPES = [
     # channel counts the 64-channel K chunk does not divide (Neon's 8 / 32-channel nets): the last chunk is zero-filled
     # by TMA beyond the tensor's channel extent; stride 1 only

@@ -22,8 +22,18 @@ def _planes_value(pl):
 @pytest.mark.parametrize("n,h,w,cout", [(2, 256, 256, 128), (1, 150, 333, 64), (3, 64, 64, 32), (1, 100, 72, 128),
                                         (1, 128, 128, 192)])
 @pytest.mark.parametrize("u8", [False, True])
-@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("tc", [True, False, "bulk-store", "quad"])
 def test_stem_matches_fp64(n, h, w, cout, u8, tc):
+    # tc = "bulk-store" / "quad": the tcgen05 kernel with that drain forced (the default takes the bulk-store drain for
+    # large batches only; csrc/conv_tc.cuh)
+    drain = {"bulk-store": 5, "quad": 4}.get(tc)
+    if drain is not None:
+        old = _lib.get_option("direct_epi")
+        _lib.set_option("direct_epi", drain)
+        try:
+            return test_stem_matches_fp64(n, h, w, cout, u8, True)
+        finally:
+            _lib.set_option("direct_epi", old)
     conv = conv3x3(3, cout, 2)
     with torch.no_grad():
         conv.weight.copy_(uniform(tuple(conv.weight.shape), "stem.w", 1) / 27 ** 0.5)

@@ -9,7 +9,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 from convcase import make_planes  # noqa: E402
+from mcquic_b200 import _lib  # noqa: E402
 from mcquic_b200.engine import Act, Engine, pack_conv  # noqa: E402
+
+_lib.apply_options(os.environ.get("MCQ_OPTIONS", ""))   # e.g. MCQ_OPTIONS=direct_epi=1 (applied here through mcq_set_option)
 
 eng = Engine("tcgen05")
 g = torch.Generator().manual_seed(0)
