@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) conv_chain_kernel(const __gr
         tc_fence_after();
         if (cp.dbg && blockIdx.x == 0 && threadIdx.x == 64 && it < 256) cp.dbg[2048 + 2 * it] = clock64();
         const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * ACC_STRIDE;
-        drain_tile<PASSES>(p, nullptr, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, effective_w_scale(p));
+        drain_tile<PASSES>(p, nullptr, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, effective_w_scale(p), []() {});
         if (cp.dbg && blockIdx.x == 0 && threadIdx.x == 64 && it < 256) cp.dbg[2048 + 2 * it + 1] = clock64();
         tc_fence_before();
         __syncwarp();

@@ -311,7 +311,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       mbar_wait(tfull_bar(buf), use & 1u, 16, p.wait_sleep_ns);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES, false, DRAIN>(p, nullptr, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, effective_w_scale(p));
+      drain_tile<PASSES, false, DRAIN>(p, nullptr, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, effective_w_scale(p), []() {});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));

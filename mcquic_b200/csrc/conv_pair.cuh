@@ -63,11 +63,16 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
       ::"r"(bar), "h"(mask)
       : "memory");
 }
+// Arrive on the same barrier in CTA `cta` of the cluster.  Default semantics (.release at CTA scope), NOT .release.cluster:
+// the latter compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive -- every drain warp of the peer CTA then waits, once
+// per tile, until all its outstanding global stores are visible device-wide (ncu source view: the hottest non-wait
+// instructions of the peer's drain).  What the arrive has to order is tensor-memory traffic -- tcgen05.wait::ld before it in
+// program order, tcgen05.fence::before_thread_sync / ::after_thread_sync around the barrier -- not global memory.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(local_bar), "r"(cta)
       : "memory");
 }
@@ -312,11 +317,24 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       };
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
-      prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
-      mbar_wait(tfull_bar(buf), use & 1u, 26, p.wait_sleep_ns);
-      tc_fence_after();
+      // L2 prefetch of the fp32 operands: this tile's on the first trip, from then on the NEXT tile's (a whole tile of lead)
+      if (it == 0) prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
+      if (it + 1 < my_work) {
+        int ct2, x2, y2, n2;
+        decode_tile(work_item(it + 1), ct2, x2, y2, n2);
+        prefetch_epilogue_operands(p, bn, ct2, cg, q, lane, [&](int row, int& n, int& oy, int& ox) {
+          ox = x2 + (row & (HALO_TW - 1));
+          oy = y2 + (row >> 3);
+          n = n2;
+          return (ox < p.wout) && (oy < p.hout) && (n < p.n);
+        });
+      }
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES, GN, DRAIN>(p, &om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, effective_w_scale(p));
+      drain_tile<PASSES, GN, DRAIN>(p, &om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias,
+                                    effective_w_scale(p), [&]() {
+                                      mbar_wait(tfull_bar(buf), use & 1u, 26, p.wait_sleep_ns);
+                                      tc_fence_after();
+                                    });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

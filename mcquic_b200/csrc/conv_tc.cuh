@@ -374,10 +374,10 @@ __device__ __forceinline__ void drain_tile_quad(const ConvArgs& p, uint32_t t_ac
 // 16 channels x 32 pixels box.  The buffer is single: a store must have been read out (wait_group.read) before the next
 // batch is staged -- by then the warp has spent a batch's worth of math.  Image borders and phantom tiles need no
 // masking: the TMA clips the box.
-template <int PASSES, class PixFn>
+template <int PASSES, class PixFn, class WaitFn>
 __device__ __forceinline__ void drain_tile_tma(const ConvArgs& p, const OutMaps* om, uint32_t t_acc, int bn, int ct, int cg,
                                                int q, int lane, uint32_t stage, PixFn pix, const float* bias_src,
-                                               const float wscale) {
+                                               const float wscale, WaitFn wait_accumulator) {
   constexpr bool FAST = PASSES == 1;
   const bool shuffled = p.store == MCQ_STORE_SHUFFLE_NHWC;
   int n, oy, ox;
@@ -391,124 +391,152 @@ __device__ __forceinline__ void drain_tile_tma(const ConvArgs& p, const OutMaps*
   const uint32_t row32 = stage + (uint32_t)lane * 32u;               // fp16: 32 B per row, chunk c at c ^ ((row >> 2) & 1)
   const uint32_t sw32 = (uint32_t)((lane >> 2) & 1);
   const bool skip = p.debug_skip_store != 0;
-  for (int cc = cg * 32; cc < bn; cc += 128) {
+  const float* src1 = (p.mode == MCQ_EPI_LINEAR || p.mode == MCQ_EPI_GATE) ? p.res1 : nullptr;
+  const float* src2 = (p.mode == MCQ_EPI_LINEAR) ? p.res2 : p.aux;
+  // this warp's 16-column batches: b -> first column (batches 2i, 2i + 1 are the halves of its i-th 32-column chunk)
+  auto col_of = [&](int b) { return cg * 32 + (b >> 1) * 128 + (b & 1) * 16; };
+  auto live = [&](int b) { const int c = col_of(b); return c < bn && ct * bn + c < p.cout; };   // warp-uniform, monotone
+  auto off_of = [&](int b) {
+    const int c0 = ct * bn + col_of(b);
+    return shuffled ? epilogue_offset(p, n, oy, ox, c0) : pixoff + c0;
+  };
+  // The fp32 operands of a batch are requested one batch ahead, into the registers the previous batch has just consumed:
+  // batch 0's before the accumulator wait, batch b + 1's as soon as batch b has added its operands -- its activation math
+  // and its staging then run while the loads are in flight.
+  // (one operand is requested ahead: the residual, or the GDN / IGDN operand.  Launches with two -- the attention gate,
+  // `z - dequant + side` -- load the second one where it is used: 16 more live registers would spill the tile loop's state,
+  // and a spill reload costs an L2 round trip here, the whole L1 being carved out as shared memory)
+  const float* ahead = src1 ? src1 : src2;
+  const float* late = src1 ? src2 : nullptr;
+  float o1[16];
+  auto request = [&](int b) {
+    if (!ok || !ahead) return;
+    const size_t off = off_of(b);
+    ld_global_256(ahead + off, o1);
+    ld_global_256(ahead + off + 8, o1 + 8);
+  };
+  if (live(0)) request(0);
+  wait_accumulator();
+#pragma unroll 1
+  for (int b = 0; live(b); ++b) {
+    const int col0 = col_of(b);
+    const int c0 = ct * bn + col0;
+    int cx = c0, cz = 0;                                             // channel / sub-pixel-row coordinates of the box
+    if (shuffled) {
+      const int cq = p.cout >> 2, sub = c0 / cq;
+      cx = (sub & 1) * cq + (c0 - sub * cq);
+      cz = sub >> 1;
+    }
+    uint32_t r[16];
+    float y[16];
+    tmem_ld16(t_acc + (uint32_t)col0, r);
+    if (PASSES == 3) {
+      uint32_t l[16];
+      tmem_ld16(t_acc + (uint32_t)(bn + col0), l);
+      tmem_ld_wait();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int col0 = cc + half * 16;
-      if (col0 >= bn) break;
-      const int c0 = ct * bn + col0;
-      if (c0 >= p.cout) break;                                       // warp-uniform
-      const size_t off = shuffled ? epilogue_offset(p, n, oy, ox, c0) : pixoff + c0;
-      int cx = c0, cz = 0;                                           // channel / sub-pixel-row coordinates of the box
-      if (shuffled) {
-        const int cq = p.cout >> 2, sub = c0 / cq;
-        cx = (sub & 1) * cq + (c0 - sub * cq);
-        cz = sub >> 1;
-      }
-      uint32_t r[16];
-      float y[16];
-      tmem_ld16(t_acc + (uint32_t)col0, r);
-      float o1[16], o2[16];
-      const float* src1 = (p.mode == MCQ_EPI_LINEAR || p.mode == MCQ_EPI_GATE) ? p.res1 : nullptr;
-      const float* src2 = (p.mode == MCQ_EPI_LINEAR) ? p.res2 : p.aux;
-      if (ok && src1) { ld_global_256(src1 + off, o1); ld_global_256(src1 + off + 8, o1 + 8); }
-      if (ok && src2) { ld_global_256(src2 + off, o2); ld_global_256(src2 + off + 8, o2 + 8); }
-      if (PASSES == 3) {
-        uint32_t l[16];
-        tmem_ld16(t_acc + (uint32_t)(bn + col0), l);
-        tmem_ld_wait();
+      for (int j = 0; j < 16; ++j) y[j] = fmaf(__uint_as_float(l[j]), kLoInv, __uint_as_float(r[j]));
+    } else {
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) y[j] = fmaf(__uint_as_float(l[j]), kLoInv, __uint_as_float(r[j]));
-      } else {
-        tmem_ld_wait();
+      for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
+    }
+    {
+      float bb[16];
+      load_f32v<16>(bias_src, c0, bb);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]);
-      }
-      {
-        float b[16];
-        load_f32v<16>(bias_src, c0, b);
+      for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], wscale, bb[j]);
+    }
+    if (ok) {                                                        // rows outside the image: values unused (clipped)
+      if (p.mode == MCQ_EPI_LINEAR) {
+        if (src1) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], wscale, b[j]);
-      }
-      if (ok) {                                                      // rows outside the image: values unused (clipped)
-        if (p.mode == MCQ_EPI_LINEAR) {
-          if (src1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] = y[j] + p.res1_scale * o1[j];
-          }
-          if (src2) {
+          for (int j = 0; j < 16; ++j) y[j] = y[j] + p.res1_scale * o1[j];
+          if (late) {
+            float o2[16];
+            const size_t off = off_of(b);
+            ld_global_256(late + off, o2);
+            ld_global_256(late + off + 8, o2 + 8);
 #pragma unroll
             for (int j = 0; j < 16; ++j) y[j] = y[j] + o2[j];
           }
-        } else if (p.mode == MCQ_EPI_GATE) {
+        } else if (ahead) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) y[j] = o2[j] * sigmoid_f<FAST>(y[j]) + o1[j];
-        } else if (p.mode == MCQ_EPI_GDN) {
+          for (int j = 0; j < 16; ++j) y[j] = y[j] + o1[j];
+        }
+      } else if (p.mode == MCQ_EPI_GATE) {
+        float o2[16];
+        const size_t off = off_of(b);
+        ld_global_256(late + off, o2);
+        ld_global_256(late + off + 8, o2 + 8);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if constexpr (FAST) y[j] = o2[j] * rsqrtf(y[j]);
-            else y[j] = o2[j] * (1.0f / sqrtf(y[j]));
-          }
-        } else {
+        for (int j = 0; j < 16; ++j) y[j] = o2[j] * sigmoid_f<FAST>(y[j]) + o1[j];
+      } else if (p.mode == MCQ_EPI_GDN) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if constexpr (FAST) y[j] = o2[j] * (y[j] * rsqrtf(y[j]));
-            else y[j] = o2[j] * sqrtf(y[j]);
-          }
+        for (int j = 0; j < 16; ++j) {
+          if constexpr (FAST) y[j] = o1[j] * rsqrtf(y[j]);
+          else y[j] = o1[j] * (1.0f / sqrtf(y[j]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if constexpr (FAST) y[j] = o1[j] * (y[j] * rsqrtf(y[j]));
+          else y[j] = o1[j] * sqrtf(y[j]);
         }
       }
-      if (p.out_f32) {
-        if (lane == 0) bulk_wait_read<0>();                          // the store that last read the staging buffer
-        __syncwarp();
+    }
+    if (live(b + 1)) request(b + 1);                                 // o1 is dead from here on
+    if (p.out_f32) {
+      if (lane == 0) bulk_wait_read<0>();                            // the store that last read the staging buffer
+      __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row64 + ((((uint32_t)c) ^ sw64) << 4)),
-                       "f"(y[4 * c]), "f"(y[4 * c + 1]), "f"(y[4 * c + 2]), "f"(y[4 * c + 3])
-                       : "memory");
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (!skip) tma_store_5d(&om->f32, stage, cx, bx0, cz, by0, bn0);
-          bulk_commit();
-        }
+      for (int c = 0; c < 4; ++c)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row64 + ((((uint32_t)c) ^ sw64) << 4)),
+                     "f"(y[4 * c]), "f"(y[4 * c + 1]), "f"(y[4 * c + 2]), "f"(y[4 * c + 3])
+                     : "memory");
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (!skip) tma_store_5d(&om->f32, stage, cx, bx0, cz, by0, bn0);
+        bulk_commit();
       }
+    }
 #pragma unroll
-      for (int slot = 0; slot < 2; ++slot) {
-        const bool on = slot == 0 ? p.o0_hi != nullptr : p.o1_hi != nullptr;
-        const bool with_lo = slot == 0 ? p.o0_lo != nullptr : p.o1_lo != nullptr;
-        if (!on) continue;
-        float t[16];
-        act_group<16, FAST>(y, t, slot == 0 ? p.o0_act : p.o1_act);
-        uint32_t h[8], lw[8];
-        if (with_lo) {
+    for (int slot = 0; slot < 2; ++slot) {
+      const bool on = slot == 0 ? p.o0_hi != nullptr : p.o1_hi != nullptr;
+      const bool with_lo = slot == 0 ? p.o0_lo != nullptr : p.o1_lo != nullptr;
+      if (!on) continue;
+      float t[16];
+      act_group<16, FAST>(y, t, slot == 0 ? p.o0_act : p.o1_act);
+      uint32_t h[8], lw[8];
+      if (with_lo) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) split_f32x2(t[2 * j], t[2 * j + 1], h[j], lw[j]);
-        } else {
+        for (int j = 0; j < 8; ++j) split_f32x2(t[2 * j], t[2 * j + 1], h[j], lw[j]);
+      } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) h[j] = f2h2_sat(t[2 * j], t[2 * j + 1]);
-        }
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
+        for (int j = 0; j < 8; ++j) h[j] = f2h2_sat(t[2 * j], t[2 * j + 1]);
+      }
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t a = row32 + ((((uint32_t)c) ^ sw32) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[4 * c]), "r"(h[4 * c + 1]),
-                       "r"(h[4 * c + 2]), "r"(h[4 * c + 3])
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t a = row32 + ((((uint32_t)c) ^ sw32) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[4 * c]), "r"(h[4 * c + 1]),
+                     "r"(h[4 * c + 2]), "r"(h[4 * c + 3])
+                     : "memory");
+        if (with_lo)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 1024u), "r"(lw[4 * c]), "r"(lw[4 * c + 1]),
+                       "r"(lw[4 * c + 2]), "r"(lw[4 * c + 3])
                        : "memory");
-          if (with_lo)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 1024u), "r"(lw[4 * c]), "r"(lw[4 * c + 1]),
-                         "r"(lw[4 * c + 2]), "r"(lw[4 * c + 3])
-                         : "memory");
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (!skip) {
+          tma_store_5d(slot == 0 ? &om->o0_hi : &om->o1_hi, stage, cx, bx0, cz, by0, bn0);
+          if (with_lo) tma_store_5d(slot == 0 ? &om->o0_lo : &om->o1_lo, stage + 1024u, cx, bx0, cz, by0, bn0);
         }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (!skip) {
-            tma_store_5d(slot == 0 ? &om->o0_hi : &om->o1_hi, stage, cx, bx0, cz, by0, bn0);
-            if (with_lo) tma_store_5d(slot == 0 ? &om->o0_lo : &om->o1_lo, stage + 1024u, cx, bx0, cz, by0, bn0);
-          }
-          bulk_commit();
-        }
+        bulk_commit();
       }
     }
   }
@@ -588,12 +616,14 @@ __device__ __forceinline__ void drain_tile_rows(const ConvArgs& p, uint32_t t_ac
         uint32_t r[16];
         float y[16];
         tmem_ld16(t_acc + (uint32_t)col0, r);
-        // fp32 operands: requested before the accumulator wait
-        float o1[16], o2[16];
+        // fp32 operand (residual, or the GDN / IGDN operand): requested before the accumulator wait.  A second operand
+        // (attention gate, `z - dequant + side`: rare) is loaded where it is used -- see drain_tile_tma.
+        float o1[16];
         const float* src1 = (p.mode == MCQ_EPI_LINEAR || p.mode == MCQ_EPI_GATE) ? p.res1 : nullptr;
         const float* src2 = (p.mode == MCQ_EPI_LINEAR) ? p.res2 : p.aux;
-        if (live && src1) { ld_global_256(src1 + off, o1); ld_global_256(src1 + off + 8, o1 + 8); }
-        if (live && src2) { ld_global_256(src2 + off, o2); ld_global_256(src2 + off + 8, o2 + 8); }
+        const float* ahead = src1 ? src1 : src2;
+        const float* late = src1 ? src2 : nullptr;
+        if (live && ahead) { ld_global_256(ahead + off, o1); ld_global_256(ahead + off + 8, o1 + 8); }
         if (PASSES == 3) {
           uint32_t l[16];
           tmem_ld16(t_acc + (uint32_t)(bn + col0), l);
@@ -617,25 +647,34 @@ __device__ __forceinline__ void drain_tile_rows(const ConvArgs& p, uint32_t t_ac
           if (src1) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) y[j] = y[j] + p.res1_scale * o1[j];
-          }
-          if (src2) {
+            if (late) {
+              float o2[16];
+              ld_global_256(late + off, o2);
+              ld_global_256(late + off + 8, o2 + 8);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] = y[j] + o2[j];
+              for (int j = 0; j < 16; ++j) y[j] = y[j] + o2[j];
+            }
+          } else if (ahead) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) y[j] = y[j] + o1[j];
           }
         } else if (p.mode == MCQ_EPI_GATE) {
+          float o2[16];
+          ld_global_256(late + off, o2);
+          ld_global_256(late + off + 8, o2 + 8);
 #pragma unroll
           for (int j = 0; j < 16; ++j) y[j] = o2[j] * sigmoid_f<PASSES == 1>(y[j]) + o1[j];
         } else if (p.mode == MCQ_EPI_GDN) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if constexpr (PASSES == 1) y[j] = o2[j] * rsqrtf(y[j]);
-            else y[j] = o2[j] * (1.0f / sqrtf(y[j]));
+            if constexpr (PASSES == 1) y[j] = o1[j] * rsqrtf(y[j]);
+            else y[j] = o1[j] * (1.0f / sqrtf(y[j]));
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if constexpr (PASSES == 1) y[j] = o2[j] * (y[j] * rsqrtf(y[j]));
-            else y[j] = o2[j] * sqrtf(y[j]);
+            if constexpr (PASSES == 1) y[j] = o1[j] * (y[j] * rsqrtf(y[j]));
+            else y[j] = o1[j] * sqrtf(y[j]);
           }
         }
         if (p.out_f32) {
@@ -758,17 +797,21 @@ __device__ __forceinline__ void drain_tile_rows(const ConvArgs& p, uint32_t t_ac
 
 // DRAIN (chosen by the host, drain_kind() in mcq_api.cu): each variant is a separate kernel instantiation -- two drains in
 // one kernel do not fit its 96 registers per thread.
-template <int PASSES, bool GN = false, int DRAIN = DRAIN_ROWS, class PixFn>
+// wait_accumulator(): blocks until the tile's accumulator is complete (mbarrier wait + tcgen05 fence); the bulk-store drain
+// calls it after it has requested its first fp32 operands, the others on entry.
+template <int PASSES, bool GN = false, int DRAIN = DRAIN_ROWS, class PixFn, class WaitFn>
 __device__ __forceinline__ void drain_tile(const ConvArgs& p, const OutMaps* om, uint32_t t_acc, int bn, int ct, int cg,
                                            int q, int lane, uint32_t stage, PixFn pix, const float* bias_src,
-                                           const float wscale) {
+                                           const float wscale, WaitFn wait_accumulator) {
   if constexpr (DRAIN == DRAIN_QUAD) {
     static_assert(!GN, "the GroupNorm-statistics drain is row-per-lane");
+    wait_accumulator();
     drain_tile_quad<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, wscale);
   } else if constexpr (DRAIN == DRAIN_TMA) {
     static_assert(!GN, "the GroupNorm-statistics drain stores from registers");
-    drain_tile_tma<PASSES>(p, om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, wscale);
+    drain_tile_tma<PASSES>(p, om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, wscale, wait_accumulator);
   } else {
+    wait_accumulator();
     drain_tile_rows<PASSES, GN>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, wscale);
   }
 }
@@ -988,11 +1031,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       auto pix = tile_pix(t, ct);
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
-      prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
-      mbar_wait(tfull_bar(buf), use & 1u, 4, p.wait_sleep_ns);
-      tc_fence_after();
+      // L2 prefetch of the fp32 operands: this tile's on the first trip, from then on the NEXT tile's (a whole tile of lead)
+      if (it == 0) prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
+      if (t + (int)gridDim.x < total_tiles) {
+        int ct2;
+        auto pix2 = tile_pix(t + (int)gridDim.x, ct2);
+        prefetch_epilogue_operands(p, bn, ct2, cg, q, lane, pix2);
+      }
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES, false, DRAIN>(p, &om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, wscale);
+      drain_tile<PASSES, false, DRAIN>(p, &om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, wscale,
+                                       [&]() {
+                                         mbar_wait(tfull_bar(buf), use & 1u, 4, p.wait_sleep_ns);
+                                         tc_fence_after();
+                                       });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) stem_tc_kernel(const ConvArgs 
       mbar_wait(tfull(ab), ((uint32_t)(i >> 1)) & 1u, 44);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * acc_cols);
-      drain_tile<3, false, DRAIN>(p, &om, t_acc, bn, 0, cg, q, lane, stage, pix, bias_smem, effective_w_scale(p));
+      drain_tile<3, false, DRAIN>(p, &om, t_acc, bn, 0, cg, q, lane, stage, pix, bias_smem, effective_w_scale(p), []() {});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(ab));
