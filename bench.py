@@ -207,6 +207,65 @@ def _by_class(rows, peak):
     return classes
 
 
+def _dominant_in_graph(dev, peak):
+    """The dominant kernel (conv_pair_kernel<3>, 64 x 64 x 64 x 128 -> 128) as it runs inside the timed step: a chain of
+    dependent launches captured in ONE CUDA graph, CUDA events around the replay, L2 flushed before it; per-launch time =
+    replay time / launches.  Two epilogue kinds as in the model: plane -> plane (first conv of a ResidualBlock) and
+    fp32 residual in, fp32 + SiLU planes out (second conv).  The per-launch events of the eager leg add the launch gap and
+    an idle pipeline at every kernel boundary; this figure has neither."""
+    import torch
+    from mcquic_b200.engine import Act, Engine, pack_conv
+    L, n, hw, c = 10, BATCH, 64, CHANNEL
+    eng = Engine("tcgen05")
+    eng.chain = False
+    eng.passes = 3
+    g = torch.Generator().manual_seed(0)
+    packs = [pack_conv(((torch.rand(c, c, 3, 3, generator=g) * 2 - 1) / (9 * c) ** 0.5).to(dev), torch.zeros(c, device=dev),
+                       1, 0, dev) for _ in range(L)]
+    x = (torch.randn(n, hw, hw, c, generator=g) * 0.5).to(dev)
+    hi = x.to(torch.float16)
+    a0 = (hi, ((x - hi.float()) * 2048.0).to(torch.float16))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {}
+    for kind in ("plane_to_plane", "residual_fp32_out"):
+        def body():
+            a, act, res = a0, Act(n, hw, hw, c), x
+            for i in range(L):
+                if kind == "plane_to_plane":
+                    o = eng.conv(packs[i], a, act, {"silu"})
+                else:
+                    o = eng.conv(packs[i], a, act, {"f32", "silu"}, res1=res, res1_scale=0.5)
+                    res = o.f32
+                a, act = o.silu, o
+            return a
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            body()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            keep = body()
+        ts = []
+        for _ in range(5):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        us = 1e3 * sorted(ts)[len(ts) // 2] / L
+        alg = 2.0 * n * hw * hw * c * c * 9 / us / 1e6
+        out[kind] = {"us_per_launch": us, "alg_tflops": alg, "frac": alg / peak, "executed_tflops": 3 * alg,
+                     "executed_frac": 3 * alg / peak}
+        del gr, keep
+    out["what"] = (f"{L} dependent launches of the dominant shape (n={n}, {hw}x{hw}, {c}->{c}, 3-pass) in one CUDA graph, "
+                   "median of 5 replays / launches, L2 flushed before each replay")
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
 def _eager_gpu_baseline(dev, x_dev):
     """The reference's own GPU path on THIS GPU in THIS run: its algorithm executed op by op through ATen / cuDNN / cuBLAS
     (the functional restatement oracle/mcquic_oracle.py on CUDA tensors -- the reference package cannot be imported on the
@@ -421,6 +480,7 @@ def run_ours(args):
                                    "alg_frac": BATCH * ALG_GFLOP_PER_IMAGE / 1e3 / (ms / args.steps * 1e-3) / peak,
                                    "basis": "5.724 algorithmic TFLOP per 64-image step / the timed ms_per_step"},
                     "by_layer_class": _by_class(rows, peak)}
+        roofline["dominant_in_graph"] = _dominant_in_graph(dev, peak)
     # (the roofline leg above runs right after the timed region, before the heavier legs below heat the GPU / fill its memory:
     #  measured, the same launches take up to 35 % longer when timed after the batch-512 leg)
     # ---- strong-scaling leg (BASELINE configs[3]): 512 images in total, 512 / N per rank, same step (encode, the one
