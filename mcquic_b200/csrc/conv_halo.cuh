@@ -34,7 +34,8 @@ struct HaloArgs {
   int base_mode;    // 0: descriptor base_offset = 0; 1: base_offset = (start >> 7) & 7
   int tiles_m;      // pixel tiles (n * tiles_y * tiles_x)
   int groups_m;     // ceil(tiles_m / CL)
-  int resident;     // pair kernel, 1-pass: the whole weight matrix of the N tile stays in shared memory (nbs = all stages)
+  int resident;     // the whole weight matrix of the N tile stays in shared memory (nbs = all stages): pair kernel 1-pass,
+                    // halo kernel whenever a single N tile's stages all fit
   int per_ct;       // resident mode with several N tiles: clusters per N tile (cluster c serves N tile c % tiles_c only)
 };
 
@@ -192,14 +193,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         ++a_issue;
       };
       for (int i = 0; i < na - 1; ++i) issue_a();
+      // hp.resident (single N tile whose weight stages all fit: narrow layers such as the 128 -> 12 output convolution or
+      // Neon's 32-channel nets): the ring holds every stage of the N tile, filled during the first work item and never
+      // recycled -- no weight traffic and no empty-barrier round trip for any later tile
+      bool load_b = true;
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         int ct, x0, y0, n;
         decode_tile(w, ct, x0, y0, n);
         const int row0 = ct * bn + (int)crank * (bn / CL);
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int sg = 0; sg < spc; ++sg) {
-            mbar_wait(b_empty(bs), bph ^ 1u, 12, p.wait_sleep_ns);
-            if (elect_one()) {
+            if (!hp.resident) mbar_wait(b_empty(bs), bph ^ 1u, 12, p.wait_sleep_ns);
+            if (load_b && elect_one()) {
               mbar_expect_tx(b_full(bs), b_stage_bytes);
               for (int tt = 0; tt < hp.tps; ++tt) {
                 const uint32_t sb = b_base + b_stage_bytes * bs + b_tap_bytes * tt;
@@ -218,6 +223,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             if (sg == t_star) issue_a();
           }
         }
+        if (hp.resident) load_b = false;
       }
     }
   } else if (warp == 1) {
@@ -247,7 +253,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const uint64_t a_hi0 = make_sdesc_halo(a_base + a_buf_bytes * ab, sbo, hp.base_mode);
           const uint64_t a_lo0 = a_hi0 + (uint64_t)(hp.a_bytes >> 4);
           for (int sg = 0; sg < spc; ++sg) {
-            mbar_wait(b_full(bs), bph, 15);
+            if (!hp.resident || it == 0) mbar_wait(b_full(bs), bph, 15);
             tc_fence_after();
             const uint64_t b0 = make_sdesc(b_base + b_stage_bytes * bs);
             if (elect_one()) {
@@ -274,7 +280,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 acc_i = 1u;
               }
             }
-            if (CL > 1) umma_commit_mc(b_empty(bs), kMask); else umma_commit(b_empty(bs));
+            if (!hp.resident) {
+              if (CL > 1) umma_commit_mc(b_empty(bs), kMask); else umma_commit(b_empty(bs));
+            }
             if (sg == spc - 1) umma_commit(a_empty(ab));   // halo buffer free once the chunk's last tap has been read
             }
             __syncwarp();

@@ -77,7 +77,10 @@ Option g_options[] = {
     {"epi_skip", 0},          // profiling aid: drain TMEM but store nothing
     {"pair", -1},             // CTA-pair kernel: -1 = auto (3-pass and weight-resident 1-pass layers), 0 / 1 = force
     {"pair_resident", 1},     // weight-stationary 1-pass mode of the pair kernel
+    {"pair_narrow", 1},       // pair kernel also for layers of 16 / 32 / 64 (padded) output channels
+    {"pair_nbs", 0},          // A/B knob: cap on the weight stages of the streaming (3-pass) mode; 0 = all that fit
     {"halo", 1},              // single-CTA halo kernel for 3x3 stride-1 layers the pair kernel does not take
+    {"halo_resident", 1},     // its weight-stationary mode (single N tile, all weight stages fit)
     {"halo_pitch", 10}, {"halo_base", 0}, {"halo_cl", 2}, {"halo_tps", 0}, {"halo_nbs", 0},
     {"small_grid_pct", 100},  // grid cap (% of the SMs) of launches with fewer work items than clusters
     {"chain", 1}, {"chain_ipc", 0}, {"chain_nosync", 0}, {"chain_sync_mode", 0},
@@ -492,6 +495,14 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
   if (nbs > 8) nbs = 8;
   if (opt("halo_nbs") > 0 && opt("halo_nbs") < nbs) nbs = opt("halo_nbs");
   if (nbs < 2) return MCQ_ERR_UNSUPPORTED;
+  {
+    // weight-stationary mode: a single N tile whose (cin / 64) * (9 / tps) stages all fit in the ring
+    const int all_stages = ((a.cin + TC_BK - 1) / TC_BK) * (9 / hp.tps);
+    if (a.tiles_c == 1 && all_stages <= nbs && opt("halo_resident")) {
+      hp.resident = 1;
+      nbs = all_stages;
+    }
+  }
   hp.nbs = nbs;
   const size_t smem = a_buf * hp.na + b_stage * nbs + 8 * (2 * hp.na + 2 * nbs + 4) + 16 + 1024 + epi_bytes;
 
@@ -571,7 +582,13 @@ int launch_pair_t(ConvArgs& a, HaloArgs& hp, const CUtensorMap* maps, size_t sme
 }
 
 int launch_pair(ConvArgs& a, cudaStream_t st) {
-  const int bn = 128;
+  // N tile: 128 columns, or the whole of a narrow layer (16 / 32 / 64 padded output channels: each CTA of the pair then
+  // holds 8 / 16 / 32 weight rows -- whole 8-row swizzle atoms)
+  int bn = 128;
+  if (a.cout_pad < 128) {
+    if (!opt("pair_narrow") || (a.cout_pad != 16 && a.cout_pad != 32 && a.cout_pad != 64)) return MCQ_ERR_UNSUPPORTED;
+    bn = a.cout_pad;
+  }
   if (a.cout_pad % bn != 0) return MCQ_ERR_UNSUPPORTED;
   const int np = a.passes == 3 ? 2 : 1;
   a.bn = bn;
@@ -599,6 +616,7 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
   hp.na = (a.passes == 3) ? 2 : 3;
   int nbs = (int)((budget - a_buf * hp.na) / b_stage);
   if (nbs > 8) nbs = 8;
+  if (opt("pair_nbs") > 0 && opt("pair_nbs") < nbs) nbs = opt("pair_nbs");   // A/B knob: fewer weight stages
   // weight-stationary mode: 1-pass, one N tile, and all (cin / 64) * (9 / tps) weight stages fit beside two halo buffers
   const int all_stages = ((a.cin + TC_BK - 1) / TC_BK) * (9 / hp.tps);
   if (a.passes == 1 && a.tiles_c <= num_sms() / 2 && all_stages <= 8 && a_buf * 2 + b_stage * all_stages <= budget &&
@@ -797,8 +815,8 @@ int mcq_conv2d(const mcq_conv_params* p, mcq_stream_t stream) {
     rc = MCQ_ERR_UNSUPPORTED;
     // CTA pairs (cta_group::2) pay off where the tensor pipe is the limiter (3-pass); the 1-pass path is epilogue-bound
     // (streaming weights); with a single 128-column N tile the weights stay resident in the pair's shared memory instead
-    const bool pair_resident = a.passes == 1 && a.cout_pad % 128 == 0 && a.cout_pad <= 512 && a.cin == 128 &&
-                               opt("pair_resident");
+    const bool pair_resident = a.passes == 1 && ((a.cout_pad % 128 == 0 && a.cout_pad <= 512) || a.cout_pad < 128) &&
+                               a.cin == 128 && opt("pair_resident");
     if (a.gn_ws) rc = halo_supported(a) ? launch_pair(a, st) : MCQ_ERR_UNSUPPORTED;   // only the pair kernel has it
     else
     // (streaming-weight 1-pass pairs pay off once K is long enough to amortise the epilogue: cin >= 256, measured on the

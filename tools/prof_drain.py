@@ -28,6 +28,7 @@ packs = [pack_conv(((torch.rand(c, c, 3, 3, generator=g) * 2 - 1) / (9 * c) ** 0
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 sizes = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [64, 128, 16]
 OPTS = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 5]
+_lib.apply_options(os.environ.get("MCQ_OPTIONS", ""))   # further A/B knobs, e.g. MCQ_OPTIONS=pair_nbs=3
 out = {}
 for hw in sizes:
     n = 64 if hw <= 64 else 32
