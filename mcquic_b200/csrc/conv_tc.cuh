@@ -200,6 +200,11 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -209,7 +214,29 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // box of 16 channels x the 32 pixels one drain warp owns; fp32: SWIZZLE_64B, fp16 planes: SWIZZLE_32B
 struct OutMaps {
   CUtensorMap f32, o0_hi, o0_lo, o1_hi, o1_lo;
+  // fp32 epilogue operands (residuals / GDN operand / gate operands; the same 5-D view, box = one whole tile x its N tile's
+  // channels): the TMA producer prefetches them into L2 one tile ahead with cp.async.bulk.prefetch.tensor -- one
+  // instruction of one thread instead of a prefetch.global.L2 per lane and line through the L1TEX pipe
+  CUtensorMap in0, in1;
+  int n_in;   // how many of in0 / in1 are valid
 };
+
+// L2 prefetch of the fp32 epilogue operands of the tile whose first pixel is (x0, y0, n0) and whose N tile is `ct`
+// (DRAIN_TMA launches; called by one elected lane of the TMA producer warp)
+__device__ __forceinline__ void prefetch_tile_operands(const ConvArgs& p, const OutMaps& om, int bn, int ct, int x0, int y0,
+                                                       int n0) {
+  if (om.n_in == 0) return;
+  const int c0 = ct * bn;
+  if (c0 >= p.cout) return;
+  int cx = c0, cz = 0;
+  if (p.store == MCQ_STORE_SHUFFLE_NHWC) {
+    const int cq = p.cout >> 2, sub = c0 / cq;
+    cx = (sub & 1) * cq + (c0 - sub * cq);
+    cz = sub >> 1;
+  }
+  tma_prefetch_l2_5d(&om.in0, cx, x0, cz, y0, n0);
+  if (om.n_in > 1) tma_prefetch_l2_5d(&om.in1, cx, x0, cz, y0, n0);
+}
 
 constexpr int DRAIN_ROWS = 0;   // row per lane: direct / smem-transposed global stores (any shape)
 constexpr int DRAIN_QUAD = 1;   // quad layout: full-line global accesses
@@ -926,6 +953,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int by = mt % p.tiles_y;
         const int bz = mt / p.tiles_y;
         const int x0 = bx * p.tw, y0 = by * p.th, n0 = bz * p.tn, c0 = ct * bn;
+        if constexpr (DRAIN == DRAIN_TMA) {
+          // fp32 epilogue operands -> L2: this tile's on the first trip, then always one tile ahead
+          auto pf = [&](int tt) {
+            const int ct2 = tt / tiles_m;
+            int mt2 = tt - ct2 * tiles_m;
+            const int bx2 = mt2 % p.tiles_x;
+            mt2 /= p.tiles_x;
+            prefetch_tile_operands(p, om, bn, ct2, bx2 * p.tw, (mt2 % p.tiles_y) * p.th, (mt2 / p.tiles_y) * p.tn);
+          };
+          if (elect_one()) {
+            if (t == (int)blockIdx.x) pf(t);
+            if (t + (int)gridDim.x < total_tiles) pf(t + (int)gridDim.x);
+          }
+          __syncwarp();
+        }
         for (int tap = 0; tap < ntaps; ++tap) {
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty_bar(s), ph ^ 1u, 1, p.wait_sleep_ns);
@@ -1032,11 +1074,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
       // L2 prefetch of the fp32 operands: this tile's on the first trip, from then on the NEXT tile's (a whole tile of lead)
-      if (it == 0) prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
-      if (t + (int)gridDim.x < total_tiles) {
-        int ct2;
-        auto pix2 = tile_pix(t + (int)gridDim.x, ct2);
-        prefetch_epilogue_operands(p, bn, ct2, cg, q, lane, pix2);
+      // (bulk-store launches: the TMA producer does it with one bulk prefetch per tile)
+      if constexpr (DRAIN != DRAIN_TMA) {
+        if (it == 0) prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
+        if (t + (int)gridDim.x < total_tiles) {
+          int ct2;
+          auto pix2 = tile_pix(t + (int)gridDim.x, ct2);
+          prefetch_epilogue_operands(p, bn, ct2, cg, q, lane, pix2);
+        }
       }
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
       drain_tile<PASSES, false, DRAIN>(p, &om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, wscale,

@@ -77,6 +77,10 @@ Option g_options[] = {
     {"epi_skip", 0},          // profiling aid: drain TMEM but store nothing
     {"pair", -1},             // CTA-pair kernel: -1 = auto (3-pass and weight-resident 1-pass layers), 0 / 1 = force
     {"pair_resident", 1},     // weight-stationary 1-pass mode of the pair kernel
+    {"tma_prefetch", 0},      // bulk-store launches: 1 = L2 prefetch of the fp32 epilogue operands by the TMA producer (one
+                              // cp.async.bulk.prefetch.tensor per tile, one tile ahead).  Measured (profiles/r2_drain_ab.txt):
+                              // no gain over no prefetch at all -- the operand read is bound by the L1TEX wavefronts of its
+                              // row-per-lane loads, not by latency -- so these launches prefetch nothing by default
     {"pair_narrow", 1},       // pair kernel also for layers of 16 / 32 / 64 (padded) output channels
     {"pair_nbs", 0},          // A/B knob: cap on the weight stages of the streaming (3-pass) mode; 0 = all that fit
     {"halo", 1},              // single-CTA halo kernel for 3x3 stride-1 layers the pair kernel does not take
@@ -146,8 +150,45 @@ int encode_out_map(CUtensorMap* map, const void* ptr, bool f32, const ConvArgs& 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : MCQ_ERR_DRIVER;
 }
+// L2-prefetch view of one fp32 epilogue operand (same geometry as the outputs): box = one whole 128-pixel tile x the
+// channels of one N tile; no shared-memory layout is involved (nothing is loaded), so no swizzle
+int encode_in_map(CUtensorMap* map, const void* ptr, const ConvArgs& a) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MCQ_ERR_DRIVER;
+  const cuuint64_t es = 4;
+  cuuint64_t dims[5], strides[4];
+  cuuint64_t cper;
+  if (a.store == MCQ_STORE_NHWC) {
+    const cuuint64_t c = (cuuint64_t)a.cout, w = (cuuint64_t)a.wout, h = (cuuint64_t)a.hout;
+    dims[0] = c; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = (cuuint64_t)a.n;
+    strides[0] = c * es; strides[1] = w * c * es; strides[2] = w * c * es; strides[3] = h * w * c * es;
+    cper = c;
+  } else {
+    const cuuint64_t cq = (cuuint64_t)(a.cout >> 2), w = (cuuint64_t)a.wout, h = (cuuint64_t)a.hout, w2 = 2 * w;
+    dims[0] = 2 * cq; dims[1] = w; dims[2] = 2; dims[3] = h; dims[4] = (cuuint64_t)a.n;
+    strides[0] = 2 * cq * es; strides[1] = w2 * cq * es; strides[2] = 2 * w2 * cq * es; strides[3] = 2 * h * w2 * cq * es;
+    cper = cq;
+  }
+  cuuint64_t bc = (cuuint64_t)a.bn < cper ? (cuuint64_t)a.bn : cper;
+  if (bc > 256) bc = 256;
+  cuuint32_t box[5] = {(cuuint32_t)bc, (cuuint32_t)a.tw, 1u, (cuuint32_t)a.th, (cuuint32_t)a.tn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MCQ_ERR_DRIVER;
+}
 int encode_out_maps(OutMaps& om, const ConvArgs& a) {
   int rc = 0;
+  om.n_in = 0;
+  if (opt("tma_prefetch")) {
+    const float* ins[3] = {a.res1, a.res2, a.aux};
+    for (const float* ptr : ins) {
+      if (!ptr || rc || om.n_in >= 2) continue;
+      rc = encode_in_map(om.n_in == 0 ? &om.in0 : &om.in1, ptr, a);
+      om.n_in++;
+    }
+  }
   if (a.out_f32) rc = encode_out_map(&om.f32, a.out_f32, true, a);
   if (!rc && a.o0_hi) rc = encode_out_map(&om.o0_hi, a.o0_hi, false, a);
   if (!rc && a.o0_lo) rc = encode_out_map(&om.o0_lo, a.o0_lo, false, a);
