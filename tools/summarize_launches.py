@@ -43,7 +43,14 @@ def main(path, steps, out_json=None):
     out["conv_dram_bytes_per_step"] = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"] for v in conv.values())
     out["conv_share"] = sum(v["share"] for v in conv.values())
     print(f"# tcgen05 conv kernels: {100*out['conv_share']:.1f}% of the step, DRAM traffic {out['conv_dram_bytes_per_step']/1e9:.2f} GB per step")
-    dom = [v for k, v in ours.items() if "conv_pair_kernel<3" in k.replace(" ", "") and "true" not in k and ", 1>" not in k]
+    # the dominant kernel: the 3-pass CTA-pair kernel in its bulk-store instantiation <PASSES = 3, GN = 0, DRAIN = 2> = exactly
+    # the 3x3 stride-1 encode convolutions on >= 32x32 maps (launches with >= 2 tiles per CTA, mcq_api.cu: drain_kind)
+    def targs(name):
+        inner = name.split("<", 1)[1].rsplit(">", 1)[0] if "<" in name else ""
+        return [t.strip().replace("(int)", "").replace("(bool)", "") for t in inner.split(",")]
+    dom = [v for k, v in ours.items() if "conv_pair_kernel" in k and targs(k)[:3] in (["3", "0", "2"], ["3", "false", "2"])]
+    if not dom:   # launch lists from before the drain variants existed
+        dom = [v for k, v in ours.items() if "conv_pair_kernel<3" in k.replace(" ", "") and "true" not in k and ", 1>" not in k]
     if dom:
         n_l = sum(v["launches_per_step"] for v in dom)
         out["dominant_kernel_dram_bytes_per_launch"] = sum(v["dram_read_bytes_per_step"] + v["dram_write_bytes_per_step"]
