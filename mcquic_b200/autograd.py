@@ -19,6 +19,7 @@ PixelShuffle) and the soft quantizer's softmax / straight-through estimator are 
 derives -- stated plainly: in this round only the convolutions of the training step are hand-written kernels.
 """
 import ctypes
+import weakref
 from typing import Optional
 
 import torch
@@ -114,7 +115,8 @@ class _Packed:
     can be captured in ONE CUDA graph.  (fp16 operands scaled to max |w| = 256..512 have a factor 128 of head-room and 2^-22
     of resolution below that, far more than weights drift between re-scalings; `reset_weight_scales()` re-derives them.)"""
 
-    def __init__(self):
+    def __init__(self, owner=None):
+        self.owner = None if owner is None else weakref.ref(owner)   # id(owner) is reused once the module is collected
         self.key = None
         self.fwd = None
         self.dgrad = None
@@ -137,10 +139,12 @@ def _exp_of(pc) -> int:
 
 def _packs_for(owner: nn.Module, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> _Packed:
     pk = _PACKS.get(id(owner))
-    key = (_version(weight), weight.data_ptr(), None if bias is None else _version(bias))
+    key = (_version(weight), weight.data_ptr(), tuple(weight.shape), None if bias is None else _version(bias))
     capturing = weight.is_cuda and torch.cuda.is_current_stream_capturing()
-    if pk is None:
-        pk = _PACKS[id(owner)] = _Packed()
+    if pk is None or pk.owner is None or pk.owner() is not owner:
+        # (a collected module's id -- and, through the caching allocator, even its weight's address and version -- can come
+        #  back with another layer: the entry belongs to the module it was made for, nothing else)
+        pk = _PACKS[id(owner)] = _Packed(owner)
     if pk.key != key or capturing or weight.grad_fn is not None:
         # new weight values (or a graph capture, whose replays must re-pack, or weights that are themselves computed each
         # step like GDN's reparametrised gamma): drop the packings, keep the exponents

@@ -18,6 +18,7 @@ runs in libmcquic_b200.so (`_lib.py`).  Fusion map (reference op -> where it wen
 """
 import contextlib
 import ctypes
+import weakref
 import os
 import math
 from dataclasses import dataclass
@@ -145,7 +146,7 @@ class Engine:
         self.lib = lib if lib is not None else _lib.load()
         self.impl = {"tcgen05": _lib.IMPL_TCGEN05, "simt": _lib.IMPL_SIMT}[impl]
         self.passes = 3
-        self._packed: Dict[Tuple[int, int], Tuple[Tuple, PackedConv]] = {}
+        self._packed: Dict[Tuple[int, int], Tuple] = {}   # (id(module), store) -> (weight version, packing, weakref(module))
         # independent sub-graphs (the two AttentionBlock branches, quantizationHead || latentHead,
         # dequantizationHead || sideHead) run on side streams: on <=16x16 feature maps one conv cannot fill 148 SMs
         self.multistream = not self.emulated
@@ -308,20 +309,23 @@ class Engine:
                 return 0
 
         if isinstance(mod, GenDivNorm):
-            ver = (version(mod.beta), version(mod.gamma), mod.beta.data_ptr(), mod.gamma.data_ptr())
+            ver = (version(mod.beta), version(mod.gamma), mod.beta.data_ptr(), mod.gamma.data_ptr(), tuple(mod.gamma.shape))
         elif mod.bias is None:
-            ver = (version(mod.weight), mod.weight.data_ptr())
+            ver = (version(mod.weight), mod.weight.data_ptr(), tuple(mod.weight.shape))
         else:
-            ver = (version(mod.weight), version(mod.bias), mod.weight.data_ptr(), mod.bias.data_ptr())
+            ver = (version(mod.weight), version(mod.bias), mod.weight.data_ptr(), mod.bias.data_ptr(),
+                   tuple(mod.weight.shape))
         hit = self._packed.get(key)
-        if hit is not None and hit[0] == ver:
+        # (id(mod) can come back with another module once `mod` is collected -- and with it, through the caching allocator,
+        #  the weight's address and version: the entry also remembers which module it was packed for)
+        if hit is not None and hit[0] == ver and hit[2]() is mod:
             return hit[1]
         if isinstance(mod, GenDivNorm):
             beta, gamma = mod.effective()
             pc = pack_conv(gamma[:, :, None, None], beta, 1, _lib.STORE_NHWC, gamma.device, amax)
         else:
             pc = pack_conv(mod.weight, mod.bias, mod.stride[0], store, mod.weight.device, amax)
-        self._packed[key] = (ver, pc)
+        self._packed[key] = (ver, pc, weakref.ref(mod))
         return pc
 
     def prepare(self, root: nn.Module):
@@ -595,7 +599,7 @@ class Engine:
         except RuntimeError:
             ver = (0, 0, conv.weight.data_ptr(), conv.bias.data_ptr())
         hit = self._packed.get(key)
-        if hit is not None and hit[0] == ver:
+        if hit is not None and hit[0] == ver and hit[2]() is conv:
             return hit[1]
         cout = conv.out_channels
         hi, lo, scale = split_weight(conv.weight.detach().float().reshape(cout, 27))
@@ -604,7 +608,7 @@ class Engine:
         rows[:cout, 0:27] = lo
         rows[:cout, 32:59] = hi
         packed = (rows.contiguous(), scale, conv.bias.detach().contiguous().float(), cout_pad)
-        self._packed[key] = (ver, packed)
+        self._packed[key] = (ver, packed, weakref.ref(conv))
         return packed
 
     def stem(self, conv: nn.Conv2d, x: torch.Tensor, pad: Tuple[int, int, int, int], want: Set[str],

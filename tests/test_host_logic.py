@@ -269,3 +269,38 @@ def test_uint8_images_take_the_reference_input_transform():
     assert torch.equal(out8, O.to_uint8(xf32))
     with pytest.raises(RuntimeError):
         model.encode(torch.zeros(1, 3, 64, 64, dtype=torch.int32))
+
+
+def test_packing_cache_survives_reuse_of_a_module_id():
+    """`Engine._packed` / `autograd._PACKS` are keyed by id(module).  Once a module is collected CPython hands its id -- and
+    the allocator its weight's address, with version counter 0 again -- to the next layer created; the cache entry must then
+    not be served (seen on the GPU box: a dgrad packing with cin = 128 returned for a 64-channel layer)."""
+    import gc
+    from torch import nn
+    from mcquic_b200 import autograd as A
+    eng = Engine(lib=EmulatedLib())
+
+    def make(cin, cout):
+        return nn.Conv2d(cin, cout, 3, padding=1)
+
+    first = make(16, 32)
+    ident = id(first)
+    pc = eng._packed_for(first)
+    pk = A._packs_for(first, first.weight, first.bias)
+    pk.fwd = pc
+    assert pc.cin == 16
+    del first, pc
+    gc.collect()
+    reused = None
+    keep = []
+    for _ in range(2000):                    # a freed object's address comes back almost immediately
+        cand = make(24, 8)
+        if id(cand) == ident:
+            reused = cand
+            break
+        keep.append(cand)
+    if reused is None:
+        pytest.skip("the interpreter did not reuse the module id")
+    assert eng._packed_for(reused).cin == 24
+    pk2 = A._packs_for(reused, reused.weight, reused.bias)
+    assert pk2 is not pk and pk2.fwd is None

@@ -16,6 +16,10 @@ WANT = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "dram__bytes_read.su
         "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__cluster_size",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_lgds.sum",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__m_l1tex2xbar_write_bytes_mem_global_op_tma_st.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_bytes.sum"]
 
