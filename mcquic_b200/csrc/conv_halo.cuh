@@ -73,7 +73,7 @@ template <int PASSES, int CL, int DRAIN = DRAIN_ROWS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                 const ConvArgs p, const HaloArgs hp) {
+                 const ConvArgs p, const HaloArgs hp, const __grid_constant__ OutMaps om) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -101,7 +101,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * na + 2 * nbs + 2 + b); };
   uint32_t* tmem_slot =
       reinterpret_cast<uint32_t*>(smem_gen + (bar_base - smem_base) + 8u * (2 * na + 2 * nbs + 4));
-  const uint32_t epi_base = (bar_base + 8u * (2 * na + 2 * nbs + 4) + 16u + 127u) & ~127u;
+  const uint32_t epi_base = (bar_base + 8u * (2 * na + 2 * nbs + 4) + 16u + 511u) & ~511u;   // 512 B: swizzle period of the staging
   float* bias_smem = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + TC_EPI_WARPS * TC_EPI_STAGE_BYTES);
   const bool bias_staged = p.cout <= TC_BIAS_SMEM_FLOATS;
   if (bias_staged)
@@ -315,14 +315,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       auto pix = tile_pix(w, ct);
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
-      prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
-      mbar_wait(tfull_bar(buf), use & 1u, 16, p.wait_sleep_ns);
-      tc_fence_after();
+      if (DRAIN != DRAIN_TMA) prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
-      drain_tile<PASSES, false, DRAIN>(p, nullptr, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias, effective_w_scale(p), []() {});
+      drain_tile<PASSES, false, DRAIN>(p, &om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_staged ? bias_smem : p.bias,
+                                       effective_w_scale(p), [&]() {
+                                         mbar_wait(tfull_bar(buf), use & 1u, 16, p.wait_sleep_ns);
+                                         tc_fence_after();
+                                       });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+    if constexpr (DRAIN == DRAIN_TMA) {
+      if (lane == 0) bulk_wait_all();          // this lane's bulk stores have left shared memory and are complete
     }
   }
 

@@ -20,8 +20,11 @@ ap.add_argument("--k", type=str, default="2048,2048,2048")
 ap.add_argument("--n", type=int, default=32)
 ap.add_argument("--hw", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--opt", default="", help="library options name=value,... (mcq_set_option), e.g. direct_epi=1")
 ap.add_argument("--layers", type=int, default=0)
 args = ap.parse_args()
+from mcquic_b200 import _lib as _mcq_lib  # noqa: E402
+_mcq_lib.apply_options(args.opt)
 k = [int(v) for v in args.k.split(",")]
 model = Compressor(args.channel, args.m, k).eval()
 model.load_state_dict(synthetic_state_dict(args.channel, args.m, k, seed=0))

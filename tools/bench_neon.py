@@ -24,9 +24,12 @@ ap.add_argument("--channel", type=int, default=256)
 ap.add_argument("--k", type=int, default=4096)
 ap.add_argument("--dense", type=int, default=0)
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--opt", default="", help="library options name=value,... (mcq_set_option), e.g. direct_epi=1")
 ap.add_argument("--decode-passes", type=int, default=3)
 ap.add_argument("--layers", type=int, default=0, help="also print the N most expensive conv shapes of the eager pass")
 args = ap.parse_args()
+from mcquic_b200 import _lib as _mcq_lib  # noqa: E402
+_mcq_lib.apply_options(args.opt)
 size = [16, 8, 8, 8, 8, 4, 4, 4, 4, 2, 2, 2, 2, 1, 1, 1, 1]
 if os.environ.get("NEON_SIZE"):
     size = [int(v) for v in os.environ["NEON_SIZE"].split(",")]
