@@ -215,18 +215,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int w = work_item(wi_);
         int ct, x0, y0, n;
         decode_tile(w, ct, x0, y0, n);
-        if constexpr (DRAIN == DRAIN_TMA) {
-          // fp32 epilogue operands of this CTA's tile -> L2: this work item's on the first trip, then one item ahead
-          if (elect_one()) {
-            if (wi_ == 0) prefetch_tile_operands(p, om, bn, ct, x0, y0, n);
-            if (wi_ + 1 < my_work) {
-              int ct2, x2, y2, n2;
-              decode_tile(work_item(wi_ + 1), ct2, x2, y2, n2);
-              prefetch_tile_operands(p, om, bn, ct2, x2, y2, n2);
-            }
-          }
-          __syncwarp();
-        }
         const int row_half = ct * bn + (int)crank * (bn / 2);
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int sg = 0; sg < spc; ++sg) {
@@ -330,7 +318,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
       // L2 prefetch of the fp32 operands: this tile's on the first trip, from then on the NEXT tile's (a whole tile of lead)
-      // (bulk-store launches: the TMA producer does it with one bulk prefetch per tile)
+      // (bulk-store launches prefetch nothing: measured no gain, profiles/r2_drain_ab.txt)
       if (DRAIN != DRAIN_TMA && it == 0) prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
       if (DRAIN != DRAIN_TMA && it + 1 < my_work) {
         int ct2, x2, y2, n2;

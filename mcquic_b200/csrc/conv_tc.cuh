@@ -188,21 +188,12 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
 __device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-__device__ __forceinline__ void st_global_128(void* ptr, const uint32_t (&w)[4]) {
-  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-               : "memory");
-}
 
 // ---- bulk-tensor stores (shared -> global) of the drain; bulk groups belong to the issuing thread
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
-               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -214,182 +205,14 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // box of 16 channels x the 32 pixels one drain warp owns; fp32: SWIZZLE_64B, fp16 planes: SWIZZLE_32B
 struct OutMaps {
   CUtensorMap f32, o0_hi, o0_lo, o1_hi, o1_lo;
-  // fp32 epilogue operands (residuals / GDN operand / gate operands; the same 5-D view, box = one whole tile x its N tile's
-  // channels): the TMA producer prefetches them into L2 one tile ahead with cp.async.bulk.prefetch.tensor -- one
-  // instruction of one thread instead of a prefetch.global.L2 per lane and line through the L1TEX pipe
-  CUtensorMap in0, in1;
-  int n_in;   // how many of in0 / in1 are valid
 };
 
-// L2 prefetch of the fp32 epilogue operands of the tile whose first pixel is (x0, y0, n0) and whose N tile is `ct`
-// (DRAIN_TMA launches; called by one elected lane of the TMA producer warp)
-__device__ __forceinline__ void prefetch_tile_operands(const ConvArgs& p, const OutMaps& om, int bn, int ct, int x0, int y0,
-                                                       int n0) {
-  if (om.n_in == 0) return;
-  const int c0 = ct * bn;
-  if (c0 >= p.cout) return;
-  int cx = c0, cz = 0;
-  if (p.store == MCQ_STORE_SHUFFLE_NHWC) {
-    const int cq = p.cout >> 2, sub = c0 / cq;
-    cx = (sub & 1) * cq + (c0 - sub * cq);
-    cz = sub >> 1;
-  }
-  tma_prefetch_l2_5d(&om.in0, cx, x0, cz, y0, n0);
-  if (om.n_in > 1) tma_prefetch_l2_5d(&om.in1, cx, x0, cz, y0, n0);
-}
-
 constexpr int DRAIN_ROWS = 0;   // row per lane: direct / smem-transposed global stores (any shape)
-constexpr int DRAIN_QUAD = 1;   // quad layout: full-line global accesses
 constexpr int DRAIN_TMA = 2;    // row per lane, outputs staged in shared memory and written by bulk-tensor stores
+// (1 was a quad-layout drain with full-line global accesses: measured, slower than DRAIN_TMA everywhere, removed --
+//  profiles/r2_ncu_drain_variants.txt keeps its numbers)
 
 // ---------------------------------------------------------------- epilogue
-// Quad drain: full-line global accesses.
-//
-// tcgen05.ld hands every lane one GEMM row (= pixel).  Storing from that layout (the "direct" drain below) makes every
-// 256-bit access of a warp touch 32 different 128 B lines, 32 B each -- and the L1TEX data pipe, which also feeds the
-// tensor core its shared-memory operands, pays per LINE visited, not per byte (ncu, 3-pass 64x64 layer: LSU wavefronts
-// 41 % + tensor-core operand wavefronts 30 % of the pipe's peak; ~10 k LSU wavefronts per 128 x 128 tile against ~4.6 k
-// cycles of MMA).  Here a warp's 32 pixels x 32 channels block is re-distributed through its 2 KB staging buffer so that
-// the four lanes of a quad hold the four 32 B pieces of ONE pixel's 128 B line: lane 4g+j owns channels [c0 + 8j, +8) of
-// pixels 4g .. 4g+3.  Every global instruction then covers 8 complete lines (fp32; 8 half lines for fp16 planes) instead
-// of 32 quarter lines: a quarter of the line visits for the residual read, the fp32 store and the plane stores.  All
-// epilogue math is element-wise, so it runs unchanged in the new layout.
-template <int PASSES, class PixFn>
-__device__ __forceinline__ void drain_tile_quad(const ConvArgs& p, uint32_t t_acc, int bn, int ct, int cg, int q, int lane,
-                                                uint32_t stage, PixFn pix, const float* bias_src, const float wscale) {
-  constexpr bool FAST = PASSES == 1;
-  const int g = lane >> 2, j = lane & 3;
-  const bool shuffled = p.store == MCQ_STORE_SHUFFLE_NHWC;
-  // operand roles: `pre` is requested one pixel ahead of its use, `sec` (second residual / gate operand: rare) at its use
-  const float* pre = p.mode == MCQ_EPI_LINEAR ? (p.res1 ? p.res1 : p.res2) : (p.mode == MCQ_EPI_GATE ? p.res1 : p.aux);
-  const float* sec = p.mode == MCQ_EPI_LINEAR ? (p.res1 ? p.res2 : nullptr) : (p.mode == MCQ_EPI_GATE ? p.aux : nullptr);
-  const uint32_t wbase = stage + (uint32_t)lane * 64u;   // staging: row per lane, 64 B; 16 B chunk c at c ^ ((row >> 1) & 3)
-  const uint32_t wsw = (uint32_t)((lane >> 1) & 3);
-  for (int cc = cg * 32; cc < bn; cc += 128) {
-    const int c0 = ct * bn + cc;
-    if (c0 >= p.cout) break;
-    size_t off[4];
-    bool ok_[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int n, oy, ox;
-      ok_[k] = pix(q * 32 + 4 * g + k, n, oy, ox) && !p.debug_skip_store;
-      off[k] = (shuffled ? epilogue_offset(p, n, oy, ox, c0)
-                         : (((size_t)n * p.hout + oy) * p.wout + ox) * (size_t)p.cout + c0) + (size_t)(8 * j);
-    }
-    float o1[2][8];
-    if (pre && ok_[0]) ld_global_256(pre + off[0], o1[0]);
-    // accumulator block [32 pixels x 32 columns]: TMEM -> registers (row per lane) -> staging -> registers (quad layout:
-    // v[8 k + e] = channel c0 + 8 j + e of pixel 4g + k)
-    float v[32];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[16];
-      float w[16];
-      tmem_ld16(t_acc + (uint32_t)(cc + half * 16), r);
-      if (PASSES == 3) {
-        uint32_t l[16];
-        tmem_ld16(t_acc + (uint32_t)(bn + cc + half * 16), l);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = fmaf(__uint_as_float(l[i]), kLoInv, __uint_as_float(r[i]));
-      } else {
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = __uint_as_float(r[i]);
-      }
-      __syncwarp();                                          // the previous round's reads of the staging buffer are done
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wbase + ((((uint32_t)c) ^ wsw) << 4)),
-                     "f"(w[4 * c]), "f"(w[4 * c + 1]), "f"(w[4 * c + 2]), "f"(w[4 * c + 3])
-                     : "memory");
-      __syncwarp();
-      if ((j >> 1) == half) {                                // this round carries channels [16 half, 16 half + 16)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t row = (uint32_t)(4 * g + k);
-          const uint32_t rbase = stage + row * 64u;
-          const uint32_t rsw = (row >> 1) & 3u;
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const uint32_t chunk = (uint32_t)((j & 1) * 2 + e);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v[8 * k + 4 * e]), "=f"(v[8 * k + 4 * e + 1]), "=f"(v[8 * k + 4 * e + 2]),
-                           "=f"(v[8 * k + 4 * e + 3])
-                         : "r"(rbase + ((chunk ^ rsw) << 4))
-                         : "memory");
-          }
-        }
-      }
-    }
-    float b[8];
-    load_f32v<8>(bias_src, c0 + 8 * j, b);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k + 1 < 4) {
-        if (pre && ok_[(k + 1) & 3]) ld_global_256(pre + off[(k + 1) & 3], o1[(k + 1) & 1]);
-      }
-      if (!ok_[k]) continue;
-      float y[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = fmaf(v[8 * k + e], wscale, b[e]);
-      if (p.mode == MCQ_EPI_LINEAR) {
-        if (p.res1) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] = y[e] + p.res1_scale * o1[k & 1][e];
-          if (sec) {
-            float o2[8];
-            ld_global_256(sec + off[k], o2);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = y[e] + o2[e];
-          }
-        } else if (pre) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] = y[e] + o1[k & 1][e];
-        }
-      } else if (p.mode == MCQ_EPI_GATE) {
-        float o2[8];
-        ld_global_256(sec + off[k], o2);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = o2[e] * sigmoid_f<FAST>(y[e]) + o1[k & 1][e];
-      } else if (p.mode == MCQ_EPI_GDN) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if constexpr (FAST) y[e] = o1[k & 1][e] * rsqrtf(y[e]);
-          else y[e] = o1[k & 1][e] * (1.0f / sqrtf(y[e]));
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if constexpr (FAST) y[e] = o1[k & 1][e] * (y[e] * rsqrtf(y[e]));
-          else y[e] = o1[k & 1][e] * sqrtf(y[e]);
-        }
-      }
-      if (p.out_f32) st_global_256(p.out_f32 + off[k], reinterpret_cast<const uint32_t(&)[8]>(y[0]));
-#pragma unroll
-      for (int slot = 0; slot < 2; ++slot) {
-        __half* hi_p = slot == 0 ? p.o0_hi : p.o1_hi;
-        __half* lo_p = slot == 0 ? p.o0_lo : p.o1_lo;
-        if (!hi_p) continue;
-        float t[8];
-        act_group<8, FAST>(y, t, slot == 0 ? p.o0_act : p.o1_act);
-        uint32_t h[4], lw[4];
-        if (lo_p) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) split_f32x2(t[2 * e], t[2 * e + 1], h[e], lw[e]);
-          st_global_128(hi_p + off[k], h);
-          st_global_128(lo_p + off[k], lw);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h[e] = f2h2_sat(t[2 * e], t[2 * e + 1]);
-          st_global_128(hi_p + off[k], h);
-        }
-      }
-    }
-  }
-}
-
 // TMA-store drain.
 //
 // ncu (profiles/r2_ncu_drain_variants.txt) shows what bounds the layers with fp32 outputs: the L1TEX data pipe, which also
@@ -624,7 +447,7 @@ __device__ __forceinline__ void drain_tile_rows(const ConvArgs& p, uint32_t t_ac
   // operand reads) -- and, measured, everywhere else too.  At 64x64: 1-pass plane->plane 64 -> 60 us (mainloop alone
   // 45), 3-pass 164 -> 157 us; whole step -2 %.
   const bool plane_only = p.mode == MCQ_EPI_LINEAR && !p.res1 && !p.res2 && !p.out_f32 && p.o0_hi && !p.o1_hi;
-  // direct_epilogue (A/B knob, mcq_set_option("direct_epi")): 3 / 4 = quad drain (another kernel instantiation) where the host chose it, else as 1;
+  // direct_epilogue (A/B knob, mcq_set_option("direct_epi")): >= 3 = as 1 here (the host picks DRAIN_TMA instantiations);
   // 1 = direct drain for every NHWC / PixelShuffle-NHWC store, 2 = plane-only outputs only, 0 = never
   const bool direct_ok = p.direct_epilogue == 1 || p.direct_epilogue >= 3 || (p.direct_epilogue == 2 && plane_only);
   const bool shuffled = p.store == MCQ_STORE_SHUFFLE_NHWC;
@@ -830,11 +653,7 @@ template <int PASSES, bool GN = false, int DRAIN = DRAIN_ROWS, class PixFn, clas
 __device__ __forceinline__ void drain_tile(const ConvArgs& p, const OutMaps* om, uint32_t t_acc, int bn, int ct, int cg,
                                            int q, int lane, uint32_t stage, PixFn pix, const float* bias_src,
                                            const float wscale, WaitFn wait_accumulator) {
-  if constexpr (DRAIN == DRAIN_QUAD) {
-    static_assert(!GN, "the GroupNorm-statistics drain is row-per-lane");
-    wait_accumulator();
-    drain_tile_quad<PASSES>(p, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, wscale);
-  } else if constexpr (DRAIN == DRAIN_TMA) {
+  if constexpr (DRAIN == DRAIN_TMA) {
     static_assert(!GN, "the GroupNorm-statistics drain stores from registers");
     drain_tile_tma<PASSES>(p, om, t_acc, bn, ct, cg, q, lane, stage, pix, bias_src, wscale, wait_accumulator);
   } else {
@@ -953,21 +772,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int by = mt % p.tiles_y;
         const int bz = mt / p.tiles_y;
         const int x0 = bx * p.tw, y0 = by * p.th, n0 = bz * p.tn, c0 = ct * bn;
-        if constexpr (DRAIN == DRAIN_TMA) {
-          // fp32 epilogue operands -> L2: this tile's on the first trip, then always one tile ahead
-          auto pf = [&](int tt) {
-            const int ct2 = tt / tiles_m;
-            int mt2 = tt - ct2 * tiles_m;
-            const int bx2 = mt2 % p.tiles_x;
-            mt2 /= p.tiles_x;
-            prefetch_tile_operands(p, om, bn, ct2, bx2 * p.tw, (mt2 % p.tiles_y) * p.th, (mt2 / p.tiles_y) * p.tn);
-          };
-          if (elect_one()) {
-            if (t == (int)blockIdx.x) pf(t);
-            if (t + (int)gridDim.x < total_tiles) pf(t + (int)gridDim.x);
-          }
-          __syncwarp();
-        }
         for (int tap = 0; tap < ntaps; ++tap) {
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty_bar(s), ph ^ 1u, 1, p.wait_sleep_ns);
@@ -1074,7 +878,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
       // L2 prefetch of the fp32 operands: this tile's on the first trip, from then on the NEXT tile's (a whole tile of lead)
-      // (bulk-store launches: the TMA producer does it with one bulk prefetch per tile)
+      // (bulk-store launches prefetch nothing: measured, their operand read is bound by the L1TEX wavefronts of its loads, not
+      //  by latency -- profiles/r2_drain_ab.txt)
       if constexpr (DRAIN != DRAIN_TMA) {
         if (it == 0) prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
         if (t + (int)gridDim.x < total_tiles) {

@@ -69,18 +69,14 @@ EncodeTiledFn get_encode_fn() {
 struct Option { const char* name; int value; };
 Option g_options[] = {
     {"direct_epi", 3},        // drain (drain_kind()): 3 = bulk-tensor stores for large launches, else direct; 5 = bulk-tensor
-                              // stores wherever they apply; 4 = quad layout wherever it applies; 1 = direct (row per lane)
-                              // for every NHWC / PixelShuffle store, 2 = direct for plane-only outputs, 0 = smem-transposed
+                              // stores wherever they apply; 1 = direct (row per lane) for every NHWC / PixelShuffle store,
+                              // 2 = direct for plane-only outputs, 0 = smem-transposed
     {"wait_sleep_ns", 0},     // nanosleep between mbarrier polls of the producer / drain warps
     {"tc_spread", 33},        // conv_tc: narrow the N tile until this % of the SMs have a tile
     {"pdl", 1},               // programmatic dependent launch
     {"epi_skip", 0},          // profiling aid: drain TMEM but store nothing
     {"pair", -1},             // CTA-pair kernel: -1 = auto (3-pass and weight-resident 1-pass layers), 0 / 1 = force
     {"pair_resident", 1},     // weight-stationary 1-pass mode of the pair kernel
-    {"tma_prefetch", 0},      // bulk-store launches: 1 = L2 prefetch of the fp32 epilogue operands by the TMA producer (one
-                              // cp.async.bulk.prefetch.tensor per tile, one tile ahead).  Measured (profiles/r2_drain_ab.txt):
-                              // no gain over no prefetch at all -- the operand read is bound by the L1TEX wavefronts of its
-                              // row-per-lane loads, not by latency -- so these launches prefetch nothing by default
     {"pair_narrow", 1},       // pair kernel also for layers of 16 / 32 / 64 (padded) output channels
     {"pair_nbs", 0},          // A/B knob: cap on the weight stages of the streaming (3-pass) mode; 0 = all that fit
     {"halo", 1},              // single-CTA halo kernel for 3x3 stride-1 layers the pair kernel does not take
@@ -111,12 +107,12 @@ int pow2_ceil(int v) {
 // tiles each CTA walks -- a launch with less than two is latency-bound (small maps) and keeps the plain drain, whose
 // stores need no staging round trip and no bulk-group wait before the kernel can end.
 //   direct_epi = 3 (default): DRAIN_TMA for large launches that can take it;  5: DRAIN_TMA wherever it applies;
-//   4: DRAIN_QUAD wherever it applies;  0 / 1 / 2: DRAIN_ROWS (see the option table)
+//   0 / 1 / 2: DRAIN_ROWS (see the option table)
 int drain_kind(const ConvArgs& a, long long work_per_cta) {
   if (a.direct_epilogue < 3 || a.mode == EPI_ARGMIN || a.gn_ws) return DRAIN_ROWS;
   const int cper = a.store == MCQ_STORE_NHWC ? a.cout : (a.store == MCQ_STORE_SHUFFLE_NHWC ? a.cout >> 2 : 0);
   if (cper == 0) return DRAIN_ROWS;
-  if (a.direct_epilogue == 4) return (a.bn % 32 == 0 && cper % 32 == 0) ? DRAIN_QUAD : DRAIN_ROWS;
+  if (a.direct_epilogue == 4) return DRAIN_ROWS;   // (was the quad-layout drain: removed)
   if (a.bn % 16 != 0 || cper % 16 != 0) return DRAIN_ROWS;
   if (a.direct_epilogue == 3 && work_per_cta < 2) return DRAIN_ROWS;
   // N tiles below 64 columns leave 12 of the 16 drain warps without a column: the few that work then serialise on their
@@ -153,45 +149,8 @@ int encode_out_map(CUtensorMap* map, const void* ptr, bool f32, const ConvArgs& 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : MCQ_ERR_DRIVER;
 }
-// L2-prefetch view of one fp32 epilogue operand (same geometry as the outputs): box = one whole 128-pixel tile x the
-// channels of one N tile; no shared-memory layout is involved (nothing is loaded), so no swizzle
-int encode_in_map(CUtensorMap* map, const void* ptr, const ConvArgs& a) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return MCQ_ERR_DRIVER;
-  const cuuint64_t es = 4;
-  cuuint64_t dims[5], strides[4];
-  cuuint64_t cper;
-  if (a.store == MCQ_STORE_NHWC) {
-    const cuuint64_t c = (cuuint64_t)a.cout, w = (cuuint64_t)a.wout, h = (cuuint64_t)a.hout;
-    dims[0] = c; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = (cuuint64_t)a.n;
-    strides[0] = c * es; strides[1] = w * c * es; strides[2] = w * c * es; strides[3] = h * w * c * es;
-    cper = c;
-  } else {
-    const cuuint64_t cq = (cuuint64_t)(a.cout >> 2), w = (cuuint64_t)a.wout, h = (cuuint64_t)a.hout, w2 = 2 * w;
-    dims[0] = 2 * cq; dims[1] = w; dims[2] = 2; dims[3] = h; dims[4] = (cuuint64_t)a.n;
-    strides[0] = 2 * cq * es; strides[1] = w2 * cq * es; strides[2] = 2 * w2 * cq * es; strides[3] = 2 * h * w2 * cq * es;
-    cper = cq;
-  }
-  cuuint64_t bc = (cuuint64_t)a.bn < cper ? (cuuint64_t)a.bn : cper;
-  if (bc > 256) bc = 256;
-  cuuint32_t box[5] = {(cuuint32_t)bc, (cuuint32_t)a.tw, 1u, (cuuint32_t)a.th, (cuuint32_t)a.tn};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : MCQ_ERR_DRIVER;
-}
 int encode_out_maps(OutMaps& om, const ConvArgs& a) {
   int rc = 0;
-  om.n_in = 0;
-  if (opt("tma_prefetch")) {
-    const float* ins[3] = {a.res1, a.res2, a.aux};
-    for (const float* ptr : ins) {
-      if (!ptr || rc || om.n_in >= 2) continue;
-      rc = encode_in_map(om.n_in == 0 ? &om.in0 : &om.in1, ptr, a);
-      om.n_in++;
-    }
-  }
   if (a.out_f32) rc = encode_out_map(&om.f32, a.out_f32, true, a);
   if (!rc && a.o0_hi) rc = encode_out_map(&om.o0_hi, a.o0_hi, false, a);
   if (!rc && a.o0_lo) rc = encode_out_map(&om.o0_lo, a.o0_lo, false, a);
@@ -456,11 +415,9 @@ int launch_tc(ConvArgs& a, cudaStream_t st) {
   } while (0)
   if (a.passes == 3) {
     if (drain == DRAIN_TMA) MCQ_LAUNCH_TC(3, DRAIN_TMA, 123);
-    else if (drain == DRAIN_QUAD) MCQ_LAUNCH_TC(3, DRAIN_QUAD, 113);
     else MCQ_LAUNCH_TC(3, DRAIN_ROWS, 103);
   } else {
     if (drain == DRAIN_TMA) MCQ_LAUNCH_TC(1, DRAIN_TMA, 121);
-    else if (drain == DRAIN_QUAD) MCQ_LAUNCH_TC(1, DRAIN_QUAD, 111);
     else MCQ_LAUNCH_TC(1, DRAIN_ROWS, 101);
   }
 #undef MCQ_LAUNCH_TC
@@ -593,10 +550,6 @@ int launch_halo(ConvArgs& a, cudaStream_t st) {
     if (rc) return rc;
     if (a.passes == 3) return launch_halo_t<3, 2, DRAIN_TMA>(a, hp, maps, smem, grid, st, om);
     return launch_halo_t<1, 2, DRAIN_TMA>(a, hp, maps, smem, grid, st, om);
-  }
-  if (drain == DRAIN_QUAD) {
-    if (a.passes == 3) return launch_halo_t<3, 2, DRAIN_QUAD>(a, hp, maps, smem, grid, st, om);
-    return launch_halo_t<1, 2, DRAIN_QUAD>(a, hp, maps, smem, grid, st, om);
   }
   if (a.passes == 3) {
     if (cl == 1) return launch_halo_t<3, 1>(a, hp, maps, smem, grid, st, om);
@@ -742,10 +695,6 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
     if (rc) return rc;
     if (a.passes == 3) return launch_pair_t<3, false, DRAIN_TMA>(a, hp, maps, smem, grid, st, om);
     return launch_pair_t<1, false, DRAIN_TMA>(a, hp, maps, smem, grid, st, om);
-  }
-  if (drain == DRAIN_QUAD) {
-    if (a.passes == 3) return launch_pair_t<3, false, DRAIN_QUAD>(a, hp, maps, smem, grid, st, om);
-    return launch_pair_t<1, false, DRAIN_QUAD>(a, hp, maps, smem, grid, st, om);
   }
   if (a.passes == 3) return launch_pair_t<3>(a, hp, maps, smem, grid, st, om);
   return launch_pair_t<1>(a, hp, maps, smem, grid, st, om);
@@ -963,9 +912,8 @@ int mcq_stem_conv_tc(const void* x, int32_t x_is_u8, int32_t n, int32_t h, int32
     const int rc = encode_out_maps(om, v);
     if (rc) return rc;
   }
-  cudaError_t e = drain == DRAIN_TMA    ? ensure_dyn_smem<KTag<802>>(stem_tc_kernel<DRAIN_TMA>, smem)
-                  : drain == DRAIN_QUAD ? ensure_dyn_smem<KTag<801>>(stem_tc_kernel<DRAIN_QUAD>, smem)
-                                        : ensure_dyn_smem<KTag<800>>(stem_tc_kernel<DRAIN_ROWS>, smem);
+  cudaError_t e = drain == DRAIN_TMA ? ensure_dyn_smem<KTag<802>>(stem_tc_kernel<DRAIN_TMA>, smem)
+                                     : ensure_dyn_smem<KTag<800>>(stem_tc_kernel<DRAIN_ROWS>, smem);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()));
@@ -977,9 +925,8 @@ int mcq_stem_conv_tc(const void* x, int32_t x_is_u8, int32_t n, int32_t h, int32
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = opt("pdl") ? 1 : 0;
-  e = drain == DRAIN_TMA    ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<DRAIN_TMA>, a, s, om)
-      : drain == DRAIN_QUAD ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<DRAIN_QUAD>, a, s, om)
-                            : cudaLaunchKernelEx(&cfg, stem_tc_kernel<DRAIN_ROWS>, a, s, om);
+  e = drain == DRAIN_TMA ? cudaLaunchKernelEx(&cfg, stem_tc_kernel<DRAIN_TMA>, a, s, om)
+                         : cudaLaunchKernelEx(&cfg, stem_tc_kernel<DRAIN_ROWS>, a, s, om);
   g_launches++;
   return e == cudaSuccess ? cuda_status() : (int)e;
 }

@@ -22,11 +22,11 @@ def _planes_value(pl):
 @pytest.mark.parametrize("n,h,w,cout", [(2, 256, 256, 128), (1, 150, 333, 64), (3, 64, 64, 32), (1, 100, 72, 128),
                                         (1, 128, 128, 192)])
 @pytest.mark.parametrize("u8", [False, True])
-@pytest.mark.parametrize("tc", [True, False, "bulk-store", "quad"])
+@pytest.mark.parametrize("tc", [True, False, "bulk-store"])
 def test_stem_matches_fp64(n, h, w, cout, u8, tc):
-    # tc = "bulk-store" / "quad": the tcgen05 kernel with that drain forced (the default takes the bulk-store drain for
+    # tc = "bulk-store": the tcgen05 kernel with that drain forced (the default takes the bulk-store drain for
     # large batches only; csrc/conv_tc.cuh)
-    drain = {"bulk-store": 5, "quad": 4}.get(tc)
+    drain = {"bulk-store": 5}.get(tc)
     if drain is not None:
         old = _lib.get_option("direct_epi")
         _lib.set_option("direct_epi", drain)

@@ -5,7 +5,7 @@ for each (map size, passes, epilogue kind, direct_epi option).
   full  : plane -> fp32 + SiLU planes with an fp32 residual read (second conv of a ResidualBlock)
 
 Usage (GPU box):  python tools/prof_drain.py [hw,hw,...] [opt,opt,...]   -> one JSON line; direct_epi values A/B'd (default
-1 = row per lane with global stores, 5 = bulk-tensor stores wherever they apply; 4 = quad layout)."""
+1 = row per lane with global stores, 5 = bulk-tensor stores wherever they apply)."""
 import json
 import os
 import sys
