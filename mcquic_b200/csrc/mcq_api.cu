@@ -77,6 +77,7 @@ Option g_options[] = {
     {"epi_skip", 0},          // profiling aid: drain TMEM but store nothing
     {"pair", -1},             // CTA-pair kernel: -1 = auto (3-pass and weight-resident 1-pass layers), 0 / 1 = force
     {"pair_resident", 1},     // weight-stationary 1-pass mode of the pair kernel
+    {"pair_96", 1},           // pair kernel with 96-column N tiles for 3-pass layers of 96 k output channels (C = 192 models)
     {"pair_narrow", 1},       // pair kernel also for layers of 16 / 32 / 64 (padded) output channels
     {"pair_nbs", 0},          // A/B knob: cap on the weight stages of the streaming (3-pass) mode; 0 = all that fit
     {"halo", 1},              // single-CTA halo kernel for 3x3 stride-1 layers the pair kernel does not take
@@ -598,6 +599,10 @@ int launch_pair(ConvArgs& a, cudaStream_t st) {
   if (a.cout_pad < 128) {
     if (!opt("pair_narrow") || (a.cout_pad != 16 && a.cout_pad != 32 && a.cout_pad != 64)) return MCQ_ERR_UNSUPPORTED;
     bn = a.cout_pad;
+  } else if (a.cout_pad % 128 != 0 && a.cout_pad % 96 == 0 && a.passes == 3 && opt("pair_96")) {
+    // 192-channel models (qp >= 3: Compressor(192, ...)): two 96-column N tiles -- the 3-pass [hi*hi | hi*lo] MMA is then
+    // N = 192 wide, each CTA of the pair holds 96 / 48 weight rows (whole 8-row swizzle atoms)
+    bn = 96;
   }
   if (a.cout_pad % bn != 0) return MCQ_ERR_UNSUPPORTED;
   const int np = a.passes == 3 ? 2 : 1;
