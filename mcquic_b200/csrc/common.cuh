@@ -52,7 +52,8 @@ struct ConvArgs {
   int argmin_stride;              // points are argmin_stride keys / aux entries apart (= number of codebooks)
   int debug_skip_store;           // MCQ_EPI_SKIP=1: drain TMEM but store nothing (profiling aid)
   int wait_sleep_ns;              // nanosleep between mbarrier polls of the producer / drain warps (MCQ_WAIT_SLEEP_NS)
-  int direct_epilogue;            // 1 (default): transpose-free drain where it applies, see drain_tile (MCQ_DIRECT_EPI=0: off)
+  int direct_epilogue;            // mcq_set_option("direct_epi"): which drain a launch takes, see drain_kind() (mcq_api.cu) and
+                                  // drain_tile_rows (conv_tc.cuh); default 3
   // GroupNorm statistics fused into the drain (pair kernel, GN instantiation only): every drain warp writes, per
   // gn_unit consecutive channels, (sum y, sum y^2) over its 32 pixels to gn_ws[(n * gn_rb + row block) * gn_units + unit]
   float2* gn_ws;

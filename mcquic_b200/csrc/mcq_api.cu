@@ -119,6 +119,9 @@ int drain_kind(const ConvArgs& a, long long work_per_cta) {
   // N tiles below 64 columns leave 12 of the 16 drain warps without a column: the few that work then serialise on their
   // single staging buffer (measured: the 32-channel Neon training step 163 -> 167 ms with the bulk-store drain)
   if (a.direct_epilogue == 3 && a.bn < 64) return DRAIN_ROWS;
+  // bulk-tensor stores need 16-byte aligned tensors (torch allocations are; a caller of the C ABI may pass anything)
+  const uintptr_t ptrs = (uintptr_t)a.out_f32 | (uintptr_t)a.o0_hi | (uintptr_t)a.o0_lo | (uintptr_t)a.o1_hi | (uintptr_t)a.o1_lo;
+  if (ptrs & 15) return DRAIN_ROWS;
   return DRAIN_TMA;
 }
 
