@@ -83,8 +83,12 @@ class BaseCompressor(nn.Module):
         # many images (0 = whole batch at once), so that a layer's output is still in the 126 MB L2 when the next layer of
         # the same slice reads it (at batch 64 one 64x64x128 activation is 134 MB fp32 + 67 MB planes: every layer streams
         # through HBM).  Results are bit-identical (images are independent).
+        # Measured at batch 64 (tools/exp_slices.py, profiles/r2_decode_slices_experiment.txt): with round 1's drain 32-image
+        # decode slices won (5.51 -> 5.37 ms); with the bulk-store drain the whole batch at once does (4.58 vs 4.81 ms) -- the
+        # layers no longer wait on their own global stores, and half-size launches have twice the kernel boundaries.
+        # Encode always preferred the whole batch (7.37 vs 7.62 ms at 32).
         self.encode_slice = 0
-        self.decode_slice = 32      # measured at batch 64 (tools/exp_slices.py): decode 5.51 -> 5.37 ms; encode loses
+        self.decode_slice = 0
 
     @property
     def QuantizationParameter(self) -> str:

@@ -262,6 +262,25 @@ def test_fp16_range_stress(case):
     assert model.engine.lib.mcq_device_error_flag() == 0
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_batch_slices_of_the_full_resolution_layers_change_nothing(graphs):
+    """`encode_slice` / `decode_slice` (L2-resident sub-batches of the full-resolution layers; off by default since the
+    bulk-store drain) must give the very same codes and pixels as the whole batch at once, also for a ragged last slice."""
+    cfg = dict(channel=128, m=1, k=[8192, 2048, 512])
+    sd = synthetic_state_dict(cfg["channel"], cfg["m"], cfg["k"], seed=0)
+    model = _model(cfg, sd)
+    model.use_graphs = graphs
+    x = uniform((7, 3, 128, 192), "slices.image", 0).cuda()
+    ref_codes = model.encode(x)
+    ref_x = model.decode(ref_codes)
+    for sl in (2, 4):
+        model.encode_slice = model.decode_slice = sl
+        codes = model.encode(x)
+        assert all(torch.equal(a, b) for a, b in zip(codes, ref_codes)), sl
+        assert torch.equal(model.decode(codes), ref_x), sl
+    assert model.engine.lib.mcq_device_error_flag() == 0
+
+
 @pytest.mark.parametrize("hw,n", [((128, 128), 16), ((100, 72), 6), ((64, 128), 32)])
 def test_host_pipeline_matches_device_path(hw, n):
     """encode(pinned host batch) / decode(out=pinned host tensor): the chunked copy/compute pipeline (first and last
