@@ -233,9 +233,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const uint32_t idesc_wide = (1u << 4) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const bool wide = (PASSES == 3) && (2 * bn <= 256);
       const int spc = 9 / hp.tps;
-      uint32_t tap_off16[9];   // halo offset of tap (r, s) in 16 B units: (r * pitch + s) pixels x 128 B
-#pragma unroll
-      for (int t = 0; t < 9; ++t) tap_off16[t] = (uint32_t)((t / 3) * hp.pitch + (t % 3)) * 8u;
+      // halo offset of tap (r, s) in 16 B units: (r * pitch + s) pixels x 128 B (computed, not tabulated: a table indexed
+      // by the runtime stage index would live in local memory, see conv_pair.cuh)
+      auto tap_off16 = [&](int tap) {
+        const int r = tap / 3;
+        return (uint32_t)(r * hp.pitch + (tap - 3 * r)) * 8u;
+      };
       int ab = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
@@ -261,7 +264,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll 3
             for (int tt = 0; tt < hp.tps; ++tt) {
               const int tap = sg * hp.tps + tt;
-              const uint64_t at = (uint64_t)tap_off16[tap];
+              const uint64_t at = (uint64_t)tap_off16(tap);
               const uint64_t bt = b0 + (uint64_t)(tt * (int)(b_tap_bytes >> 4));
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {

@@ -248,9 +248,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const uint32_t idesc_n = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t idesc_2n = (1u << 4) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t sbo = (uint32_t)hp.pitch * 128u;
-      uint32_t tap_off16[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) tap_off16[t] = (uint32_t)((t / 3) * hp.pitch + (t % 3)) * 8u;
+      // halo offset of tap (r, s) in 16 B units: (r * pitch + s) pixels x 128 B -- computed where it is used: a 9-entry
+      // table indexed by the (runtime) stage index lives in LOCAL memory, and a local load of the one thread that feeds the
+      // tensor core queues behind the drain warps' global accesses in the SM's L1TEX FIFO
+      auto tap_off16 = [&](int tap) {
+        const int r = tap / 3;
+        return (uint32_t)(r * hp.pitch + (tap - 3 * r)) * 8u;
+      };
       int ab = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
       for (; it < my_work; ++it) {
@@ -273,7 +277,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             uint32_t acc_i = acc;
 #pragma unroll 3
             for (int tt = 0; tt < hp.tps; ++tt) {
-              const uint64_t at = (uint64_t)tap_off16[sg * hp.tps + tt];
+              const uint64_t at = (uint64_t)tap_off16(sg * hp.tps + tt);
               const uint64_t bt = b0 + (uint64_t)(tt * (int)(b_tap_bytes >> 4));
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) {

@@ -356,27 +356,30 @@ __device__ __forceinline__ void drain_tile_tma(const ConvArgs& p, const OutMaps*
       const bool on = slot == 0 ? p.o0_hi != nullptr : p.o1_hi != nullptr;
       const bool with_lo = slot == 0 ? p.o0_lo != nullptr : p.o1_lo != nullptr;
       if (!on) continue;
-      float t[16];
-      act_group<16, FAST>(y, t, slot == 0 ? p.o0_act : p.o1_act);
-      uint32_t h[8], lw[8];
-      if (with_lo) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) split_f32x2(t[2 * j], t[2 * j + 1], h[j], lw[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] = f2h2_sat(t[2 * j], t[2 * j + 1]);
-      }
       if (lane == 0) bulk_wait_read<0>();
       __syncwarp();
+      // (eight channels at a time: the activation / split temporaries of all sixteen at once are what pushed the tile
+      //  loop's state out of the 96 registers, and a spill reload queues behind this warp's global loads)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        float yy[8], t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yy[j] = y[8 * c + j];
+        act_group<8, FAST>(yy, t, slot == 0 ? p.o0_act : p.o1_act);
+        uint32_t h[4], lw[4];
+        if (with_lo) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split_f32x2(t[2 * j], t[2 * j + 1], h[j], lw[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h[j] = f2h2_sat(t[2 * j], t[2 * j + 1]);
+        }
         const uint32_t a = row32 + ((((uint32_t)c) ^ sw32) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[4 * c]), "r"(h[4 * c + 1]),
-                     "r"(h[4 * c + 2]), "r"(h[4 * c + 3])
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
                      : "memory");
         if (with_lo)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 1024u), "r"(lw[4 * c]), "r"(lw[4 * c + 1]),
-                       "r"(lw[4 * c + 2]), "r"(lw[4 * c + 3])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 1024u), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]),
+                       "r"(lw[3])
                        : "memory");
       }
       fence_async_smem();
