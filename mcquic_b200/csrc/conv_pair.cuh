@@ -309,8 +309,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     const uint32_t stage = epi_base + (uint32_t)(warp - 2) * TC_EPI_STAGE_BYTES;
-    for (int it = 0; it < my_work; ++it) {
-      const int w = work_item(it);
+    // the loop carries (it, w) and two bounds, not the cluster's place in the schedule (my_ct, my_lane, cluster_id, ...):
+    // every value that stays live across the drain competes with it for the 96 registers
+    const int w_step = per_ct ? per_ct : num_clusters;
+    const int w_end = per_ct ? my_ct * hp.groups_m + hp.groups_m : total_work;
+    int w = work_item(0);
+    for (int it = 0; w < w_end; ++it, w += w_step) {
       int ct, x0, y0, n0;
       decode_tile(w, ct, x0, y0, n0);
       auto pix = [&](int row, int& n, int& oy, int& ox) {
@@ -324,9 +328,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       // L2 prefetch of the fp32 operands: this tile's on the first trip, from then on the NEXT tile's (a whole tile of lead)
       // (bulk-store launches prefetch nothing: measured no gain, profiles/r2_drain_ab.txt)
       if (DRAIN != DRAIN_TMA && it == 0) prefetch_epilogue_operands(p, bn, ct, cg, q, lane, pix);
-      if (DRAIN != DRAIN_TMA && it + 1 < my_work) {
+      if (DRAIN != DRAIN_TMA && w + w_step < w_end) {
         int ct2, x2, y2, n2;
-        decode_tile(work_item(it + 1), ct2, x2, y2, n2);
+        decode_tile(w + w_step, ct2, x2, y2, n2);
         prefetch_epilogue_operands(p, bn, ct2, cg, q, lane, [&](int row, int& n, int& oy, int& ox) {
           ox = x2 + (row & (HALO_TW - 1));
           oy = y2 + (row >> 3);
