@@ -37,6 +37,8 @@ BATCH, H, W = 64, 256, 256
 STRONG_TOTAL = 512                           # BASELINE configs[3]: qp=1 batch 512 sharded over the ranks
 ALG_GFLOP_PER_IMAGE = 89.44                  # encode 37.33 + decode 52.11 at 256x256
 METRIC = "encode+decode MPix/s at qp=1, batch 64x3x256x256"
+# one workload string for both arms (the driver pairs the `--impl reference` line with ours by metric and config)
+WORKLOAD = "qp=1 Compressor(128,1,[8192,2048,512]) encode+decode, batch 64x3x256x256 per GPU"
 
 
 def _peaks():
@@ -180,7 +182,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "qp=1 Compressor(128,1,[8192,2048,512]) encode+decode, 256x256 RGB, CPU PyTorch fp32",
+        "config": {"workload": WORKLOAD, "images_per_gpu": 64, "arm": "the reference's CPU PyTorch fp32 path on the host cores",
                    "sample": desc},
         "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -529,7 +531,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 split x3 (fp32-grade) encode / f16 x1 decode, f32 accumulate",
             "data": "synthetic",
-            "config": {"workload": "qp=1 Compressor(128,1,[8192,2048,512]) encode+decode, batch 64x3x256x256 per GPU",
+            "config": {"workload": WORKLOAD,
                        "images_per_gpu": BATCH, "l2": "256 MB flush before every timed step", "cuda_graphs": True,
                        "collective": "all_gather int32[10752] code histogram per step" if world > 1 else "none (1 GPU)"},
             "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": x_host_u8.numel(),
