@@ -304,3 +304,29 @@ def test_packing_cache_survives_reuse_of_a_module_id():
     assert eng._packed_for(reused).cin == 24
     pk2 = A._packs_for(reused, reused.weight, reused.bias)
     assert pk2 is not pk and pk2.fwd is None
+
+
+def test_reference_arm_of_the_bench_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle, on a bounded sample) runs without a GPU and
+    pairs with our arm: same metric, unit, direction and config.workload; ranks other than 0 print nothing"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    env = dict(os.environ, RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "MPix/s" and d["higher_is_better"] is True
+    assert d["config"]["workload"] == bench.WORKLOAD
+    assert d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, env=dict(os.environ, RANK="1"), timeout=600)
+    assert other.returncode == 0 and other.stdout.strip() == ""
