@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -106,7 +108,7 @@ int64_t encode_stream(const int64_t* sym, int m, int hw, int k, const uint32_t* 
 
 // returns 0, or -3 when the stream ends before m * hw symbols were decoded (truncated / header does not match the stream)
 int decode_stream(const uint32_t* r, const uint32_t* end, int m, int hw, int k, const uint32_t* cdfs,
-                  const uint16_t* luts, int64_t* out) {
+                  const uint16_t* const* luts, int64_t* out) {
   if (end - r < 2) return -3;
   uint64_t x = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
   Reader rd{r + 2, end};
@@ -114,7 +116,7 @@ int decode_stream(const uint32_t* r, const uint32_t* end, int m, int hw, int k, 
   const uint64_t mask = (1ull << kPrec) - 1;
   for (int mi = 0; mi < m; ++mi) {
     const uint32_t* cdf = cdfs + (size_t)mi * cdf_len;
-    const uint16_t* lut = luts + ((size_t)mi << kPrec);
+    const uint16_t* lut = luts[mi];
     for (int j = 0; j < hw; ++j) {
       const uint32_t cum = (uint32_t)(x & mask);
       const uint32_t s = lut[cum];
@@ -138,9 +140,52 @@ int decode_stream(const uint32_t* r, const uint32_t* end, int m, int hw, int k, 
   return 0;
 }
 
+// n_threads > 0: that many threads.  0 = automatic: as many as pay for their own start-up -- creating and joining a
+// std::thread costs 50-100 us, about what coding 4 k symbols takes, so a thread has to get kSymbolsPerThread of them
+// (measured on the `Validator.speed` shapes, 10 x 3 x 768 x 512: the three levels of a batch hold 20 k symbols;
+// one thread codes them in 0.46 ms, eight threads in 1.2 ms)
+constexpr int64_t kSymbolsPerThread = 16384;
+// cum_freq -> symbol table of one codebook (the reference scans the CDF linearly for every symbol).  Filling its 2^16
+// entries costs as much as decoding a few thousand symbols, and a model decodes with the same handful of CDFs call after
+// call: the tables are kept, keyed by the CDF's contents (a changed CDF -- frequency EMA update -- simply misses).
+struct Lut {
+  std::vector<uint32_t> cdf;
+  std::vector<uint16_t> table;
+};
+constexpr size_t kLutCacheEntries = 32;      // 32 x (k + 1 words + 128 KB)
+
+// nullptr: the CDF does not cover [0, 2^16) monotonically
+std::shared_ptr<const Lut> lut_for(const uint32_t* cdf, int k) {
+  static std::mutex mu;
+  static std::vector<std::shared_ptr<const Lut>> cache;
+  static size_t next = 0;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    for (const auto& e : cache)
+      if ((int)e->cdf.size() == k + 1 && std::memcmp(e->cdf.data(), cdf, sizeof(uint32_t) * (size_t)(k + 1)) == 0) return e;
+  }
+  if (cdf[0] != 0 || cdf[k] != (1u << kPrec)) return nullptr;     // the table must cover [0, 2^16) completely
+  auto lut = std::make_shared<Lut>();
+  lut->cdf.assign(cdf, cdf + k + 1);
+  lut->table.resize((size_t)1 << kPrec);
+  for (int s = 0; s < k; ++s) {
+    if (cdf[s + 1] < cdf[s] || cdf[s + 1] > (1u << kPrec)) return nullptr;
+    for (uint32_t c = cdf[s]; c < cdf[s + 1]; ++c) lut->table[c] = (uint16_t)s;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() < kLutCacheEntries) cache.push_back(lut);
+  else { cache[next] = lut; next = (next + 1) % kLutCacheEntries; }
+  return lut;
+}
+
 template <class F>
-void parallel_for(int n, int n_threads, F fn) {
-  int t = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+void parallel_for(int n, int n_threads, int64_t symbols_per_item, F fn) {
+  int t = n_threads;
+  if (t <= 0) {
+    t = (int)std::thread::hardware_concurrency();
+    const int64_t worth = (int64_t)n * symbols_per_item / kSymbolsPerThread;
+    if (worth < t) t = (int)worth;
+  }
   t = std::max(1, std::min(t, n));
   if (t == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
   std::vector<std::thread> pool;
@@ -191,7 +236,7 @@ int mcq_rans_encode_level(const int64_t* codes, int32_t n, int32_t m, int32_t hw
   if (!codes || !cdfs || !out || !out_sizes || n <= 0 || m <= 0 || hw <= 0 || k <= 0 || k > 65535) return -1;
   if (capacity % 4 != 0 || capacity < 16) return -1;
   std::vector<int> status(n, 0);
-  parallel_for(n, n_threads, [&](int i) {
+  parallel_for(n, n_threads, (int64_t)m * hw, [&](int i) {
     thread_local std::vector<Slot> slots;
     thread_local std::vector<uint32_t> words;
     const int64_t cap_words = capacity / 4;
@@ -208,21 +253,17 @@ int mcq_rans_encode_level(const int64_t* codes, int32_t n, int32_t m, int32_t hw
 int mcq_rans_decode_level(const uint8_t* in, const int32_t* in_sizes, int64_t stride, int32_t n, int32_t m, int32_t hw,
                           int32_t k, const uint32_t* cdfs, int64_t* codes_out, int32_t n_threads) {
   if (!in || !in_sizes || !cdfs || !codes_out || n <= 0 || m <= 0 || hw <= 0 || k <= 0 || k > 65535) return -1;
-  // cum_freq -> symbol tables (the reference scans the CDF linearly for every symbol)
-  std::vector<uint16_t> luts((size_t)m << kPrec);
+  std::vector<std::shared_ptr<const Lut>> held((size_t)m);     // keeps the tables alive while other calls recycle the cache
+  std::vector<const uint16_t*> luts((size_t)m);
   for (int mi = 0; mi < m; ++mi) {
-    const uint32_t* cdf = cdfs + (size_t)mi * (k + 1);
-    uint16_t* lut = luts.data() + ((size_t)mi << kPrec);
-    if (cdf[0] != 0 || cdf[k] != (1u << kPrec)) return -1;     // the table must cover [0, 2^16) completely
-    for (int s = 0; s < k; ++s) {
-      if (cdf[s + 1] < cdf[s] || cdf[s + 1] > (1u << kPrec)) return -1;
-      for (uint32_t c = cdf[s]; c < cdf[s + 1]; ++c) lut[c] = (uint16_t)s;
-    }
+    held[mi] = lut_for(cdfs + (size_t)mi * (k + 1), k);
+    if (!held[mi]) return -1;
+    luts[mi] = held[mi]->table.data();
   }
   for (int i = 0; i < n; ++i)
     if (in_sizes[i] < 8 || in_sizes[i] % 4 != 0 || in_sizes[i] > stride) return -2;
   std::vector<int> status((size_t)n, 0);
-  parallel_for(n, n_threads, [&](int i) {
+  parallel_for(n, n_threads, (int64_t)m * hw, [&](int i) {
     const size_t nwords = (size_t)in_sizes[i] / 4;
     std::vector<uint32_t> words(nwords, 0u);   // aligned copy
     std::memcpy(words.data(), in + (size_t)i * stride, (size_t)in_sizes[i]);
