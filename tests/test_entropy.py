@@ -189,3 +189,47 @@ def test_compress_decompress_api_and_bpp_known_answer():
         small._quantizer._entropyCoder.update(hist)
     after = sum(len(b) for img in small.compress(x)[1] for b in img)
     assert after <= before
+
+
+def test_decode_tables_are_cached_by_cdf_contents_and_threads_are_optional():
+    """the decoder keeps its cum_freq -> symbol tables across calls, keyed by the CDF's contents: more distinct CDFs than
+    the cache holds (32), a CDF that changes between two calls (frequency EMA update), and concurrent callers all decode
+    what was encoded; the automatic thread count (0) and explicit counts produce the same streams"""
+    import threading
+    rng = np.random.default_rng(7)
+    cases = []
+    for i in range(40):
+        k = int(rng.choice([17, 512, 2048]))
+        pmf = rng.random(k) ** 3 + 1e-4
+        cdf = entropy.pmf_to_quantized_cdf(pmf / pmf.sum())[None]
+        codes = torch.from_numpy(rng.integers(0, k, size=(3, 1, 5, 7)))
+        streams = entropy.encode_level(codes, cdf)
+        assert streams == entropy.encode_level(codes, cdf, threads=1) == entropy.encode_level(codes, cdf, threads=3)
+        cases.append((codes, cdf, streams))
+        assert torch.equal(entropy.decode_level(streams, 1, 5, 7, cdf), codes)
+    for codes, cdf, streams in cases:                      # the first eight have been evicted by now
+        assert torch.equal(entropy.decode_level(streams, 1, 5, 7, cdf, threads=2), codes)
+    # same buffer, new contents: must not hit the old table
+    codes, cdf, _ = cases[0]
+    k = cdf.shape[1] - 1
+    pmf = np.linspace(1.0, 2.0, k)
+    cdf[0] = entropy.pmf_to_quantized_cdf(pmf / pmf.sum())
+    assert torch.equal(entropy.decode_level(entropy.encode_level(codes, cdf), 1, 5, 7, cdf), codes)
+    # large level: the automatic mode starts threads; the result is the single-threaded one
+    big = torch.from_numpy(rng.integers(0, k, size=(6, 1, 96, 96)))
+    s0 = entropy.encode_level(big, cdf)
+    assert s0 == entropy.encode_level(big, cdf, threads=1)
+    assert torch.equal(entropy.decode_level(s0, 1, 96, 96, cdf), big)
+    errors = []
+
+    def worker(case):
+        try:
+            for _ in range(20):
+                assert torch.equal(entropy.decode_level(case[2], 1, 5, 7, case[1]), case[0])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker, args=(cases[i],)) for i in range(1, 9)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors
