@@ -28,7 +28,9 @@ int64_t mcq_rans_stream_capacity(int64_t count);
 
 /* Replaces RansEncoder.encodeWithIndexes (cpp_exts/rans_encoder.cpp:49-60 -> buffered_rans_encoder.cpp:104-196) for a
  * whole level at once.  codes: int64 [n, m, hw] (host); cdfs: uint32 [m, k + 1]; out: n slots of `capacity` bytes;
- * out_sizes[n] receives the stream lengths.  n_threads <= 0: one thread per hardware core.  Returns 0 or -1/-2. */
+ * out_sizes[n] receives the stream lengths.  n_threads <= 0: automatic -- up to one thread per
+ * hardware core and image, but only as many as get 16 Ki symbols each (a level smaller than that is coded by the caller's
+ * thread: starting a thread costs more than coding 4 k symbols); the streams do not depend on the thread count.  Returns 0 or -1/-2. */
 int mcq_rans_encode_level(const int64_t* codes, int32_t n, int32_t m, int32_t hw, int32_t k, const uint32_t* cdfs,
                           uint8_t* out, int64_t capacity, int32_t* out_sizes, int32_t n_threads);
 
