@@ -35,7 +35,7 @@ int mcq_rans_encode_level(const int64_t* codes, int32_t n, int32_t m, int32_t hw
                           uint8_t* out, int64_t capacity, int32_t* out_sizes, int32_t n_threads);
 
 /* Replaces RansDecoder.decodeWithIndexes (cpp_exts/rans_decoder.cpp:104-173); the per-symbol linear CDF search is a
- * 65536-entry lookup table per CDF.  in: n slots of `stride` bytes holding streams of in_sizes[i] bytes.
+ * 65536-entry lookup table per CDF (kept across calls, keyed by the CDF's contents; thread-safe).  in: n slots of `stride` bytes holding streams of in_sizes[i] bytes.
  * Returns 0; -1 bad argument / CDF table that does not cover [0, 2^16]; -2 stream length < 8, not a multiple of 4 or
  * > stride; -3 a stream ended before m * hw symbols were decoded (truncated stream, or a header that claims more symbols
  * than the stream holds) -- the decoder never reads past in_sizes[i] bytes of a stream. */
