@@ -56,13 +56,30 @@ def model_params_of(config: dict) -> dict:
         {"permutationRate": params["permutationRate"]} if "permutationRate" in params else {})
 
 
+def _load_checkpoint(path: pathlib.Path, trusted: bool) -> dict:
+    """A checkpoint is {"model": state_dict, "config": plain dict, "version": str}: tensors and plain containers, which
+    the restricted unpickler (`weights_only=True`) reads.  Only a path the USER named on the command line (`--local`,
+    upstream's "trusted source" warning) may fall back to the full unpickler; a path that comes out of a `.mcq` header
+    (detect_model_from_file) never does -- a crafted file must not be able to make the CLI execute a pickle."""
+    import pickle
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except pickle.UnpicklingError as e:
+        if not trusted:
+            raise RuntimeError(f"checkpoint {path} named by the file header holds objects other than tensors and plain "
+                               "containers; pass it with `--local` if you trust it") from e
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
 def load_model(qp: int, local: Optional[pathlib.Path], device, mse: bool, logger: logging.Logger,
-               synthetic: bool = False) -> Compressor:
+               synthetic: bool = False, trusted: bool = True) -> Compressor:
     """demo.py:137-163.  Checkpoint = {"model": state_dict, "config": dict, "version": "0.1.x"}."""
     if local is not None:
         warnings.warn(f"By passing `--local`, `-qp` arg will be ignored. Checkpoint from {local} will be loaded. "
                       "Please ensure you obtain this local model from a trusted source.")
-        ckpt = torch.load(local, map_location="cpu", weights_only=False)
+        ckpt = _load_checkpoint(local, trusted)
+        if not isinstance(ckpt, dict) or "model" not in ckpt or "config" not in ckpt:
+            raise RuntimeError(f"{local} is not a checkpoint {{model, config, version}}")
         logger.info("Use local model.")
         if "version" not in ckpt:
             raise RuntimeError("You are using a too old ckpt where `version` not in it.")
@@ -107,7 +124,7 @@ def detect_model_from_file(qp, local, mse, device, logger, source: File, synthet
     """demo.py:77-93: the header's qp field is a checkpoint path or `qp_N_target`."""
     path = pathlib.Path(source.FileHeader.qp)
     if path.exists() and path.is_file() and "mcquic" in path.suffix.lower():
-        return load_model(-1, path, device, False, logger)
+        return load_model(-1, path, device, False, logger, trusted=False)      # the path is the FILE's claim, not the user's
     parsed = parse_qp(source.FileHeader.qp)
     if parsed is not None and local is None:
         return load_model(parsed[0], None, device, parsed[1], logger, synthetic)

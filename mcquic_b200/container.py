@@ -17,6 +17,8 @@ from .entropy import CodeSize, FileHeader, ImageSize
 
 # the reference release this container / checkpoint layout is compatible with (mcquic/__init__.py:1)
 REFERENCE_VERSION = "0.1.40"
+MAX_LEVELS = 16          # sanity bounds of header fields read from a file
+MAX_SIDE = 1 << 16
 
 
 def _parse_version(v: str):
@@ -91,19 +93,28 @@ class File:
             extra = (set(d) - {"fileHeader", "contents"}) | (set(fh) - {"qp", "version", "codeSize", "imageSize"})
             if extra:
                 raise KeyError(f"unknown field(s) {sorted(extra)}")    # marshmallow: unknown = RAISE
-            version_check(str(fh["version"]))                          # FileHeader.__init__ (specification.py:108-113)
             header = FileHeader(version=str(fh["version"]), qp=str(fh["qp"]),
                                 codeSize=CodeSize(m=[int(v) for v in cs["m"]], heights=[int(v) for v in cs["heights"]],
                                                   widths=[int(v) for v in cs["widths"]], k=[int(v) for v in cs["k"]]),
                                 imageSize=ImageSize(height=int(im["height"]), width=int(im["width"]),
                                                     channel=int(im["channel"])))
             contents = [bytes(c) for c in d["contents"]]
-        except (KeyError, TypeError, msgpack.exceptions.ExtraData, msgpack.exceptions.FormatError,
+        except (KeyError, TypeError, ValueError, msgpack.exceptions.ExtraData, msgpack.exceptions.FormatError,
                 msgpack.exceptions.StackError) as e:
             raise ValueError(f"not a valid .mcq file: {e}") from e
+        version_check(header.version)                                  # FileHeader.__init__ (specification.py:108-113)
         for c in contents:
             if c == b"":
                 raise ValueError("not a valid .mcq file: empty stream")
+        # plausibility of the numbers everything downstream sizes buffers and crops with (the model-specific checks --
+        # m, k, level count against the loaded model -- happen in CodeFrequency.decompress)
+        cs, im = header.codeSize, header.imageSize
+        levels = len(cs.k)
+        if not (1 <= levels <= MAX_LEVELS and len(cs.m) == len(cs.heights) == len(cs.widths) == levels == len(contents)):
+            raise ValueError("not a valid .mcq file: codeSize lists and contents must have one entry per level")
+        if any(not 1 <= v <= MAX_SIDE for v in (im.height, im.width, *cs.heights, *cs.widths)) or \
+                any(not 1 <= v <= 65535 for v in (*cs.m, *cs.k)) or not 1 <= im.channel <= 4:
+            raise ValueError("not a valid .mcq file: implausible image / code size")
         return File(header, contents)
 
     @property

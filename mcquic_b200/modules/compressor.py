@@ -530,6 +530,9 @@ class BaseCompressor(nn.Module):
         restored = self.decode(codes)
         size = headers[0].ImageSize
         H, W = restored.shape[-2], restored.shape[-1]
+        if not (0 < size.height <= H and 0 < size.width <= W):      # the header comes from a file
+            raise RuntimeError(f"decompress: header image size {size.height} x {size.width} does not fit the {H} x {W} "
+                               "pixels its code maps decode to")
         top, left = (H - size.height) // 2, (W - size.width) // 2
         return restored[..., top:top + size.height, left:left + size.width]
 

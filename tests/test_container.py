@@ -125,6 +125,54 @@ def test_malformed_files_are_rejected():
         File(f.fileHeader, [b"ok", b""]).serialize()
 
 
+def test_header_numbers_from_a_file_are_bounded():
+    """everything downstream sizes buffers and crops with these fields: zero / negative / huge sizes, list lengths that do
+    not match the number of streams and non-integers are refused at the door (the model-specific checks follow in
+    CodeFrequency.decompress)"""
+    def broken(edit):
+        d = _file().to_dict()
+        edit(d)
+        with pytest.raises(ValueError, match="not a valid .mcq file"):
+            File.deserialize(msgpack.packb(d, use_bin_type=True))
+
+    broken(lambda d: d["fileHeader"]["imageSize"].update(height=0))
+    broken(lambda d: d["fileHeader"]["imageSize"].update(width=-256))
+    broken(lambda d: d["fileHeader"]["imageSize"].update(channel=0))
+    broken(lambda d: d["fileHeader"]["imageSize"].update(height=1 << 20))
+    broken(lambda d: d["fileHeader"]["imageSize"].update(height="tall"))
+    broken(lambda d: d["fileHeader"]["codeSize"].update(heights=[1 << 30] + list(d["fileHeader"]["codeSize"]["heights"])[1:]))
+    broken(lambda d: d["fileHeader"]["codeSize"].update(k=list(d["fileHeader"]["codeSize"]["k"]) + [512]))
+    broken(lambda d: d["fileHeader"]["codeSize"].update(m=[0] * len(d["fileHeader"]["codeSize"]["m"])))
+    broken(lambda d: d.update(contents=list(d["contents"]) + [b"x"]))
+    broken(lambda d: d["fileHeader"].update(codeSize={"m": [], "heights": [], "widths": [], "k": []}) or d.update(contents=[]))
+
+
+def test_a_checkpoint_path_from_a_file_header_is_never_unpickled(tmp_path):
+    """demo.py:77-93 lets the header's qp field name a local checkpoint; such a path is the file's claim, not the user's:
+    it goes through the restricted unpickler only (a plain {model, config, version} checkpoint loads, a pickle carrying
+    code does not run), while `--local` keeps upstream's trusted-source behaviour"""
+    import pickle
+
+    marker = tmp_path / "executed"
+
+    class Evil:
+        def __reduce__(self):
+            return (open, (str(marker), "w"))
+
+    bad = tmp_path / "bad.mcquic"
+    with open(bad, "wb") as fp:
+        pickle.dump({"model": Evil(), "config": {}, "version": "0.1.0"}, fp)
+    with pytest.raises(RuntimeError, match="named by the file header"):
+        cli._load_checkpoint(bad, trusted=False)
+    assert not marker.exists()
+    good = tmp_path / "good.mcquic"
+    torch.save({"model": {"w": torch.ones(2)}, "config": {"model": {"params": {"channel": 128, "m": 1, "k": [8]}}},
+                "version": "0.1.0"}, good)
+    ck = cli._load_checkpoint(good, trusted=False)
+    assert torch.equal(ck["model"]["w"], torch.ones(2)) and ck["version"] == "0.1.0"
+    assert cli._load_checkpoint(good, trusted=True)["config"]["model"]["params"]["k"] == [8]
+
+
 def test_version_check_follows_the_reference():
     assert REFERENCE_VERSION == "0.1.40"
     assert version_check("0.1.40") and version_check("0.1.0")
